@@ -1,0 +1,214 @@
+/*
+ * bh.h — C ABI of the B200-native Barnes-Hut step engine.
+ *
+ * Drop-in boundary for the hot path of bgcarmin/NBody-Barnes-Hut-CUDA:
+ *   void simulationStep()            nbody_v5_bench.cu:255-283 (nbody_v5.cu:298-325)
+ * The reference has no plugin/FFI interface; its de-facto boundary is that
+ * argument-less function working in place on 16 file-scope device pointers
+ * (nbody_v5_bench.cu:31-40).  Every entry point below names the reference
+ * lines it replaces.  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a positive cudaError_t value for
+ *     CUDA failures, or a negative BH_E_* code; nothing throws or exits.
+ *   - `stream` arguments are a cudaStream_t passed as void* (NULL = legacy
+ *     default stream, which is what the reference uses everywhere).
+ *   - one host thread per context; a context is bound to one device.
+ *   - body slot i is body i for the whole run at this boundary
+ *     (nbody_v5_bench.cu:31-40: the reference never permutes bodies); the
+ *     Morton-ordered internal layout is private to the context.
+ */
+#ifndef BH_H_
+#define BH_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BH_ABI_VERSION 1
+
+/* negative error codes (positive values are cudaError_t) */
+#define BH_E_INVAL      (-1)  /* bad argument                                  */
+#define BH_E_NOMEM      (-2)  /* host allocation failed                        */
+#define BH_E_STATE      (-3)  /* call order violated (e.g. step before import) */
+#define BH_E_UNSUPPORTED (-4) /* parameter combination not implemented         */
+#define BH_E_DEVICE     (-5)  /* a kernel raised its device-side error flag    */
+
+/* Simulation parameters — the reference's compile-time constants
+ * (nbody_v5_bench.cu:13-18) plus the tree-shape knobs it hard-codes.       */
+typedef struct bh_params {
+    float theta;      /* THETA      0.5f   nbody_v5_bench.cu:15 */
+    float G;          /* G_CONST    0.5f   nbody_v5_bench.cu:14 */
+    float dt;         /* DT         0.02f  nbody_v5_bench.cu:16 */
+    float softening;  /* SOFTENING  50.0f  nbody_v5_bench.cu:17 (added to r^2) */
+    float max_speed;  /* MAX_SPEED  500.0f nbody_v5_bench.cu:18 */
+    int   key_bits;   /* 30: 10 bits/axis Morton key, nbody_v5_bench.cu:58-61 */
+    int   leaf_cap;   /* 1: one body per leaf, as nbody_v5_bench.cu:100-104   */
+    int   flags;      /* BH_FLAG_* */
+} bh_params;
+
+#define BH_FLAG_NO_GRAPH    1  /* launch kernels directly instead of a CUDA graph  */
+#define BH_FLAG_PHASE_TIMER 2  /* record per-phase cudaEvents (implies NO_GRAPH)   */
+
+typedef struct bh_ctx bh_ctx;
+
+/* Fill *p with the reference defaults listed above. */
+void bh_default_params(bh_params* p);
+int  bh_abi_version(void);
+const char* bh_error_string(int code);
+
+/* Replaces the 16 cudaMalloc calls + H2D copies of main()
+ * (nbody_v5_bench.cu:311-335): allocates every buffer once for n_max bodies. */
+int  bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device);
+/* Replaces nbody_v5_bench.cu:372-387. */
+void bh_destroy(bh_ctx* ctx);
+
+/* Load the reference's SoA state (nbody_v5_bench.cu:32-35, 329-335).
+ * DEVICE pointers, caller-owned, not retained.  Body i keeps id i.        */
+int  bh_import_soa(bh_ctx* ctx,
+                   const float* px, const float* py, const float* pz,
+                   const float* vx, const float* vy, const float* vz,
+                   const float* mass, int64_t n, void* stream);
+/* Same, HOST pointers (pageable or pinned); copies through the context's
+ * pinned staging buffer.                                                  */
+int  bh_import_soa_host(bh_ctx* ctx,
+                        const float* px, const float* py, const float* pz,
+                        const float* vx, const float* vy, const float* vz,
+                        const float* mass, int64_t n);
+
+/* ≙ simulationStep() called nsteps times (nbody_v5_bench.cu:255-283, 357).
+ * Asynchronous on `stream`; no host synchronisation inside.               */
+int  bh_step(bh_ctx* ctx, int nsteps, void* stream);
+
+/* Read the state back in the reference layout and ORIGINAL body order
+ * (what display() reads after the step, nbody_v5.cu:335).  Any pointer may
+ * be NULL to skip that array.  ax/ay/az are the accelerations of the most
+ * recent step (d_accX.., nbody_v5_bench.cu:222-224).  DEVICE pointers.     */
+int  bh_export_soa(bh_ctx* ctx,
+                   float* px, float* py, float* pz,
+                   float* vx, float* vy, float* vz,
+                   float* ax, float* ay, float* az, void* stream);
+/* Same, HOST pointers; synchronises before returning.                     */
+int  bh_export_soa_host(bh_ctx* ctx,
+                        float* px, float* py, float* pz,
+                        float* vx, float* vy, float* vz,
+                        float* ax, float* ay, float* az);
+
+/* End-to-end convenience used by bench.py's `e2e` leg: host SoA in, nsteps
+ * steps, host SoA out (positions+velocities), all copies inside the call.  */
+int  bh_step_host(bh_ctx* ctx,
+                  float* px, float* py, float* pz,
+                  float* vx, float* vy, float* vz,
+                  const float* mass, int64_t n, int nsteps);
+
+/* Per-phase wall time of the LAST bh_step call when BH_FLAG_PHASE_TIMER is
+ * set — the phases README.md:56-60 promises and the bench never prints.   */
+enum {
+    BH_PHASE_KEYS = 0,   /* bounds + Morton keys   (bench:259-260)          */
+    BH_PHASE_SORT,       /* radix sort + reorder   (bench:262-264)          */
+    BH_PHASE_BUILD,      /* octree emission        (bench:266-275)          */
+    BH_PHASE_COM,        /* centre of mass         (bench:279-280)          */
+    BH_PHASE_FORCE,      /* traversal              (bench:281)              */
+    BH_PHASE_UPDATE,     /* kick-drift-clamp       (bench:282)              */
+    BH_PHASE_TOTAL,
+    BH_PHASE_COUNT
+};
+int  bh_phase_ms(bh_ctx* ctx, float out[BH_PHASE_COUNT]);
+
+/* Run ONE phase of the step on the context's current state (parity tests). */
+int  bh_run_phase(bh_ctx* ctx, int phase, void* stream);
+
+/* Debug getters/setters for the parity tests: copy an internal array to /
+ * from HOST memory (synchronous).  `bytes` must match the array size.     */
+enum {
+    BH_DBG_BOUNDS = 0,   /* float[6]   as d_bounds  (bench:149-154)         */
+    BH_DBG_KEYS,         /* u32[n]     Morton keys in CURRENT internal order;
+                            after BH_PHASE_SORT they are ascending          */
+    BH_DBG_PERM,         /* i32[n]     sort permutation: sorted slot -> slot
+                            before the sort (d_indices, bench:62,264)       */
+    BH_DBG_IDS,          /* i32[n]     internal slot -> original body id    */
+    BH_DBG_POSM,         /* float4[n]  x,y,z,mass  current state            */
+    BH_DBG_VEL,          /* float4[n]  vx,vy,vz,0  current state            */
+    BH_DBG_ACC,          /* float4[n]  ax,ay,az,0  sorted order of the last
+                            step (slot i pairs with *_SORTED slot i)        */
+    BH_DBG_CELL_META,    /* int4[cells]   first,count,level|bucket<<8,parent */
+    BH_DBG_CELL_COM,     /* float4[cells] comx,comy,comz,mass               */
+    BH_DBG_CELL_CHILD,   /* i32[cells*8]  child table                       */
+    BH_DBG_POSM_SORTED,  /* float4[n]  positions the last sort/force used
+                            (Morton order of THIS step, before the drift)   */
+    BH_DBG_VEL_SORTED,   /* float4[n]  matching velocities                  */
+    BH_DBG_IDS_SORTED,   /* i32[n]     matching original ids                */
+    BH_DBG_COUNT
+};
+int  bh_debug_get(bh_ctx* ctx, int what, void* dst, size_t bytes);
+int  bh_debug_set(bh_ctx* ctx, int what, const void* src, size_t bytes);
+
+/* Scalar statistics (synchronises). */
+enum {
+    BH_STAT_N = 0,
+    BH_STAT_CELLS,            /* cells emitted by the last build            */
+    BH_STAT_ROOT,             /* id of the root cell                        */
+    BH_STAT_INTERACTIONS_CELL,/* accepted (body,cell) pairs, last force     */
+    BH_STAT_INTERACTIONS_BODY,/* direct   (body,body) pairs, last force     */
+    BH_STAT_DEVICE_ERROR,     /* sticky device error flag (0 = none)        */
+    BH_STAT_STEPS,            /* steps taken since import                   */
+    BH_STAT_MAX_STACK,        /* deepest traversal stack seen, last force   */
+    BH_STAT_COUNT
+};
+int64_t bh_stat(bh_ctx* ctx, int which);
+
+/* child-table encoding (BH_DBG_CELL_CHILD) */
+#define BH_CHILD_EMPTY 0x7F7F7F7F
+#define BH_CHILD_IS_BODY(c) ((c) < 0)
+#define BH_CHILD_BODY(c)    ((c) & 0x7FFFFFFF)
+
+/* ---- multi-GPU: Morton-range slices (north_star) ------------
+ * Every rank holds the full state; a rank traverses and integrates only
+ * groups [first_body, first_body+count) of the freshly sorted order, then
+ * the ranks all-gather their updated slices (posm, vel, ids) in place.     */
+int  bh_set_slice(bh_ctx* ctx, int rank, int world);
+/* Device pointers to the CURRENT Morton-ordered state (float4 posm, float4
+ * vel, int32 ids) and this rank's slice [first, first+count).              */
+int  bh_state_ptrs(bh_ctx* ctx, void** posm, void** vel, void** ids,
+                   int64_t* n, int64_t* slice_first, int64_t* slice_count);
+
+/* ---- standalone pieces -------------------------------------------------- */
+/* Stable LSD radix sort of (u32 key, u32 value) pairs over bits
+ * [begin_bit,end_bit) — replaces thrust::sort_by_key (bench:262-264).
+ * DEVICE pointers.  tmp==NULL: writes the scratch size to *tmp_bytes.      */
+int  bh_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in,
+                       uint32_t* keys_out, uint32_t* vals_out, int64_t n,
+                       int begin_bit, int end_bit,
+                       void* tmp, size_t* tmp_bytes, void* stream);
+
+/* Double-precision O(N*k) direct sum on the GPU for a sample of k bodies of
+ * the context's state (accuracy reference; north_star "direct sum").
+ * sample = ORIGINAL body ids (host), acc_out = double[3*k] (host).         */
+int  bh_direct_sample(bh_ctx* ctx, const int32_t* sample, int k, double* acc_out);
+/* Total kinetic and (softened, pairwise) potential energy in double.       */
+int  bh_energy(bh_ctx* ctx, double* kinetic, double* potential);
+
+/* Initial conditions (host arrays, n floats each).
+ * refdisk: main()'s generator, nbody_v5_bench.cu:294-308, glibc rand().    */
+int  bh_ic_refdisk(int64_t n, unsigned seed,
+                   float* px, float* py, float* pz,
+                   float* vx, float* vy, float* vz, float* mass);
+int  bh_ic_uniform_cube(int64_t n, uint64_t seed, float half_edge,
+                        float* px, float* py, float* pz,
+                        float* vx, float* vy, float* vz, float* mass);
+int  bh_ic_plummer(int64_t n, uint64_t seed, float scale_a, float rcut_in_a,
+                   float body_mass, float G,
+                   float* px, float* py, float* pz,
+                   float* vx, float* vy, float* vz, float* mass);
+
+/* Box probes used as roofline denominators by bench.py. */
+int  bh_probe_fp32_tflops(int device, float* tflops);
+int  bh_probe_hbm_gbs(int device, float* gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BH_H_ */

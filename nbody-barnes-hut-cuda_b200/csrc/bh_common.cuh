@@ -1,0 +1,106 @@
+// bh_common.cuh — shared device helpers and the context layout of the Barnes-Hut engine.
+// Target: sm_100a (B200).  FP32 SIMT + integer work; no tensor cores on this path
+// (BASELINE.json north_star: traversal is not a dense contraction).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/bh.h"
+
+#define BH_KEY_BITS 30
+#define BH_MAX_LEVEL 10
+#define BH_GROUP 32          // bodies per traversal group (one warp)
+#define BH_NUM_SMS_FALLBACK 148
+
+// device error flag bits (BH_STAT_DEVICE_ERROR)
+#define BH_DERR_SORT_SPIN   1   // onesweep look-back exceeded its spin budget
+#define BH_DERR_STACK       2   // traversal stack guard tripped
+#define BH_DERR_LOOP        4   // traversal iteration guard tripped
+#define BH_DERR_TREE        8   // builder found an inconsistent range
+
+struct BhDevScalars {        // one small device struct, zeroed/filled by kernels
+    float bounds[6];         // as d_bounds (nbody_v5_bench.cu:149-154)
+    int   num_cells;         // total of the leader-flag scan
+    int   root;              // id of the parentless cell
+    unsigned int err;        // BH_DERR_* bits (sticky)
+    unsigned int group_ticket;   // dynamic group scheduler of the force kernel
+    unsigned long long inter_cell;
+    unsigned long long inter_body;
+    unsigned int max_stack;
+    unsigned int bbox_enc[6];    // order-preserving uint encoding of min/max during reduction
+    unsigned int pad;
+};
+
+// ---- small device helpers ---------------------------------------------------------------
+__device__ __forceinline__ unsigned int bh_lane() { return threadIdx.x & 31u; }
+
+// order-preserving float <-> uint map so atomicMin/atomicMax work on floats
+__device__ __forceinline__ unsigned int bh_f2ord(float f) {
+    unsigned int u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float bh_ord2f(unsigned int u) {
+    return __uint_as_float((u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u);
+}
+
+// number of leading 3-bit digits two 30-bit keys share (0..10); 10 <=> equal keys
+__device__ __forceinline__ int bh_shared_digits(uint32_t a, uint32_t b) {
+    uint32_t x = a ^ b;
+    return x == 0 ? BH_MAX_LEVEL : (__clz((int)x) - (32 - BH_KEY_BITS)) / 3;
+}
+
+__device__ __forceinline__ float4 bh_ldg4(const float4* p) { return __ldg(p); }
+
+#define BH_CUDA_TRY(expr)                                  \
+    do {                                                   \
+        cudaError_t _e = (expr);                           \
+        if (_e != cudaSuccess) return (int)_e;             \
+    } while (0)
+
+// ---- kernel launchers (one translation unit each) ---------------------------------------
+struct BhSortPlan {
+    int64_t n;
+    int num_tiles;
+    size_t hist_bytes;      // passes * 256 counters
+    size_t lookback_bytes;  // passes * tiles * 256 status words
+    size_t ticket_bytes;    // passes tickets
+    size_t total_bytes;
+};
+BhSortPlan bh_sort_plan(int64_t n);
+// Pass 0 reads (keys_src, vals_src) -> (p); then p -> q -> p ...; result in q iff the pass count
+// is even (*result_in_q).  keys_q may alias keys_src.  tmp holds histogram + look-back + tickets
+// (bh_sort_plan(n).total_bytes).  If vals_in_is_iota pass 0 generates value = index.
+int bh_sort_pairs_launch(const uint32_t* keys_src, const uint32_t* vals_src, uint32_t* keys_p, uint32_t* vals_p,
+                         uint32_t* keys_q, uint32_t* vals_q, int64_t n, int begin_bit, int end_bit, void* tmp,
+                         bool vals_in_is_iota, unsigned int* err_flag, int* result_in_q, cudaStream_t st);
+
+int bh_keys_launch(const float4* posm, int64_t n, BhDevScalars* sc, uint32_t* keys, cudaStream_t st);
+int bh_bounds_launch(const float4* posm, int64_t n, BhDevScalars* sc, cudaStream_t st);
+int bh_reorder_launch(const float4* posm_in, const float4* vel_in, const int32_t* ids_in,
+                      const uint32_t* perm, float4* posm_out, float4* vel_out, int32_t* ids_out,
+                      int64_t n, cudaStream_t st);
+int bh_tree_launch(const uint32_t* keys, int64_t n, int2* pair_info, int32_t* pair_scan,
+                   int32_t* scan_block_sums, int4* cell_meta, int32_t* cell_child,
+                   int32_t* cell_arrive, BhDevScalars* sc, cudaStream_t st);
+int bh_com_launch(const float4* posm, int64_t n, const int4* cell_meta, const int32_t* cell_child,
+                  int32_t* cell_arrive, float4* cell_mom, float4* cell_com,
+                  BhDevScalars* sc, cudaStream_t st);
+int bh_force_launch(const float4* posm, int64_t n, int64_t first_body, int64_t body_count,
+                    const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
+                    float4* acc, BhDevScalars* sc, float theta, float softening, float G,
+                    int num_sms, cudaStream_t st);
+int bh_force_prepare();
+int bh_integrate_launch(const float4* posm_s, const float4* vel_s, const int32_t* ids_s, const float4* acc,
+                        float4* posm, float4* vel, int32_t* ids, int64_t first_body, int64_t body_count,
+                        float dt, float max_speed, cudaStream_t st);
+int bh_import_launch(const float* px, const float* py, const float* pz, const float* vx,
+                     const float* vy, const float* vz, const float* m, int64_t n, float4* posm,
+                     float4* vel, int32_t* ids, cudaStream_t st);
+int bh_export_launch(const float4* posm, const float4* vel, const float4* acc, const int32_t* ids,
+                     int64_t n, float* px, float* py, float* pz, float* vx, float* vy, float* vz,
+                     float* ax, float* ay, float* az, cudaStream_t st);
+int bh_direct_launch(const float4* posm, int64_t n, const int32_t* sample_slots, int k,
+                     float softening, float G, double* acc_out, cudaStream_t st);
+int bh_energy_launch(const float4* posm, const float4* vel, int64_t n, float softening, float G,
+                     double* ke_pe /*2 doubles, zeroed by the launcher*/, cudaStream_t st);

@@ -1,0 +1,511 @@
+// bh_engine.cu — context, step driver and the C ABI (include/bh.h).
+//
+// The step driver replaces simulationStep()  nbody_v5_bench.cu:255-283:
+//   reference: bbox<<<1,1>>> -> keys -> thrust sort (alloc + sync) -> memset 2N nodes -> N/1024
+//              insert launches -> blocking 4-byte D2H -> COM atomics -> force -> integrate
+//   here:      bounds -> keys -> onesweep sort -> Morton reorder -> tree emission -> COM ->
+//              group traversal -> kick-drift-clamp; ~20 launches, no host sync, no allocation,
+//              replayed as one CUDA graph per step.
+//
+// State layout in HBM (DESIGN.md §"Data layout"):
+//   current state   posm[n] float4 {x,y,z,m}, vel[n] float4 {vx,vy,vz,0}, ids[n] int32
+//                   (Morton order of the last sort; ids = original body id of each slot)
+//   sorted scratch  posm_s, vel_s, ids_s — this step's Morton order, read by force + integrate
+//   acc[n] float4   accelerations, slot i pairs with posm_s[i]
+#include "bh_common.cuh"
+
+#include <cstddef>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+struct bh_ctx {
+    int device = 0;
+    int num_sms = BH_NUM_SMS_FALLBACK;
+    bh_params prm{};
+    int64_t n_max = 0, n_alloc = 0, n = 0;
+    int64_t steps = 0;
+    bool have_state = false, have_sorted = false;
+    // slice (multi-GPU Morton ranges); default = everything
+    int rank = 0, world = 1;
+    int64_t slice_first = 0, slice_count = 0;
+
+    float4 *posm = nullptr, *vel = nullptr, *posm_s = nullptr, *vel_s = nullptr, *acc = nullptr;
+    int32_t *ids = nullptr, *ids_s = nullptr;
+    uint32_t *keys0 = nullptr, *keys1 = nullptr, *vals0 = nullptr, *vals1 = nullptr;
+    void* sort_tmp = nullptr;
+    size_t sort_tmp_bytes = 0;
+    int2* pair_info = nullptr;
+    int32_t *pair_scan = nullptr, *tile_sums = nullptr;
+    int4* cell_meta = nullptr;
+    int32_t *cell_child = nullptr, *cell_arrive = nullptr;
+    float4 *cell_mom = nullptr, *cell_com = nullptr;
+    BhDevScalars* sc = nullptr;
+    float* stage = nullptr;  // 10 * n_alloc floats, lazily allocated for the host-pointer entry points
+    double* d_scratch = nullptr;
+
+    cudaGraphExec_t graph_exec = nullptr;
+    int64_t graph_n = -1, graph_first = -1, graph_count = -1;
+    cudaStream_t own_stream = nullptr;
+    cudaEvent_t ev[BH_PHASE_COUNT + 1] = {};
+    float phase_ms[BH_PHASE_COUNT] = {};
+};
+
+namespace {
+
+template <class T>
+cudaError_t dev_alloc(T** p, size_t count) {
+    return cudaMalloc((void**)p, count * sizeof(T) + 256);
+}
+
+void free_all(bh_ctx* c) {
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    for (auto& e : c->ev) if (e) cudaEventDestroy(e);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    void* ptrs[] = {c->posm, c->vel, c->posm_s, c->vel_s, c->acc, c->ids, c->ids_s, c->keys0, c->keys1, c->vals0,
+                    c->vals1, c->sort_tmp, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
+                    c->cell_arrive, c->cell_mom, c->cell_com, c->sc, c->stage, c->d_scratch};
+    for (void* p : ptrs) if (p) cudaFree(p);
+}
+
+void default_slice(bh_ctx* c) {
+    const int64_t groups = (c->n + BH_GROUP - 1) / BH_GROUP;
+    const int64_t per = (groups + c->world - 1) / c->world;
+    int64_t first = (int64_t)c->rank * per * BH_GROUP;
+    int64_t last = (int64_t)(c->rank + 1) * per * BH_GROUP;
+    if (first > c->n) first = c->n;
+    if (last > c->n) last = c->n;
+    c->slice_first = first;
+    c->slice_count = last - first;
+}
+
+// ---- the phases ---------------------------------------------------------------------------
+int phase_keys(bh_ctx* c, cudaStream_t st) {
+    int e = bh_bounds_launch(c->posm, c->n, c->sc, st);
+    if (e) return e;
+    return bh_keys_launch(c->posm, c->n, c->sc, c->keys0, st);
+}
+
+int phase_sort(bh_ctx* c, cudaStream_t st) {
+    int in_q = 0;
+    // pass 0 reads keys0 (+ implicit iota values) -> keys1/vals1 -> keys0/vals0 -> ...; 4 passes end in keys0/vals0
+    int e = bh_sort_pairs_launch(c->keys0, nullptr, c->keys1, c->vals1, c->keys0, c->vals0, c->n, 0, BH_KEY_BITS,
+                                 c->sort_tmp, true, (unsigned int*)((char*)c->sc + offsetof(BhDevScalars, err)), &in_q, st);
+    if (e) return e;
+    if (!in_q) return BH_E_UNSUPPORTED;  // 30 bits = 4 passes: always even
+    return bh_reorder_launch(c->posm, c->vel, c->ids, c->vals0, c->posm_s, c->vel_s, c->ids_s, c->n, st);
+}
+
+int phase_build(bh_ctx* c, cudaStream_t st) {
+    return bh_tree_launch(c->keys0, c->n, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
+                          c->cell_arrive, c->sc, st);
+}
+
+int phase_com(bh_ctx* c, cudaStream_t st) {
+    return bh_com_launch(c->posm_s, c->n, c->cell_meta, c->cell_child, c->cell_arrive, c->cell_mom, c->cell_com, c->sc, st);
+}
+
+int phase_force(bh_ctx* c, cudaStream_t st) {
+    return bh_force_launch(c->posm_s, c->n, c->slice_first, c->slice_count, c->cell_meta, c->cell_child, c->cell_com,
+                           c->acc, c->sc, c->prm.theta, c->prm.softening, c->prm.G, c->num_sms, st);
+}
+
+int phase_update(bh_ctx* c, cudaStream_t st) {
+    return bh_integrate_launch(c->posm_s, c->vel_s, c->ids_s, c->acc, c->posm, c->vel, c->ids, c->slice_first,
+                               c->slice_count, c->prm.dt, c->prm.max_speed, st);
+}
+
+typedef int (*phase_fn)(bh_ctx*, cudaStream_t);
+const phase_fn kPhases[BH_PHASE_TOTAL] = {phase_keys, phase_sort, phase_build, phase_com, phase_force, phase_update};
+
+int launch_all_phases(bh_ctx* c, cudaStream_t st) {
+    for (int p = 0; p < BH_PHASE_TOTAL; ++p) {
+        int e = kPhases[p](c, st);
+        if (e) return e;
+    }
+    return 0;
+}
+
+int ensure_graph(bh_ctx* c) {
+    if (c->graph_exec && c->graph_n == c->n && c->graph_first == c->slice_first && c->graph_count == c->slice_count)
+        return 0;
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    cudaGraph_t graph = nullptr;
+    BH_CUDA_TRY(cudaStreamBeginCapture(c->own_stream, cudaStreamCaptureModeThreadLocal));
+    int e = launch_all_phases(c, c->own_stream);
+    cudaError_t ce = cudaStreamEndCapture(c->own_stream, &graph);
+    if (e) { if (graph) cudaGraphDestroy(graph); return e; }
+    if (ce != cudaSuccess) return (int)ce;
+    ce = cudaGraphInstantiate(&c->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ce != cudaSuccess) return (int)ce;
+    c->graph_n = c->n; c->graph_first = c->slice_first; c->graph_count = c->slice_count;
+    return 0;
+}
+
+int ensure_stage(bh_ctx* c) {
+    if (c->stage) return 0;
+    return (int)dev_alloc(&c->stage, (size_t)10 * c->n_alloc);
+}
+
+}  // namespace
+
+extern "C" {
+
+void bh_default_params(bh_params* p) {
+    if (!p) return;
+    p->theta = 0.5f; p->G = 0.5f; p->dt = 0.02f; p->softening = 50.0f; p->max_speed = 500.0f;
+    p->key_bits = BH_KEY_BITS; p->leaf_cap = 1; p->flags = 0;
+}
+
+int bh_abi_version(void) { return BH_ABI_VERSION; }
+
+const char* bh_error_string(int code) {
+    switch (code) {
+        case 0: return "ok";
+        case BH_E_INVAL: return "invalid argument";
+        case BH_E_NOMEM: return "host allocation failed";
+        case BH_E_STATE: return "call order violated";
+        case BH_E_UNSUPPORTED: return "unsupported parameter combination";
+        case BH_E_DEVICE: return "device-side error flag raised";
+        default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
+    }
+}
+
+int bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device) {
+    if (!out || n_max <= 0 || n_max >= ((int64_t)1 << 30)) return BH_E_INVAL;
+    *out = nullptr;
+    bh_params prm;
+    if (params) prm = *params; else bh_default_params(&prm);
+    if (prm.key_bits != BH_KEY_BITS || prm.leaf_cap != 1) return BH_E_UNSUPPORTED;
+    if (!(prm.softening > 0.0f) || !(prm.theta >= 0.0f) || !(prm.max_speed > 0.0f)) return BH_E_INVAL;
+    BH_CUDA_TRY(cudaSetDevice(device));
+    { int e0 = bh_force_prepare(); if (e0) return e0; }
+    bh_ctx* c = new (std::nothrow) bh_ctx();
+    if (!c) return BH_E_NOMEM;
+    c->device = device; c->prm = prm; c->n_max = n_max;
+    c->n_alloc = ((n_max + 4095) / 4096 + 1) * 4096;  // room for slice padding in all-gathers
+    int sms = 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) c->num_sms = sms;
+    const size_t na = (size_t)c->n_alloc;
+    BhSortPlan plan = bh_sort_plan(c->n_alloc);
+    c->sort_tmp_bytes = plan.total_bytes;
+    cudaError_t e = cudaSuccess;
+#define TRYA(x) if (e == cudaSuccess) e = (x)
+    TRYA(dev_alloc(&c->posm, na)); TRYA(dev_alloc(&c->vel, na)); TRYA(dev_alloc(&c->posm_s, na));
+    TRYA(dev_alloc(&c->vel_s, na)); TRYA(dev_alloc(&c->acc, na)); TRYA(dev_alloc(&c->ids, na)); TRYA(dev_alloc(&c->ids_s, na));
+    TRYA(dev_alloc(&c->keys0, na)); TRYA(dev_alloc(&c->keys1, na)); TRYA(dev_alloc(&c->vals0, na)); TRYA(dev_alloc(&c->vals1, na));
+    TRYA(cudaMalloc(&c->sort_tmp, plan.total_bytes));
+    TRYA(dev_alloc(&c->pair_info, na)); TRYA(dev_alloc(&c->pair_scan, na)); TRYA(dev_alloc(&c->tile_sums, na / 2048 + 16));
+    TRYA(dev_alloc(&c->cell_meta, na)); TRYA(dev_alloc(&c->cell_child, na * 8)); TRYA(dev_alloc(&c->cell_arrive, na));
+    TRYA(dev_alloc(&c->cell_mom, na)); TRYA(dev_alloc(&c->cell_com, na));
+    TRYA(dev_alloc(&c->sc, 1)); TRYA(dev_alloc(&c->d_scratch, 8));
+    TRYA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    for (auto& ev : c->ev) TRYA(cudaEventCreate(&ev));
+#undef TRYA
+    if (e == cudaSuccess) e = cudaMemset(c->sc, 0, sizeof(BhDevScalars));
+    if (e == cudaSuccess) e = cudaMemset(c->acc, 0, na * sizeof(float4));
+    if (e != cudaSuccess) { free_all(c); delete c; return (int)e; }
+    *out = c;
+    return 0;
+}
+
+void bh_destroy(bh_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    free_all(c);
+    delete c;
+}
+
+int bh_import_soa(bh_ctx* c, const float* px, const float* py, const float* pz, const float* vx, const float* vy,
+                  const float* vz, const float* mass, int64_t n, void* stream) {
+    if (!c || !px || !py || !pz || !vx || !vy || !vz || !mass || n <= 0 || n > c->n_max) return BH_E_INVAL;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    c->n = n; c->steps = 0; c->have_sorted = false;
+    default_slice(c);
+    int e = bh_import_launch(px, py, pz, vx, vy, vz, mass, n, c->posm, c->vel, c->ids, (cudaStream_t)stream);
+    if (e) return e;
+    c->have_state = true;
+    return 0;
+}
+
+static int import_host_impl(bh_ctx* c, const float* px, const float* py, const float* pz, const float* vx, const float* vy,
+                            const float* vz, const float* mass, int64_t n, bool sync) {
+    if (!c || !px || !py || !pz || !vx || !vy || !vz || !mass || n <= 0 || n > c->n_max) return BH_E_INVAL;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    int e = ensure_stage(c);
+    if (e) return e;
+    const float* src[7] = {px, py, pz, vx, vy, vz, mass};
+    for (int k = 0; k < 7; ++k)
+        BH_CUDA_TRY(cudaMemcpyAsync(c->stage + (size_t)k * c->n_alloc, src[k], (size_t)n * 4, cudaMemcpyHostToDevice, c->own_stream));
+    float* s = c->stage;
+    const size_t na = (size_t)c->n_alloc;
+    e = bh_import_soa(c, s, s + na, s + 2 * na, s + 3 * na, s + 4 * na, s + 5 * na, s + 6 * na, n, c->own_stream);
+    if (e) return e;
+    // own_stream does not order against the caller's streams: finish before returning
+    if (sync) BH_CUDA_TRY(cudaStreamSynchronize(c->own_stream));
+    return 0;
+}
+
+int bh_import_soa_host(bh_ctx* c, const float* px, const float* py, const float* pz, const float* vx, const float* vy,
+                       const float* vz, const float* mass, int64_t n) {
+    return import_host_impl(c, px, py, pz, vx, vy, vz, mass, n, true);
+}
+
+int bh_set_slice(bh_ctx* c, int rank, int world) {
+    if (!c || world < 1 || rank < 0 || rank >= world) return BH_E_INVAL;
+    c->rank = rank; c->world = world;
+    if (c->have_state) default_slice(c);
+    return 0;
+}
+
+int bh_state_ptrs(bh_ctx* c, void** posm, void** vel, void** ids, int64_t* n, int64_t* slice_first, int64_t* slice_count) {
+    if (!c) return BH_E_INVAL;
+    if (posm) *posm = c->posm;
+    if (vel) *vel = c->vel;
+    if (ids) *ids = c->ids;
+    if (n) *n = c->n;
+    if (slice_first) *slice_first = c->slice_first;
+    if (slice_count) *slice_count = c->slice_count;
+    return 0;
+}
+
+int bh_step(bh_ctx* c, int nsteps, void* stream) {
+    if (!c || nsteps < 0) return BH_E_INVAL;
+    if (!c->have_state) return BH_E_STATE;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const bool timer = (c->prm.flags & BH_FLAG_PHASE_TIMER) != 0;
+    const bool direct = timer || (c->prm.flags & BH_FLAG_NO_GRAPH) != 0;
+    if (timer) memset(c->phase_ms, 0, sizeof(c->phase_ms));
+    if (!direct) {
+        int e = ensure_graph(c);
+        if (e) return e;
+    }
+    for (int s = 0; s < nsteps; ++s) {
+        if (!direct) {
+            BH_CUDA_TRY(cudaGraphLaunch(c->graph_exec, st));
+        } else if (!timer) {
+            int e = launch_all_phases(c, st);
+            if (e) return e;
+        } else {
+            for (int p = 0; p < BH_PHASE_TOTAL; ++p) {
+                BH_CUDA_TRY(cudaEventRecord(c->ev[p], st));
+                int e = kPhases[p](c, st);
+                if (e) return e;
+            }
+            BH_CUDA_TRY(cudaEventRecord(c->ev[BH_PHASE_TOTAL], st));
+            BH_CUDA_TRY(cudaEventSynchronize(c->ev[BH_PHASE_TOTAL]));
+            for (int p = 0; p < BH_PHASE_TOTAL; ++p) {
+                float ms = 0.f;
+                cudaEventElapsedTime(&ms, c->ev[p], c->ev[p + 1]);
+                c->phase_ms[p] += ms;
+                c->phase_ms[BH_PHASE_TOTAL] += ms;
+            }
+        }
+    }
+    if (nsteps > 0) { c->steps += nsteps; c->have_sorted = true; }
+    return 0;
+}
+
+int bh_run_phase(bh_ctx* c, int phase, void* stream) {
+    if (!c || phase < 0 || phase >= BH_PHASE_TOTAL) return BH_E_INVAL;
+    if (!c->have_state) return BH_E_STATE;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    int e = kPhases[phase](c, (cudaStream_t)stream);
+    if (e) return e;
+    if (phase >= BH_PHASE_SORT) c->have_sorted = true;
+    return 0;
+}
+
+int bh_phase_ms(bh_ctx* c, float out[BH_PHASE_COUNT]) {
+    if (!c || !out) return BH_E_INVAL;
+    memcpy(out, c->phase_ms, sizeof(c->phase_ms));
+    return 0;
+}
+
+int bh_export_soa(bh_ctx* c, float* px, float* py, float* pz, float* vx, float* vy, float* vz, float* ax, float* ay,
+                  float* az, void* stream) {
+    if (!c) return BH_E_INVAL;
+    if (!c->have_state) return BH_E_STATE;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    return bh_export_launch(c->posm, c->vel, c->acc, c->ids, c->n, px, py, pz, vx, vy, vz, ax, ay, az, (cudaStream_t)stream);
+}
+
+int bh_export_soa_host(bh_ctx* c, float* px, float* py, float* pz, float* vx, float* vy, float* vz, float* ax,
+                       float* ay, float* az) {
+    if (!c) return BH_E_INVAL;
+    if (!c->have_state) return BH_E_STATE;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    int e = ensure_stage(c);
+    if (e) return e;
+    float* dst[9] = {px, py, pz, vx, vy, vz, ax, ay, az};
+    float* dev[9];
+    const size_t na = (size_t)c->n_alloc;
+    for (int k = 0; k < 9; ++k) dev[k] = dst[k] ? c->stage + (size_t)k * na : nullptr;
+    // order the export after whatever the caller queued on the legacy stream / our stream
+    BH_CUDA_TRY(cudaDeviceSynchronize());
+    e = bh_export_launch(c->posm, c->vel, c->acc, c->ids, c->n, dev[0], dev[1], dev[2], dev[3], dev[4], dev[5], dev[6],
+                         dev[7], dev[8], c->own_stream);
+    if (e) return e;
+    for (int k = 0; k < 9; ++k)
+        if (dst[k]) BH_CUDA_TRY(cudaMemcpyAsync(dst[k], dev[k], (size_t)c->n * 4, cudaMemcpyDeviceToHost, c->own_stream));
+    BH_CUDA_TRY(cudaStreamSynchronize(c->own_stream));
+    return 0;
+}
+
+int bh_step_host(bh_ctx* c, float* px, float* py, float* pz, float* vx, float* vy, float* vz, const float* mass,
+                 int64_t n, int nsteps) {
+    int e = import_host_impl(c, px, py, pz, vx, vy, vz, mass, n, false);
+    if (e) return e;
+    e = bh_step(c, nsteps, c->own_stream);
+    if (e) return e;
+    // export on the same stream: no device-wide sync needed
+    e = ensure_stage(c);
+    if (e) return e;
+    const size_t na = (size_t)c->n_alloc;
+    float* s = c->stage;
+    e = bh_export_launch(c->posm, c->vel, c->acc, c->ids, c->n, s, s + na, s + 2 * na, s + 3 * na, s + 4 * na, s + 5 * na,
+                         nullptr, nullptr, nullptr, c->own_stream);
+    if (e) return e;
+    float* dst[6] = {px, py, pz, vx, vy, vz};
+    for (int k = 0; k < 6; ++k)
+        BH_CUDA_TRY(cudaMemcpyAsync(dst[k], s + (size_t)k * na, (size_t)n * 4, cudaMemcpyDeviceToHost, c->own_stream));
+    BH_CUDA_TRY(cudaStreamSynchronize(c->own_stream));
+    return 0;
+}
+
+static int dbg_locate(bh_ctx* c, int what, void** ptr, size_t* bytes) {
+    BhDevScalars h;
+    int M = 0;
+    if (what == BH_DBG_CELL_META || what == BH_DBG_CELL_COM || what == BH_DBG_CELL_CHILD) {
+        BH_CUDA_TRY(cudaMemcpy(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost));
+        M = h.num_cells;
+    }
+    const size_t n = (size_t)c->n;
+    switch (what) {
+        case BH_DBG_BOUNDS: *ptr = (char*)c->sc + offsetof(BhDevScalars, bounds); *bytes = 24; break;
+        case BH_DBG_KEYS: *ptr = c->keys0; *bytes = n * 4; break;
+        case BH_DBG_PERM: *ptr = c->vals0; *bytes = n * 4; break;
+        case BH_DBG_IDS: *ptr = c->ids; *bytes = n * 4; break;
+        case BH_DBG_POSM: *ptr = c->posm; *bytes = n * 16; break;
+        case BH_DBG_VEL: *ptr = c->vel; *bytes = n * 16; break;
+        case BH_DBG_ACC: *ptr = c->acc; *bytes = n * 16; break;
+        case BH_DBG_CELL_META: *ptr = c->cell_meta; *bytes = (size_t)M * 16; break;
+        case BH_DBG_CELL_COM: *ptr = c->cell_com; *bytes = (size_t)M * 16; break;
+        case BH_DBG_CELL_CHILD: *ptr = c->cell_child; *bytes = (size_t)M * 32; break;
+        case BH_DBG_POSM_SORTED: *ptr = c->posm_s; *bytes = n * 16; break;
+        case BH_DBG_VEL_SORTED: *ptr = c->vel_s; *bytes = n * 16; break;
+        case BH_DBG_IDS_SORTED: *ptr = c->ids_s; *bytes = n * 4; break;
+        default: return BH_E_INVAL;
+    }
+    return 0;
+}
+
+int bh_debug_get(bh_ctx* c, int what, void* dst, size_t bytes) {
+    if (!c || !dst) return BH_E_INVAL;
+    if (!c->have_state) return BH_E_STATE;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    BH_CUDA_TRY(cudaDeviceSynchronize());
+    void* p = nullptr; size_t want = 0;
+    int e = dbg_locate(c, what, &p, &want);
+    if (e) return e;
+    if (bytes != want) return BH_E_INVAL;
+    if (bytes == 0) return 0;
+    return (int)cudaMemcpy(dst, p, bytes, cudaMemcpyDeviceToHost);
+}
+
+int bh_debug_set(bh_ctx* c, int what, const void* src, size_t bytes) {
+    if (!c || !src) return BH_E_INVAL;
+    if (!c->have_state) return BH_E_STATE;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    BH_CUDA_TRY(cudaDeviceSynchronize());
+    void* p = nullptr; size_t want = 0;
+    int e = dbg_locate(c, what, &p, &want);
+    if (e) return e;
+    if (bytes != want) return BH_E_INVAL;
+    if (bytes == 0) return 0;
+    return (int)cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice);
+}
+
+int64_t bh_stat(bh_ctx* c, int which) {
+    if (!c) return BH_E_INVAL;
+    if (which == BH_STAT_N) return c->n;
+    if (which == BH_STAT_STEPS) return c->steps;
+    if (cudaSetDevice(c->device) != cudaSuccess) return BH_E_INVAL;
+    if (cudaDeviceSynchronize() != cudaSuccess) return BH_E_DEVICE;
+    BhDevScalars h;
+    if (cudaMemcpy(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost) != cudaSuccess) return BH_E_DEVICE;
+    switch (which) {
+        case BH_STAT_CELLS: return h.num_cells;
+        case BH_STAT_ROOT: return h.root;
+        case BH_STAT_INTERACTIONS_CELL: return (int64_t)h.inter_cell;
+        case BH_STAT_INTERACTIONS_BODY: return (int64_t)h.inter_body;
+        case BH_STAT_DEVICE_ERROR: return h.err;
+        case BH_STAT_MAX_STACK: return h.max_stack;
+        default: return BH_E_INVAL;
+    }
+}
+
+int bh_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t* keys_out, uint32_t* vals_out,
+                      int64_t n, int begin_bit, int end_bit, void* tmp, size_t* tmp_bytes, void* stream) {
+    if (!tmp_bytes || n < 0) return BH_E_INVAL;
+    BhSortPlan plan = bh_sort_plan(n);
+    const size_t arr = ((size_t)n * 4 + 255) / 256 * 256;
+    const size_t plan_bytes = (plan.total_bytes + 255) / 256 * 256;
+    const size_t need = plan_bytes + 2 * arr + 256;
+    if (!tmp) { *tmp_bytes = need; return 0; }
+    if (*tmp_bytes < need || !keys_in || !vals_in || !keys_out || !vals_out) return BH_E_INVAL;
+    char* base = (char*)tmp;
+    uint32_t* tk = (uint32_t*)(base + plan_bytes);
+    uint32_t* tv = (uint32_t*)(base + plan_bytes + arr);
+    unsigned int* err = (unsigned int*)(base + plan_bytes + 2 * arr);
+    BH_CUDA_TRY(cudaMemsetAsync(err, 0, 4, (cudaStream_t)stream));
+    const int passes = (end_bit - begin_bit + 7) / 8;
+    int in_q = 0;
+    // make the final pass land in (keys_out, vals_out)
+    if (passes & 1)
+        return bh_sort_pairs_launch(keys_in, vals_in, keys_out, vals_out, tk, tv, n, begin_bit, end_bit, tmp, false, err, &in_q, (cudaStream_t)stream);
+    return bh_sort_pairs_launch(keys_in, vals_in, tk, tv, keys_out, vals_out, n, begin_bit, end_bit, tmp, false, err, &in_q, (cudaStream_t)stream);
+}
+
+int bh_direct_sample(bh_ctx* c, const int32_t* sample, int k, double* acc_out) {
+    if (!c || !sample || !acc_out || k <= 0) return BH_E_INVAL;
+    if (!c->have_state || !c->have_sorted) return BH_E_STATE;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    BH_CUDA_TRY(cudaDeviceSynchronize());
+    std::vector<int32_t> ids((size_t)c->n), inv((size_t)c->n, -1), slots((size_t)k);
+    BH_CUDA_TRY(cudaMemcpy(ids.data(), c->ids_s, (size_t)c->n * 4, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < c->n; ++i)
+        if (ids[i] >= 0 && ids[i] < c->n) inv[ids[i]] = (int32_t)i;
+    for (int s = 0; s < k; ++s) {
+        if (sample[s] < 0 || sample[s] >= c->n || inv[sample[s]] < 0) return BH_E_INVAL;
+        slots[s] = inv[sample[s]];
+    }
+    int32_t* d_slots = nullptr; double* d_out = nullptr;
+    BH_CUDA_TRY(cudaMalloc(&d_slots, (size_t)k * 4));
+    if (cudaMalloc(&d_out, (size_t)k * 24) != cudaSuccess) { cudaFree(d_slots); return (int)cudaErrorMemoryAllocation; }
+    cudaMemcpy(d_slots, slots.data(), (size_t)k * 4, cudaMemcpyHostToDevice);
+    int e = bh_direct_launch(c->posm_s, c->n, d_slots, k, c->prm.softening, c->prm.G, d_out, 0);
+    cudaError_t ce = cudaMemcpy(acc_out, d_out, (size_t)k * 24, cudaMemcpyDeviceToHost);
+    cudaFree(d_slots); cudaFree(d_out);
+    return e ? e : (int)ce;
+}
+
+int bh_energy(bh_ctx* c, double* kinetic, double* potential) {
+    if (!c || !kinetic || !potential) return BH_E_INVAL;
+    if (!c->have_state) return BH_E_STATE;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    BH_CUDA_TRY(cudaDeviceSynchronize());
+    int e = bh_energy_launch(c->posm, c->vel, c->n, c->prm.softening, c->prm.G, c->d_scratch, 0);
+    if (e) return e;
+    double h[2];
+    BH_CUDA_TRY(cudaMemcpy(h, c->d_scratch, 16, cudaMemcpyDeviceToHost));
+    *kinetic = h[0]; *potential = h[1];
+    return 0;
+}
+
+}  // extern "C"

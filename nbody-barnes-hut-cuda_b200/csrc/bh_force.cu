@@ -1,0 +1,296 @@
+// bh_force.cu — warp-cooperative Barnes-Hut traversal.
+//
+// Replaces computeForceKernel  nbody_v5_bench.cu:191-225  (one thread per body, private
+// int stack[64], 76-byte AoS nodes).
+//
+// One warp owns a GROUP of 32 Morton-consecutive bodies (one body per lane).  The warp keeps
+// ONE traversal stack in shared memory and pops up to 32 cells at a time, one per lane:
+//   - every lane tests its cell against the group's bounding box (exact AABB of the 32
+//     positions): accept iff  w_L^2 < theta^2 * (d^2 + SOFTENING), d = distance from the cell's
+//     centre of mass to the box.  This is bench:207-208 (`width / sqrtf(d2 + SOFTENING) < THETA`)
+//     squared and evaluated at the closest point of the group, so the decision is uniform for
+//     the warp and every body of the group would also have accepted under the reference test;
+//   - __ballot_sync/__popc compact accepted cells into a shared interaction list, opened cells
+//     push their child cells back on the stack and their loose bodies on a direct list (warp
+//     prefix sums over __shfl_up_sync); identical-key buckets append their body range;
+//   - whenever a list holds 32 entries the warp evaluates a 32x32 tile: each lane keeps its own
+//     body in registers and reads the 32 sources as shared-memory broadcasts (LDS.128), doing
+//     bench:205-213's arithmetic with rsqrtf.
+// The tree (32-byte records + 32-byte child tables) and the positions stay L2-resident at
+// 1M bodies; shared memory holds only per-warp traversal state.
+#include "bh_common.cuh"
+
+namespace {
+
+constexpr int FORCE_WARPS = 4;
+constexpr int FORCE_THREADS = FORCE_WARPS * 32;
+constexpr int STACK_CAP = 1024;
+constexpr int STACK_RESERVE = 384;   // >= 224 (one wide pop/push) + 7 * deepest level, see DESIGN.md
+constexpr int ALIST_CAP = 64;
+constexpr int DLIST_CAP = 352;
+constexpr unsigned LOOP_GUARD = 1u << 24;
+
+struct __align__(16) WarpScratch {
+    float4 alist[ALIST_CAP];   // accepted cells: com.xyz, mass
+    float4 tile[32];           // gathered bodies for one direct tile
+    int stack[STACK_CAP];
+    int dlist[DLIST_CAP];      // body slots awaiting direct evaluation
+};
+
+// 32 sources against this lane's body.  bench:205-213 with dist^-3 from one rsqrt.
+__device__ __forceinline__ void eval_tile(const float4* __restrict__ src, float px, float py, float pz,
+                                          float soft, float& ax, float& ay, float& az) {
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) {
+        const float4 s = src[k];  // same address in every lane: shared-memory broadcast
+        const float dx = s.x - px, dy = s.y - py, dz = s.z - pz;
+        const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, soft)));
+        const float rinv = rsqrtf(r2);
+        const float f = (s.w * rinv) * (rinv * rinv);
+        ax = fmaf(f, dx, ax);
+        ay = fmaf(f, dy, ay);
+        az = fmaf(f, dz, az);
+    }
+}
+
+__global__ void __launch_bounds__(FORCE_THREADS) force_kernel(const float4* __restrict__ posm, int64_t first_body,
+                                                             int64_t body_count, const int4* __restrict__ cell_meta,
+                                                             const int32_t* __restrict__ cell_child,
+                                                             const float4* __restrict__ cell_com,
+                                                             float4* __restrict__ acc, BhDevScalars* sc, float theta,
+                                                             float soft, float G) {
+    __shared__ WarpScratch s_warp[FORCE_WARPS];
+    __shared__ float s_w2[BH_MAX_LEVEL + 1];
+
+    if (threadIdx.x <= BH_MAX_LEVEL) {
+        const float root_w = __fsub_rn(sc->bounds[3], sc->bounds[0]);   // bench:208 maxX - minX of the root
+        const float w = ldexpf(root_w, -(int)threadIdx.x);              // exact halving per level
+        s_w2[threadIdx.x] = __fmul_rn(w, w);
+    }
+    __syncthreads();
+
+    const int lane = bh_lane();
+    const unsigned lt_mask = (1u << lane) - 1u;
+    WarpScratch& W = s_warp[threadIdx.x >> 5];
+    const float theta2 = __fmul_rn(theta, theta);
+    const int root = sc->root;
+    const int4* child4 = reinterpret_cast<const int4*>(cell_child);
+    const int64_t ngroups = (body_count + BH_GROUP - 1) / BH_GROUP;
+    const int64_t end_body = first_body + body_count;
+
+    unsigned long long tot_cell = 0, tot_body = 0;
+    unsigned max_sp = 0;
+
+    for (;;) {
+        unsigned g = 0;
+        if (lane == 0) g = atomicAdd(&sc->group_ticket, 1u);
+        g = __shfl_sync(0xffffffffu, g, 0);
+        if ((int64_t)g >= ngroups) break;
+
+        const int64_t my = first_body + (int64_t)g * BH_GROUP + lane;
+        const bool valid = my < end_body;
+        const int nb = (int)min((int64_t)BH_GROUP, end_body - (first_body + (int64_t)g * BH_GROUP));
+        const float4 me = __ldg(posm + (valid ? my : end_body - 1));
+
+        // exact AABB of the group
+        float lox = me.x, loy = me.y, loz = me.z, hix = me.x, hiy = me.y, hiz = me.z;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o));
+            loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o));
+            loz = fminf(loz, __shfl_xor_sync(0xffffffffu, loz, o));
+            hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
+            hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
+            hiz = fmaxf(hiz, __shfl_xor_sync(0xffffffffu, hiz, o));
+        }
+        const float cx = __fmul_rn(__fadd_rn(lox, hix), 0.5f), hx = __fmul_rn(__fsub_rn(hix, lox), 0.5f);
+        const float cy = __fmul_rn(__fadd_rn(loy, hiy), 0.5f), hy = __fmul_rn(__fsub_rn(hiy, loy), 0.5f);
+        const float cz = __fmul_rn(__fadd_rn(loz, hiz), 0.5f), hz = __fmul_rn(__fsub_rn(hiz, loz), 0.5f);
+
+        float ax = 0.f, ay = 0.f, az = 0.f;
+        int sp = 0, na = 0, nd = 0;
+        unsigned acc_cells = 0, dir_bodies = 0;
+        if (root >= 0) {
+            if (lane == 0) W.stack[0] = root;
+            sp = 1;
+        }
+        __syncwarp();
+
+        unsigned guard = 0;
+        while (sp > 0) {
+            if (++guard > LOOP_GUARD) { if (lane == 0) atomicOr(&sc->err, BH_DERR_LOOP); break; }
+            // wide pop while a full push still fits, single pop (plain DFS) otherwise
+            const int take = (sp <= STACK_CAP - STACK_RESERVE) ? min(sp, 32) : 1;
+            const bool mine = lane < take;
+            const int cell = mine ? W.stack[sp - 1 - lane] : 0;
+            sp -= take;
+            __syncwarp();
+
+            float4 cm = make_float4(0.f, 0.f, 0.f, 0.f);
+            int4 mt = make_int4(0, 0, 0, 0);
+            bool accept = false, bucket = false;
+            if (mine) {
+                cm = __ldg(cell_com + cell);
+                mt = __ldg(cell_meta + cell);
+                bucket = (mt.z >> 8) & 1;
+                const float dx = fmaxf(0.0f, __fsub_rn(fabsf(__fsub_rn(cm.x, cx)), hx));
+                const float dy = fmaxf(0.0f, __fsub_rn(fabsf(__fsub_rn(cm.y, cy)), hy));
+                const float dz = fmaxf(0.0f, __fsub_rn(fabsf(__fsub_rn(cm.z, cz)), hz));
+                const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+                accept = s_w2[mt.z & 0xFF] < __fmul_rn(theta2, __fadd_rn(d2, soft));
+            }
+
+            // ---- accepted cells -> interaction list ----
+            const unsigned am = __ballot_sync(0xffffffffu, mine && accept);
+            if (mine && accept) W.alist[na + __popc(am & lt_mask)] = cm;
+            na += __popc(am);
+            acc_cells += __popc(am);
+            __syncwarp();
+            if (na >= 32) {
+                na -= 32;
+                eval_tile(W.alist + na, me.x, me.y, me.z, soft, ax, ay, az);
+                __syncwarp();
+            }
+
+            // ---- opened internal cells: child cells -> stack, loose bodies -> direct list ----
+            const bool open = mine && !accept && !bucket;
+            int e[8];
+            int packed = 0;  // child cells in the low half, bodies in the high half
+            if (open) {
+                const int4 lo = __ldg(child4 + 2 * cell), hi = __ldg(child4 + 2 * cell + 1);
+                e[0] = lo.x; e[1] = lo.y; e[2] = lo.z; e[3] = lo.w;
+                e[4] = hi.x; e[5] = hi.y; e[6] = hi.z; e[7] = hi.w;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (e[q] < 0) packed += 1 << 16;
+                    else if (e[q] != BH_CHILD_EMPTY) packed += 1;
+                }
+            }
+            int incl = packed;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            if (open) {
+                int so = sp + ((incl - packed) & 0xFFFF);
+                int dof = nd + ((incl - packed) >> 16);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    if (e[q] < 0) W.dlist[dof++] = e[q] & 0x7FFFFFFF;
+                    else if (e[q] != BH_CHILD_EMPTY) W.stack[so++] = e[q];
+                }
+            }
+            sp += total & 0xFFFF;
+            nd += total >> 16;
+            dir_bodies += total >> 16;
+            max_sp = max(max_sp, (unsigned)sp);
+            __syncwarp();
+
+            // ---- direct list: full tiles ----
+            while (nd >= 32) {
+                nd -= 32;
+                W.tile[lane] = __ldg(posm + W.dlist[nd + lane]);
+                __syncwarp();
+                eval_tile(W.tile, me.x, me.y, me.z, soft, ax, ay, az);
+                __syncwarp();
+            }
+
+            // ---- rejected buckets: their bodies are a contiguous range ----
+            unsigned bm = __ballot_sync(0xffffffffu, mine && !accept && bucket);
+            while (bm) {
+                const int src = __ffs(bm) - 1;
+                bm &= bm - 1;
+                const int bfirst = __shfl_sync(0xffffffffu, mt.x, src);
+                const int bcount = __shfl_sync(0xffffffffu, mt.y, src);
+                dir_bodies += bcount;
+                for (int b = 0; b < bcount; b += 32) {
+                    const int m = min(32, bcount - b);
+                    if (lane < m) W.dlist[nd + lane] = bfirst + b + lane;
+                    nd += m;
+                    __syncwarp();
+                    if (nd >= 32) {
+                        nd -= 32;
+                        W.tile[lane] = __ldg(posm + W.dlist[nd + lane]);
+                        __syncwarp();
+                        eval_tile(W.tile, me.x, me.y, me.z, soft, ax, ay, az);
+                        __syncwarp();
+                    }
+                }
+            }
+        }
+
+        // ---- partial tiles (zero-mass padding contributes exactly 0) ----
+        if (na > 0) {
+            if (lane >= na) W.alist[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+            eval_tile(W.alist, me.x, me.y, me.z, soft, ax, ay, az);
+            __syncwarp();
+        }
+        if (nd > 0) {
+            W.tile[lane] = lane < nd ? __ldg(posm + W.dlist[lane]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            __syncwarp();
+            eval_tile(W.tile, me.x, me.y, me.z, soft, ax, ay, az);
+            __syncwarp();
+        }
+
+        if (valid) acc[my] = make_float4(G * ax, G * ay, G * az, 0.f);
+        tot_cell += (unsigned long long)acc_cells * nb;
+        tot_body += (unsigned long long)dir_bodies * nb;
+    }
+
+    if (lane == 0) {
+        if (tot_cell) atomicAdd(&sc->inter_cell, tot_cell);
+        if (tot_body) atomicAdd(&sc->inter_body, tot_body);
+        atomicMax(&sc->max_stack, max_sp);
+    }
+}
+
+__global__ void reset_force_scalars(BhDevScalars* sc) {
+    if (threadIdx.x == 0) {
+        sc->group_ticket = 0;
+        sc->inter_cell = 0;
+        sc->inter_body = 0;
+        sc->max_stack = 0;
+    }
+}
+
+__global__ void __launch_bounds__(256) zero_acc_kernel(float4* acc, int64_t first, int64_t count) {
+    for (int64_t t = (int64_t)blockIdx.x * 256 + threadIdx.x; t < count; t += (int64_t)gridDim.x * 256)
+        acc[first + t] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+
+}  // namespace
+
+static int g_force_ctas_per_sm = 0;
+// occupancy query done once, outside any stream capture
+int bh_force_prepare() {
+    if (g_force_ctas_per_sm > 0) return 0;
+    int max_ctas = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas, force_kernel, FORCE_THREADS, 0);
+    if (e != cudaSuccess) return (int)e;
+    g_force_ctas_per_sm = max_ctas < 1 ? 1 : max_ctas;
+    return 0;
+}
+
+int bh_force_launch(const float4* posm, int64_t n, int64_t first_body, int64_t body_count,
+                    const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
+                    float4* acc, BhDevScalars* sc, float theta, float softening, float G,
+                    int num_sms, cudaStream_t st) {
+    if (body_count <= 0) return 0;
+    reset_force_scalars<<<1, 32, 0, st>>>(sc);
+    if (n < 2) {  // a single body feels nothing (its self term is exactly zero, bench:205-213)
+        zero_acc_kernel<<<1, 256, 0, st>>>(acc, first_body, body_count);
+        return (int)cudaGetLastError();
+    }
+    { int e = bh_force_prepare(); if (e) return e; }
+    const int max_ctas = g_force_ctas_per_sm;
+    const int64_t ngroups = (body_count + BH_GROUP - 1) / BH_GROUP;
+    int64_t want = (ngroups + FORCE_WARPS - 1) / FORCE_WARPS;
+    int64_t grid = (int64_t)(num_sms > 0 ? num_sms : BH_NUM_SMS_FALLBACK) * max_ctas;  // persistent: fill the chip once
+    if (grid > want) grid = want;
+    force_kernel<<<(int)grid, FORCE_THREADS, 0, st>>>(posm, first_body, body_count, cell_meta, cell_child, cell_com, acc, sc,
+                                                     theta, softening, G);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,275 @@
+// bh_sort.cu — hand-written onesweep LSD radix sort of (u32 key, u32 value) pairs.
+//
+// Replaces thrust::sort_by_key(d_keys, d_keys + N, d_vals)  nbody_v5_bench.cu:262-264
+// (stable ascending; ties keep ascending input position).
+//
+// Structure (8-bit digits):
+//   1. one histogram kernel counts every pass's digits in a single read of the keys
+//      (shared-memory histograms, one global atomic per bin per CTA);
+//   2. a 256-thread kernel turns each pass's histogram into exclusive bucket bases;
+//   3. one "onesweep" kernel per digit: a CTA takes a tile ticket, ranks its 4096 keys with
+//      warp-level match/ballot digit histograms (stable), publishes its per-digit counts,
+//      resolves the cross-tile prefix by decoupled look-back on packed status words, stages
+//      the tile digit-ordered in shared memory and writes runs out coalesced.
+// Algorithmic traffic: 4 B (histogram) + 16 B per pass per pair.
+#include "bh_common.cuh"
+
+namespace {
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX = 1 << RADIX_BITS;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_WARPS = SORT_THREADS / 32;
+constexpr int ITEMS = 16;
+constexpr int TILE = SORT_THREADS * ITEMS;  // 4096 pairs per CTA
+constexpr int MAX_PASSES = 4;
+
+constexpr uint32_t ST_MASK = 0x3FFFFFFFu;
+constexpr uint32_t ST_LOCAL = 0x40000000u;  // tile's own count is published
+constexpr uint32_t ST_INCL = 0x80000000u;   // inclusive prefix over all earlier tiles is published
+constexpr unsigned SPIN_LIMIT = 1u << 24;
+
+struct PassDesc {
+    int shift[MAX_PASSES];
+    uint32_t mask[MAX_PASSES];
+    int passes;
+};
+
+__global__ void __launch_bounds__(SORT_THREADS) histogram_kernel(const uint32_t* __restrict__ keys, int64_t n,
+                                                                PassDesc pd, uint32_t* __restrict__ hist) {
+    __shared__ uint32_t s_hist[MAX_PASSES][RADIX];
+    for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += SORT_THREADS) (&s_hist[0][0])[i] = 0;
+    __syncthreads();
+    // warp-uniform trip count so the match below always sees the full warp
+    for (int64_t base = (int64_t)blockIdx.x * SORT_THREADS + (threadIdx.x & ~31); base < n;
+         base += (int64_t)gridDim.x * SORT_THREADS) {
+        const int64_t i = base + bh_lane();
+        const bool valid = i < n;
+        const uint32_t k = valid ? __ldg(keys + i) : 0u;
+#pragma unroll
+        for (int p = 0; p < MAX_PASSES; ++p) {
+            if (p < pd.passes) {
+                // invalid lanes get a private pseudo-digit so they match nobody
+                const uint32_t d = valid ? ((k >> pd.shift[p]) & pd.mask[p]) : (0x10000u + bh_lane());
+                // warp-aggregate: Morton-coherent input puts most of a warp in one bin
+                const unsigned peers = __match_any_sync(0xffffffffu, d);
+                if (valid && (int)bh_lane() == __ffs(peers) - 1) atomicAdd(&s_hist[p][d], (uint32_t)__popc(peers));
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < pd.passes * RADIX; i += SORT_THREADS) {
+        uint32_t c = (&s_hist[0][0])[i];
+        if (c) atomicAdd(hist + i, c);
+    }
+}
+
+// exclusive scan of each pass's 256 counters, in place (one CTA, one warp-scan per pass row)
+__global__ void __launch_bounds__(RADIX) scan_hist_kernel(uint32_t* hist, int passes) {
+    __shared__ uint32_t s_warp[RADIX / 32];
+    for (int p = 0; p < passes; ++p) {
+        uint32_t v = hist[p * RADIX + threadIdx.x];
+        uint32_t inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((int)bh_lane() >= o) inc += t;
+        }
+        if (bh_lane() == 31) s_warp[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        uint32_t base = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) base += s_warp[w];
+        hist[p * RADIX + threadIdx.x] = base + inc - v;
+        __syncthreads();
+    }
+}
+
+template <bool IOTA>
+__global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const uint32_t* __restrict__ keys_in,
+                                                               const uint32_t* __restrict__ vals_in,
+                                                               uint32_t* __restrict__ keys_out,
+                                                               uint32_t* __restrict__ vals_out, int64_t n, int shift,
+                                                               uint32_t mask, const uint32_t* __restrict__ bucket_base,
+                                                               volatile uint32_t* lookback, unsigned int* ticket,
+                                                               unsigned int* err_flag) {
+    __shared__ uint32_t s_buf[TILE];
+    __shared__ uint32_t s_whist[SORT_WARPS][RADIX];
+    __shared__ uint32_t s_tile_excl[RADIX];
+    __shared__ int64_t s_global_off[RADIX];
+    __shared__ uint32_t s_scan[SORT_WARPS];
+    __shared__ unsigned int s_tile;
+
+    const int lane = bh_lane(), warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&s_whist[0][0])[i] = 0;
+    __syncthreads();
+    const unsigned tile = s_tile;
+    const int64_t tile_base = (int64_t)tile * TILE;
+    const int64_t warp_base = tile_base + (int64_t)warp * (32 * ITEMS);
+    const int tile_valid = (int)((n - tile_base) < TILE ? (n - tile_base) : TILE);
+
+    uint32_t key[ITEMS], val[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        int64_t i = warp_base + k * 32 + lane;
+        key[k] = i < n ? __ldg(keys_in + i) : 0xFFFFFFFFu;
+    }
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        int64_t i = warp_base + k * 32 + lane;
+        if (IOTA) val[k] = (uint32_t)i;
+        else val[k] = i < n ? __ldg(vals_in + i) : 0u;
+    }
+
+    // ---- stable in-warp ranking with match-any digit groups --------------------------------
+    uint32_t rank[ITEMS];
+    uint32_t* my_hist = s_whist[warp];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t d = (key[k] >> shift) & mask;
+        const unsigned peers = __match_any_sync(0xffffffffu, d);
+        const int leader = __ffs(peers) - 1;
+        uint32_t base = 0;
+        if (lane == leader) { base = my_hist[d]; my_hist[d] = base + (uint32_t)__popc(peers); }
+        base = __shfl_sync(0xffffffffu, base, leader);
+        rank[k] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
+        __syncwarp();
+    }
+    __syncthreads();
+
+    // ---- per-digit: warp offsets, tile count, publish, look-back --------------------------
+    {
+        const int d = threadIdx.x;  // SORT_THREADS == RADIX
+        uint32_t running = 0;
+#pragma unroll
+        for (int w = 0; w < SORT_WARPS; ++w) {
+            uint32_t c = s_whist[w][d];
+            s_whist[w][d] = running;
+            running += c;
+        }
+        volatile uint32_t* my_status = lookback + (size_t)tile * RADIX + d;
+        *my_status = (tile == 0 ? ST_INCL : ST_LOCAL) | running;
+
+        // exclusive scan of the tile's digit counts across the 256 threads
+        uint32_t inc = running;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) s_scan[warp] = inc;
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (int w = 0; w < warp; ++w) wbase += s_scan[w];
+        const uint32_t excl_in_tile = wbase + inc - running;
+        s_tile_excl[d] = excl_in_tile;
+
+        uint32_t prior = 0;
+        if (tile > 0) {
+            int p = (int)tile - 1;
+            unsigned spins = 0;
+            while (true) {
+                uint32_t s = lookback[(size_t)p * RADIX + d];
+                if (s & ST_INCL) { prior += s & ST_MASK; break; }
+                if (s & ST_LOCAL) { prior += s & ST_MASK; --p; spins = 0; continue; }
+                if (++spins > SPIN_LIMIT) { atomicOr(err_flag, BH_DERR_SORT_SPIN); break; }
+            }
+            *my_status = ST_INCL | (prior + running);
+        }
+        s_global_off[d] = (int64_t)bucket_base[d] + (int64_t)prior - (int64_t)excl_in_tile;
+    }
+    __syncthreads();
+
+    // ---- stage digit-ordered in shared memory, write coalesced runs ------------------------
+    uint32_t pos[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const uint32_t d = (key[k] >> shift) & mask;
+        pos[k] = s_tile_excl[d] + s_whist[warp][d] + rank[k];
+        s_buf[pos[k]] = key[k];
+    }
+    __syncthreads();
+    int64_t dst[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const int p = threadIdx.x + k * SORT_THREADS;
+        const uint32_t kk = s_buf[p];
+        const uint32_t d = (kk >> shift) & mask;
+        dst[k] = s_global_off[d] + p;
+        if (p < tile_valid) keys_out[dst[k]] = kk;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) s_buf[pos[k]] = val[k];
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        const int p = threadIdx.x + k * SORT_THREADS;
+        if (p < tile_valid) vals_out[dst[k]] = s_buf[p];
+    }
+}
+
+PassDesc make_passes(int begin_bit, int end_bit) {
+    PassDesc pd{};
+    int b = begin_bit;
+    while (b < end_bit && pd.passes < MAX_PASSES) {
+        int w = end_bit - b < RADIX_BITS ? end_bit - b : RADIX_BITS;
+        pd.shift[pd.passes] = b;
+        pd.mask[pd.passes] = (1u << w) - 1u;
+        ++pd.passes;
+        b += w;
+    }
+    return pd;
+}
+
+}  // namespace
+
+BhSortPlan bh_sort_plan(int64_t n) {
+    BhSortPlan p{};
+    p.n = n;
+    p.num_tiles = (int)((n + TILE - 1) / TILE);
+    if (p.num_tiles < 1) p.num_tiles = 1;
+    p.hist_bytes = sizeof(uint32_t) * MAX_PASSES * RADIX;
+    p.lookback_bytes = sizeof(uint32_t) * (size_t)MAX_PASSES * p.num_tiles * RADIX;
+    p.ticket_bytes = 256;  // MAX_PASSES tickets, padded
+    p.total_bytes = p.hist_bytes + p.lookback_bytes + p.ticket_bytes;
+    return p;
+}
+
+// Pass 0 reads (keys_src, vals_src) and writes (keys_p, vals_p); later passes ping-pong p -> q -> p ...
+// The sorted pairs end in p when the pass count is odd and in q when it is even (*result_in_q).
+// keys_q may alias keys_src (the source is dead after pass 0).
+int bh_sort_pairs_launch(const uint32_t* keys_src, const uint32_t* vals_src, uint32_t* keys_p, uint32_t* vals_p,
+                         uint32_t* keys_q, uint32_t* vals_q, int64_t n, int begin_bit, int end_bit, void* tmp,
+                         bool vals_in_is_iota, unsigned int* err_flag, int* result_in_q, cudaStream_t st) {
+    if (n < 0 || begin_bit < 0 || end_bit > 32 || begin_bit >= end_bit) return BH_E_INVAL;
+    if (end_bit - begin_bit > MAX_PASSES * RADIX_BITS) return BH_E_INVAL;
+    if (n >= (int64_t)ST_MASK) return BH_E_UNSUPPORTED;
+    PassDesc pd = make_passes(begin_bit, end_bit);
+    if (result_in_q) *result_in_q = (pd.passes & 1) ? 0 : 1;
+    if (n == 0) return 0;
+    BhSortPlan plan = bh_sort_plan(n);
+    uint32_t* hist = (uint32_t*)tmp;
+    uint32_t* lookback = (uint32_t*)((char*)tmp + plan.hist_bytes);
+    unsigned int* tickets = (unsigned int*)((char*)tmp + plan.hist_bytes + plan.lookback_bytes);
+    BH_CUDA_TRY(cudaMemsetAsync(tmp, 0, plan.total_bytes, st));
+    int hblocks = (int)((n + (int64_t)SORT_THREADS * 8 - 1) / ((int64_t)SORT_THREADS * 8));
+    if (hblocks > BH_NUM_SMS_FALLBACK * 8) hblocks = BH_NUM_SMS_FALLBACK * 8;
+    histogram_kernel<<<hblocks, SORT_THREADS, 0, st>>>(keys_src, n, pd, hist);
+    scan_hist_kernel<<<1, RADIX, 0, st>>>(hist, pd.passes);
+    const uint32_t *kin = keys_src, *vin = vals_src;
+    for (int p = 0; p < pd.passes; ++p) {
+        uint32_t* kout = (p & 1) ? keys_q : keys_p;
+        uint32_t* vout = (p & 1) ? vals_q : vals_p;
+        volatile uint32_t* lb = lookback + (size_t)p * plan.num_tiles * RADIX;
+        if (p == 0 && vals_in_is_iota)
+            onesweep_kernel<true><<<plan.num_tiles, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, n, pd.shift[p], pd.mask[p],
+                                                                          hist + p * RADIX, lb, tickets + p, err_flag);
+        else
+            onesweep_kernel<false><<<plan.num_tiles, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, n, pd.shift[p], pd.mask[p],
+                                                                           hist + p * RADIX, lb, tickets + p, err_flag);
+        kin = kout;
+        vin = vout;
+    }
+    return (int)cudaGetLastError();
+}

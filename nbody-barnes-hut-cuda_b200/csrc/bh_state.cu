@@ -1,0 +1,232 @@
+// bh_state.cu — streaming kernels over the body state: bounding cube, Morton keys,
+// Morton reorder, kick-drift-clamp integrator, SoA import/export.
+//
+// All of them are HBM-streaming: 128-bit loads/stores on float4 SoA
+// {x,y,z,m} / {vx,vy,vz,-}, grids sized to a multiple of the SM count with grid-stride loops.
+//
+//   bounds    replaces computeBoundingBoxKernel  nbody_v5_bench.cu:134-156 (one thread there)
+//   keys      replaces computeMortonCodesKernel  nbody_v5_bench.cu:42-63
+//   integrate replaces integrateKernel           nbody_v5_bench.cu:227-249
+#include "bh_common.cuh"
+
+namespace {
+
+constexpr int kThreads = 256;
+
+inline int grid_for(int64_t n, int per_thread, int num_sms_hint = BH_NUM_SMS_FALLBACK) {
+    int64_t blocks = (n + (int64_t)kThreads * per_thread - 1) / ((int64_t)kThreads * per_thread);
+    int64_t cap = (int64_t)num_sms_hint * 8;  // 8 resident CTAs of 256 threads per SM
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+// ---- bounding cube ----------------------------------------------------------------------
+__global__ void reset_step_scalars(BhDevScalars* sc) {
+    if (threadIdx.x == 0) {
+        // the reference starts its min/max at +-1e10f (bench:138); keep that so the
+        // result is identical even for degenerate inputs
+        sc->bbox_enc[0] = sc->bbox_enc[1] = sc->bbox_enc[2] = bh_f2ord(1e10f);
+        sc->bbox_enc[3] = sc->bbox_enc[4] = sc->bbox_enc[5] = bh_f2ord(-1e10f);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) bounds_kernel(const float4* __restrict__ posm, int64_t n,
+                                                         BhDevScalars* sc) {
+    float lo[3] = {1e10f, 1e10f, 1e10f}, hi[3] = {-1e10f, -1e10f, -1e10f};
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        float4 p = __ldg(posm + i);
+        lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+        hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[a] = fminf(lo[a], __shfl_xor_sync(0xffffffffu, lo[a], o));
+            hi[a] = fmaxf(hi[a], __shfl_xor_sync(0xffffffffu, hi[a], o));
+        }
+    __shared__ float s_lo[3][kThreads / 32], s_hi[3][kThreads / 32];
+    const int w = threadIdx.x >> 5;
+    if (bh_lane() == 0)
+        for (int a = 0; a < 3; ++a) { s_lo[a][w] = lo[a]; s_hi[a][w] = hi[a]; }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        float l = s_lo[threadIdx.x][0], h = s_hi[threadIdx.x][0];
+        for (int k = 1; k < kThreads / 32; ++k) { l = fminf(l, s_lo[threadIdx.x][k]); h = fmaxf(h, s_hi[threadIdx.x][k]); }
+        atomicMin(&sc->bbox_enc[threadIdx.x], bh_f2ord(l));
+        atomicMax(&sc->bbox_enc[3 + threadIdx.x], bh_f2ord(h));
+    }
+}
+
+// bench:148-154: size = largest extent; cube anchored at the min corner.
+__device__ __forceinline__ void cube_from_enc(const BhDevScalars* sc, float b[6]) {
+    float minX = bh_ord2f(sc->bbox_enc[0]), minY = bh_ord2f(sc->bbox_enc[1]), minZ = bh_ord2f(sc->bbox_enc[2]);
+    float maxX = bh_ord2f(sc->bbox_enc[3]), maxY = bh_ord2f(sc->bbox_enc[4]), maxZ = bh_ord2f(sc->bbox_enc[5]);
+    float size = fmaxf(__fsub_rn(maxX, minX), fmaxf(__fsub_rn(maxY, minY), __fsub_rn(maxZ, minZ)));
+    b[0] = minX; b[1] = minY; b[2] = minZ;
+    b[3] = __fadd_rn(minX, size); b[4] = __fadd_rn(minY, size); b[5] = __fadd_rn(minZ, size);
+}
+
+__global__ void finish_bounds_kernel(BhDevScalars* sc) {
+    if (threadIdx.x == 0) {
+        float b[6];
+        cube_from_enc(sc, b);
+        for (int k = 0; k < 6; ++k) sc->bounds[k] = b[k];
+    }
+}
+
+// ---- Morton keys --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t spread10(uint32_t v) {  // bench:42-49 bit spreading
+    v = (v * 0x00010001u) & 0xFF0000FFu;
+    v = (v * 0x00000101u) & 0x0F00F00Fu;
+    v = (v * 0x00000011u) & 0xC30C30C3u;
+    v = (v * 0x00000005u) & 0x49249249u;
+    return v;
+}
+
+__device__ __forceinline__ uint32_t quantise(float p, float lo, float size) {
+    // bench:58 — IEEE divide, multiply by 1023.0f (not 1024: SURVEY F5), truncate to u32
+    return __float2uint_rz(__fmul_rn(__fdiv_rn(__fsub_rn(p, lo), size), 1023.0f));
+}
+
+__global__ void __launch_bounds__(kThreads) keys_kernel(const float4* __restrict__ posm, int64_t n,
+                                                       const BhDevScalars* __restrict__ sc,
+                                                       uint32_t* __restrict__ keys) {
+    const float minX = sc->bounds[0], minY = sc->bounds[1], minZ = sc->bounds[2];
+    const float size = fmaxf(__fsub_rn(sc->bounds[3], sc->bounds[0]), 1.0f);  // bench:57
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        float4 p = __ldg(posm + i);
+        uint32_t x = quantise(p.x, minX, size), y = quantise(p.y, minY, size), z = quantise(p.z, minZ, size);
+        keys[i] = (spread10(x) << 2) | (spread10(y) << 1) | spread10(z);  // bench:61, x most significant
+    }
+}
+
+// ---- Morton reorder -----------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) reorder_kernel(const float4* __restrict__ posm_in,
+                                                          const float4* __restrict__ vel_in,
+                                                          const int32_t* __restrict__ ids_in,
+                                                          const uint32_t* __restrict__ perm,
+                                                          float4* __restrict__ posm_out,
+                                                          float4* __restrict__ vel_out,
+                                                          int32_t* __restrict__ ids_out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        uint32_t j = perm[i];
+        float4 p = __ldg(posm_in + j), v = __ldg(vel_in + j);
+        int32_t id = __ldg(ids_in + j);
+        posm_out[i] = p; vel_out[i] = v; ids_out[i] = id;
+    }
+}
+
+// ---- kick-drift-clamp ----------------------------------------------------------------------
+// bench:232-248 with the contraction nvcc applies to it:
+//   v = fma(a,DT,v); s = fma(vz,vz,fma(vx,vx,vy*vy)); if s > MAX^2: v *= MAX/sqrt(s); p = fma(v,DT,p)
+// Out of place: reads the Morton-sorted scratch copy the force phase used, writes the context's
+// current state, so a captured CUDA graph sees the same pointers every step.
+__global__ void __launch_bounds__(kThreads) integrate_kernel(const float4* __restrict__ posm_s,
+                                                            const float4* __restrict__ vel_s,
+                                                            const int32_t* __restrict__ ids_s,
+                                                            const float4* __restrict__ acc, float4* __restrict__ posm,
+                                                            float4* __restrict__ vel, int32_t* __restrict__ ids,
+                                                            int64_t first, int64_t count, float dt, float max_speed) {
+    const float vmax2 = __fmul_rn(max_speed, max_speed);
+    for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < count; t += (int64_t)gridDim.x * kThreads) {
+        const int64_t i = first + t;
+        float4 p = __ldg(posm_s + i), v = __ldg(vel_s + i);
+        const float4 a = __ldg(acc + i);
+        float x = __fmaf_rn(a.x, dt, v.x), y = __fmaf_rn(a.y, dt, v.y), z = __fmaf_rn(a.z, dt, v.z);
+        float s = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
+        if (s > vmax2) {
+            float scale = __fdiv_rn(max_speed, __fsqrt_rn(s));
+            x = __fmul_rn(x, scale); y = __fmul_rn(y, scale); z = __fmul_rn(z, scale);
+        }
+        v.x = x; v.y = y; v.z = z;
+        p.x = __fmaf_rn(x, dt, p.x); p.y = __fmaf_rn(y, dt, p.y); p.z = __fmaf_rn(z, dt, p.z);
+        vel[i] = v; posm[i] = p; ids[i] = __ldg(ids_s + i);
+    }
+}
+
+// ---- SoA import / export at the reference boundary (bench:32-35) --------------------------
+__global__ void __launch_bounds__(kThreads) import_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                                         const float* __restrict__ pz, const float* __restrict__ vx,
+                                                         const float* __restrict__ vy, const float* __restrict__ vz,
+                                                         const float* __restrict__ m, int64_t n,
+                                                         float4* __restrict__ posm, float4* __restrict__ vel,
+                                                         int32_t* __restrict__ ids) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        posm[i] = make_float4(px[i], py[i], pz[i], m[i]);
+        vel[i] = make_float4(vx[i], vy[i], vz[i], 0.0f);
+        ids[i] = (int32_t)i;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) export_kernel(const float4* __restrict__ posm, const float4* __restrict__ vel,
+                                                         const float4* __restrict__ acc, const int32_t* __restrict__ ids,
+                                                         int64_t n, float* px, float* py, float* pz, float* vx,
+                                                         float* vy, float* vz, float* ax, float* ay, float* az) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        const int32_t o = ids[i];
+        if (px || py || pz) {
+            float4 p = __ldg(posm + i);
+            if (px) px[o] = p.x;
+            if (py) py[o] = p.y;
+            if (pz) pz[o] = p.z;
+        }
+        if (vx || vy || vz) {
+            float4 v = __ldg(vel + i);
+            if (vx) vx[o] = v.x;
+            if (vy) vy[o] = v.y;
+            if (vz) vz[o] = v.z;
+        }
+        if (ax || ay || az) {
+            float4 a = __ldg(acc + i);
+            if (ax) ax[o] = a.x;
+            if (ay) ay[o] = a.y;
+            if (az) az[o] = a.z;
+        }
+    }
+}
+
+}  // namespace
+
+int bh_bounds_launch(const float4* posm, int64_t n, BhDevScalars* sc, cudaStream_t st) {
+    reset_step_scalars<<<1, 32, 0, st>>>(sc);
+    bounds_kernel<<<grid_for(n, 4), kThreads, 0, st>>>(posm, n, sc);
+    finish_bounds_kernel<<<1, 32, 0, st>>>(sc);
+    return (int)cudaGetLastError();
+}
+
+int bh_keys_launch(const float4* posm, int64_t n, BhDevScalars* sc, uint32_t* keys, cudaStream_t st) {
+    keys_kernel<<<grid_for(n, 2), kThreads, 0, st>>>(posm, n, sc, keys);
+    return (int)cudaGetLastError();
+}
+
+int bh_reorder_launch(const float4* posm_in, const float4* vel_in, const int32_t* ids_in,
+                      const uint32_t* perm, float4* posm_out, float4* vel_out, int32_t* ids_out,
+                      int64_t n, cudaStream_t st) {
+    reorder_kernel<<<grid_for(n, 2), kThreads, 0, st>>>(posm_in, vel_in, ids_in, perm, posm_out, vel_out, ids_out, n);
+    return (int)cudaGetLastError();
+}
+
+int bh_integrate_launch(const float4* posm_s, const float4* vel_s, const int32_t* ids_s, const float4* acc,
+                        float4* posm, float4* vel, int32_t* ids, int64_t first_body, int64_t body_count,
+                        float dt, float max_speed, cudaStream_t st) {
+    if (body_count <= 0) return 0;
+    integrate_kernel<<<grid_for(body_count, 2), kThreads, 0, st>>>(posm_s, vel_s, ids_s, acc, posm, vel, ids, first_body,
+                                                                  body_count, dt, max_speed);
+    return (int)cudaGetLastError();
+}
+
+int bh_import_launch(const float* px, const float* py, const float* pz, const float* vx,
+                     const float* vy, const float* vz, const float* m, int64_t n, float4* posm,
+                     float4* vel, int32_t* ids, cudaStream_t st) {
+    import_kernel<<<grid_for(n, 2), kThreads, 0, st>>>(px, py, pz, vx, vy, vz, m, n, posm, vel, ids);
+    return (int)cudaGetLastError();
+}
+
+int bh_export_launch(const float4* posm, const float4* vel, const float4* acc, const int32_t* ids,
+                     int64_t n, float* px, float* py, float* pz, float* vx, float* vy, float* vz,
+                     float* ax, float* ay, float* az, cudaStream_t st) {
+    export_kernel<<<grid_for(n, 2), kThreads, 0, st>>>(posm, vel, acc, ids, n, px, py, pz, vx, vy, vz, ax, ay, az);
+    return (int)cudaGetLastError();
+}

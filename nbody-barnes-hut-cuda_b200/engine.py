@@ -1,0 +1,312 @@
+"""ctypes binding of include/bh.h plus a thin object wrapper.
+
+Names follow the reference: ``BHEngine.simulation_step`` is ``simulationStep()``
+(nbody_v5_bench.cu:255), ``load_soa`` is the H2D block of ``main()`` (bench:329-335).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+from typing import Optional, Sequence
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB_PATH = os.path.join(_HERE, "libbh.so")
+_lib: Optional[C.CDLL] = None
+
+
+class BHError(RuntimeError):
+    pass
+
+
+class BHParams(C.Structure):
+    """bh_params — the reference's #defines (nbody_v5_bench.cu:13-18)."""
+
+    _fields_ = [
+        ("theta", C.c_float),
+        ("G", C.c_float),
+        ("dt", C.c_float),
+        ("softening", C.c_float),
+        ("max_speed", C.c_float),
+        ("key_bits", C.c_int),
+        ("leaf_cap", C.c_int),
+        ("flags", C.c_int),
+    ]
+
+
+FLAG_NO_GRAPH = 1
+FLAG_PHASE_TIMER = 2
+
+
+class PHASE:
+    KEYS, SORT, BUILD, COM, FORCE, UPDATE, TOTAL, COUNT = range(8)
+    NAMES = ["keys", "sort", "build", "com", "force", "update", "total"]
+
+
+class DBG:
+    (BOUNDS, KEYS, PERM, IDS, POSM, VEL, ACC, CELL_META, CELL_COM, CELL_CHILD,
+     POSM_SORTED, VEL_SORTED, IDS_SORTED) = range(13)
+
+
+class STAT:
+    N, CELLS, ROOT, INTERACTIONS_CELL, INTERACTIONS_BODY, DEVICE_ERROR, STEPS, MAX_STACK = range(8)
+
+
+CHILD_EMPTY = 0x7F7F7F7F
+
+
+def library_path() -> str:
+    return _LIB_PATH
+
+
+def build_library(verbose: bool = False) -> str:
+    """Compile libbh.so in tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    cmd = ["make", "-C", os.path.join(_HERE, "csrc"), "-j8"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if verbose or r.returncode != 0:
+        print(r.stdout[-4000:])
+        print(r.stderr[-4000:])
+    if r.returncode != 0:
+        raise BHError("building libbh.so failed")
+    return _LIB_PATH
+
+
+def _vp(a):
+    if a is None:
+        return None
+    if isinstance(a, np.ndarray):
+        return a.ctypes.data_as(C.c_void_p)
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if hasattr(a, "data_ptr"):  # torch tensor (host or device)
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(f"cannot pass {type(a)} as a pointer")
+
+
+def lib() -> C.CDLL:
+    """Load libbh.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise BHError(f"{_LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
+    L = C.CDLL(_LIB_PATH)
+    vp, i64, i32, f32 = C.c_void_p, C.c_int64, C.c_int, C.c_float
+    L.bh_default_params.argtypes = [C.POINTER(BHParams)]
+    L.bh_default_params.restype = None
+    L.bh_abi_version.restype = i32
+    L.bh_error_string.argtypes = [i32]
+    L.bh_error_string.restype = C.c_char_p
+    L.bh_create.argtypes = [C.POINTER(vp), i64, C.POINTER(BHParams), i32]
+    L.bh_destroy.argtypes = [vp]
+    L.bh_destroy.restype = None
+    L.bh_import_soa.argtypes = [vp] + [vp] * 7 + [i64, vp]
+    L.bh_import_soa_host.argtypes = [vp] + [vp] * 7 + [i64]
+    L.bh_step.argtypes = [vp, i32, vp]
+    L.bh_export_soa.argtypes = [vp] + [vp] * 9 + [vp]
+    L.bh_export_soa_host.argtypes = [vp] + [vp] * 9
+    L.bh_step_host.argtypes = [vp] + [vp] * 7 + [i64, i32]
+    L.bh_phase_ms.argtypes = [vp, C.POINTER(f32)]
+    L.bh_run_phase.argtypes = [vp, i32, vp]
+    L.bh_debug_get.argtypes = [vp, i32, vp, C.c_size_t]
+    L.bh_debug_set.argtypes = [vp, i32, vp, C.c_size_t]
+    L.bh_stat.argtypes = [vp, i32]
+    L.bh_stat.restype = i64
+    L.bh_set_slice.argtypes = [vp, i32, i32]
+    L.bh_state_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
+    L.bh_sort_pairs_u32.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, C.POINTER(C.c_size_t), vp]
+    L.bh_direct_sample.argtypes = [vp, vp, i32, vp]
+    L.bh_energy.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.bh_ic_refdisk.argtypes = [i64, C.c_uint] + [vp] * 7
+    L.bh_ic_uniform_cube.argtypes = [i64, C.c_uint64, f32] + [vp] * 7
+    L.bh_ic_plummer.argtypes = [i64, C.c_uint64, f32, f32, f32, f32] + [vp] * 7
+    L.bh_probe_fp32_tflops.argtypes = [i32, C.POINTER(f32)]
+    L.bh_probe_hbm_gbs.argtypes = [i32, C.POINTER(f32)]
+    _lib = L
+    return L
+
+
+def _check(code: int, what: str) -> None:
+    if code != 0:
+        msg = lib().bh_error_string(code).decode()
+        raise BHError(f"{what} failed: {code} ({msg})")
+
+
+# ---- initial conditions (host) ------------------------------------------------------------
+def _soa(n: int):
+    return [np.zeros(n, np.float32) for _ in range(7)]
+
+
+def ic_refdisk(n: int, seed: int = 42):
+    """main()'s disk, nbody_v5_bench.cu:294-308 (glibc rand)."""
+    a = _soa(n)
+    _check(lib().bh_ic_refdisk(n, seed, *[_vp(x) for x in a]), "bh_ic_refdisk")
+    return a
+
+
+def ic_uniform_cube(n: int, seed: int = 42, half_edge: float = 1000.0):
+    a = _soa(n)
+    _check(lib().bh_ic_uniform_cube(n, seed, half_edge, *[_vp(x) for x in a]), "bh_ic_uniform_cube")
+    return a
+
+
+def ic_plummer(n: int, seed: int = 42, scale_a: float = 200.0, rcut_in_a: float = 10.0,
+               body_mass: float = 4.5, G: float = 0.5):
+    a = _soa(n)
+    _check(lib().bh_ic_plummer(n, seed, scale_a, rcut_in_a, body_mass, G, *[_vp(x) for x in a]), "bh_ic_plummer")
+    return a
+
+
+def probe_fp32_tflops(device: int = 0) -> float:
+    v = C.c_float()
+    _check(lib().bh_probe_fp32_tflops(device, C.byref(v)), "bh_probe_fp32_tflops")
+    return float(v.value)
+
+
+def probe_hbm_gbs(device: int = 0) -> float:
+    v = C.c_float()
+    _check(lib().bh_probe_hbm_gbs(device, C.byref(v)), "bh_probe_hbm_gbs")
+    return float(v.value)
+
+
+def sort_pairs_u32(keys_in, vals_in, keys_out, vals_out, n: int, begin_bit: int = 0, end_bit: int = 32,
+                   tmp=None, stream: int = 0):
+    """Standalone onesweep sort on DEVICE pointers (ints or torch tensors). Returns scratch bytes if tmp is None."""
+    need = C.c_size_t(0)
+    if tmp is None:
+        _check(lib().bh_sort_pairs_u32(None, None, None, None, n, begin_bit, end_bit, None, C.byref(need), None),
+               "bh_sort_pairs_u32(size)")
+        return int(need.value)
+    need = C.c_size_t(tmp.numel() * tmp.element_size())
+    _check(lib().bh_sort_pairs_u32(_vp(keys_in), _vp(vals_in), _vp(keys_out), _vp(vals_out), n, begin_bit, end_bit,
+                                   _vp(tmp), C.byref(need), C.c_void_p(stream)), "bh_sort_pairs_u32")
+    return 0
+
+
+class BHEngine:
+    """One Barnes-Hut context on one GPU (bh_ctx)."""
+
+    def __init__(self, n_max: int, device: int = 0, flags: int = 0, **overrides):
+        L = lib()
+        self.params = BHParams()
+        L.bh_default_params(C.byref(self.params))
+        self.params.flags = flags
+        for k, v in overrides.items():
+            if not hasattr(self.params, k):
+                raise TypeError(f"unknown parameter {k}")
+            setattr(self.params, k, v)
+        self._ctx = C.c_void_p()
+        _check(L.bh_create(C.byref(self._ctx), n_max, C.byref(self.params), device), "bh_create")
+        self.n_max = n_max
+        self.device = device
+
+    # -- lifetime
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            lib().bh_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # -- state in / out
+    def load_soa(self, px, py, pz, vx, vy, vz, mass):
+        """Host numpy (or pinned torch) arrays -> device state (bench:329-335)."""
+        arrs = [px, py, pz, vx, vy, vz, mass]
+        n = len(px)
+        self._keep = arrs
+        _check(lib().bh_import_soa_host(self._ctx, *[_vp(a) for a in arrs], n), "bh_import_soa_host")
+
+    def load_soa_device(self, ptrs: Sequence, n: int, stream: int = 0):
+        _check(lib().bh_import_soa(self._ctx, *[_vp(p) for p in ptrs], n, C.c_void_p(stream)), "bh_import_soa")
+
+    def simulation_step(self, nsteps: int = 1, stream: int = 0):
+        """≙ simulationStep() x nsteps (bench:255-283); asynchronous."""
+        _check(lib().bh_step(self._ctx, nsteps, C.c_void_p(stream)), "bh_step")
+
+    def read_soa(self, want_acc: bool = True):
+        """Device state -> host SoA in ORIGINAL body order: (px,py,pz,vx,vy,vz[,ax,ay,az])."""
+        n = self.n
+        out = [np.zeros(n, np.float32) for _ in range(9 if want_acc else 6)]
+        ptrs = [_vp(a) for a in out] + [None] * (9 - len(out))
+        _check(lib().bh_export_soa_host(self._ctx, *ptrs), "bh_export_soa_host")
+        return out
+
+    def step_host(self, px, py, pz, vx, vy, vz, mass, nsteps: int = 1):
+        """Host in -> nsteps -> host out, every copy inside the call (bench.py e2e leg)."""
+        n = len(px)
+        _check(lib().bh_step_host(self._ctx, *[_vp(a) for a in (px, py, pz, vx, vy, vz, mass)], n, nsteps), "bh_step_host")
+
+    # -- introspection
+    @property
+    def n(self) -> int:
+        return int(lib().bh_stat(self._ctx, STAT.N))
+
+    def stat(self, which: int) -> int:
+        return int(lib().bh_stat(self._ctx, which))
+
+    def check_device_error(self):
+        e = self.stat(STAT.DEVICE_ERROR)
+        if e:
+            raise BHError(f"device error flag = {e}")
+
+    def run_phase(self, phase: int, stream: int = 0):
+        _check(lib().bh_run_phase(self._ctx, phase, C.c_void_p(stream)), f"bh_run_phase({phase})")
+
+    def phase_ms(self):
+        out = (C.c_float * PHASE.COUNT)()
+        _check(lib().bh_phase_ms(self._ctx, out), "bh_phase_ms")
+        return {PHASE.NAMES[i]: float(out[i]) for i in range(PHASE.TOTAL + 1)}
+
+    def debug_get(self, what: int) -> np.ndarray:
+        n, M = self.n, None
+        if what in (DBG.CELL_META, DBG.CELL_COM, DBG.CELL_CHILD):
+            M = self.stat(STAT.CELLS)
+        shapes = {
+            DBG.BOUNDS: ((6,), np.float32), DBG.KEYS: ((n,), np.uint32), DBG.PERM: ((n,), np.int32),
+            DBG.IDS: ((n,), np.int32), DBG.POSM: ((n, 4), np.float32), DBG.VEL: ((n, 4), np.float32),
+            DBG.ACC: ((n, 4), np.float32), DBG.CELL_META: ((M, 4), np.int32), DBG.CELL_COM: ((M, 4), np.float32),
+            DBG.CELL_CHILD: ((M, 8), np.int32), DBG.POSM_SORTED: ((n, 4), np.float32),
+            DBG.VEL_SORTED: ((n, 4), np.float32), DBG.IDS_SORTED: ((n,), np.int32),
+        }
+        shape, dt = shapes[what]
+        out = np.zeros(shape, dt)
+        _check(lib().bh_debug_get(self._ctx, what, _vp(out), out.nbytes), f"bh_debug_get({what})")
+        return out
+
+    def debug_set(self, what: int, arr: np.ndarray):
+        arr = np.ascontiguousarray(arr)
+        _check(lib().bh_debug_set(self._ctx, what, _vp(arr), arr.nbytes), f"bh_debug_set({what})")
+
+    def direct_sample(self, sample_ids: np.ndarray) -> np.ndarray:
+        s = np.ascontiguousarray(sample_ids, np.int32)
+        out = np.zeros((len(s), 3), np.float64)
+        _check(lib().bh_direct_sample(self._ctx, _vp(s), len(s), _vp(out)), "bh_direct_sample")
+        return out
+
+    def energy(self):
+        ke, pe = C.c_double(), C.c_double()
+        _check(lib().bh_energy(self._ctx, C.byref(ke), C.byref(pe)), "bh_energy")
+        return float(ke.value), float(pe.value)
+
+    # -- multi-GPU slices
+    def set_slice(self, rank: int, world: int):
+        _check(lib().bh_set_slice(self._ctx, rank, world), "bh_set_slice")
+
+    def state_ptrs(self):
+        vp, i64 = C.c_void_p, C.c_int64
+        posm, vel, ids, n, first, count = vp(), vp(), vp(), i64(), i64(), i64()
+        _check(lib().bh_state_ptrs(self._ctx, C.byref(posm), C.byref(vel), C.byref(ids), C.byref(n), C.byref(first),
+                                   C.byref(count)), "bh_state_ptrs")
+        return dict(posm=posm.value, vel=vel.value, ids=ids.value, n=n.value, first=first.value, count=count.value)

@@ -1,0 +1,94 @@
+// ref_wrap.cu — C ABI around the UNMODIFIED reference translation unit.  TEST/BASELINE ONLY.
+//
+// REF_SRC (= /root/reference/nbody_v5_bench.cu) is #included where it lies; its main() is
+// renamed by a macro so the eight kernels, the file-scope device pointers (bench:31-40) and
+// simulationStep() (bench:255-283) are compiled exactly as shipped.  This file only adds
+// what main() does around them (allocation bench:311-326, H2D bench:329-335, the cudaEvent
+// pair bench:355-363) behind extern "C" so Python can drive it.  Used to (1) pin Oracle-L
+// against the real reference on a B200 and (2) time the reference's own sm_100 build
+// (BASELINE.md B1).  Output goes to oracle/_ref/, which is git-ignored.
+#define main reference_main_unused
+#include REF_SRC
+#undef main
+
+#include <cstdint>
+
+namespace {
+int g_alloc_n = 0;
+template <class T> cudaError_t dalloc(T** p, size_t bytes) { return cudaMalloc((void**)p, bytes); }
+}
+
+extern "C" {
+
+void ref_free(void) {
+    if (!g_alloc_n) return;
+    cudaFree(d_posX); cudaFree(d_posY); cudaFree(d_posZ);
+    cudaFree(d_velX); cudaFree(d_velY); cudaFree(d_velZ);
+    cudaFree(d_accX); cudaFree(d_accY); cudaFree(d_accZ);
+    cudaFree(d_mass); cudaFree(d_nodes); cudaFree(d_nodeCounter);
+    cudaFree(d_leafNodeIdx); cudaFree(d_bounds); cudaFree(d_mortonCodes); cudaFree(d_indices);
+    g_alloc_n = 0;
+}
+
+// Allocate the reference's 16 buffers for n bodies and upload the SoA state.
+int ref_init(int n, const float* px, const float* py, const float* pz,
+             const float* vx, const float* vy, const float* vz, const float* mass) {
+    ref_free();
+    N = n;  // the reference's global body count (bench:31)
+    size_t f = (size_t)n * 4;
+    cudaError_t e = cudaSuccess;
+    float** fl[] = {&d_posX, &d_posY, &d_posZ, &d_velX, &d_velY, &d_velZ, &d_accX, &d_accY, &d_accZ, &d_mass};
+    for (auto p : fl) if ((e = dalloc(p, f)) != cudaSuccess) return (int)e;
+    if ((e = dalloc(&d_nodes, (size_t)n * 2 * sizeof(OctreeNode))) != cudaSuccess) return (int)e;
+    if ((e = dalloc(&d_nodeCounter, 4)) != cudaSuccess) return (int)e;
+    if ((e = dalloc(&d_leafNodeIdx, f)) != cudaSuccess) return (int)e;
+    if ((e = dalloc(&d_bounds, 24)) != cudaSuccess) return (int)e;
+    if ((e = dalloc(&d_mortonCodes, f)) != cudaSuccess) return (int)e;
+    if ((e = dalloc(&d_indices, f)) != cudaSuccess) return (int)e;
+    g_alloc_n = n;
+    cudaMemset(d_leafNodeIdx, 0, f);  // cudaMalloc leaves it undefined in the reference
+    cudaMemset(d_accX, 0, f); cudaMemset(d_accY, 0, f); cudaMemset(d_accZ, 0, f);
+    const float* src[] = {px, py, pz, vx, vy, vz, mass};
+    float* dst[] = {d_posX, d_posY, d_posZ, d_velX, d_velY, d_velZ, d_mass};
+    for (int i = 0; i < 7; ++i)
+        if ((e = cudaMemcpy(dst[i], src[i], f, cudaMemcpyHostToDevice)) != cudaSuccess) return (int)e;
+    return 0;
+}
+
+// nsteps calls of the reference's simulationStep(); total device time in ms like bench:355-363.
+int ref_step(int nsteps, float* total_ms) {
+    if (!g_alloc_n) return -3;
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a);
+    for (int s = 0; s < nsteps; ++s) simulationStep();
+    cudaEventRecord(b);
+    cudaError_t e = cudaEventSynchronize(b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, a, b);
+    if (total_ms) *total_ms = ms;
+    cudaEventDestroy(a); cudaEventDestroy(b);
+    if (e == cudaSuccess) e = cudaGetLastError();
+    return (int)e;
+}
+
+// what: 0..2 pos, 3..5 vel, 6..8 acc, 9 mass, 10 keys (sorted), 11 indices (sorted), 12 bounds[6],
+// 13 node counter, 14 root node record (19 words).
+int ref_get(int what, void* dst) {
+    if (!g_alloc_n) return -3;
+    size_t f = (size_t)g_alloc_n * 4;
+    const void* src = nullptr; size_t bytes = f;
+    switch (what) {
+        case 0: src = d_posX; break; case 1: src = d_posY; break; case 2: src = d_posZ; break;
+        case 3: src = d_velX; break; case 4: src = d_velY; break; case 5: src = d_velZ; break;
+        case 6: src = d_accX; break; case 7: src = d_accY; break; case 8: src = d_accZ; break;
+        case 9: src = d_mass; break; case 10: src = d_mortonCodes; break; case 11: src = d_indices; break;
+        case 12: src = d_bounds; bytes = 24; break;
+        case 13: src = d_nodeCounter; bytes = 4; break;
+        case 14: src = d_nodes; bytes = sizeof(OctreeNode); break;
+        default: return -1;
+    }
+    return (int)cudaMemcpy(dst, src, bytes, cudaMemcpyDeviceToHost);
+}
+
+}  // extern "C"

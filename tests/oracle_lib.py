@@ -1,0 +1,158 @@
+"""ctypes access to oracle/libbh_oracle.so — the CPU restatement (checker only, never the product)."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_PATH = os.path.join(ROOT, "oracle", "libbh_oracle.so")
+_lib = None
+
+CHILD_EMPTY = 0x7F7F7F7F
+G, THETA, DT, SOFT, VMAX = 0.5, 0.5, 0.02, 50.0, 500.0   # nbody_v5_bench.cu:13-18
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_PATH):
+            subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), _PATH], check=True, capture_output=True)
+        _lib = C.CDLL(_PATH)
+        _lib.orc_num_threads.restype = C.c_int
+    return _lib
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def f32(x):
+    return C.c_float(float(x))
+
+
+def num_threads():
+    return int(lib().orc_num_threads())
+
+
+def bounds(px, py, pz):
+    b = np.zeros(6, np.float32)
+    lib().orc_bounds(_p(px), _p(py), _p(pz), C.c_int64(len(px)), _p(b))
+    return b
+
+
+def morton_keys(px, py, pz, b):
+    n = len(px)
+    keys, idx = np.zeros(n, np.uint32), np.zeros(n, np.int32)
+    lib().orc_morton_keys(_p(px), _p(py), _p(pz), C.c_int64(n), _p(b), _p(keys), _p(idx))
+    return keys, idx
+
+
+def stable_sort(keys, idx):
+    k, i = keys.copy(), idx.copy()
+    lib().orc_stable_sort(_p(k), _p(i), C.c_int64(len(k)))
+    return k, i
+
+
+def integrate(px, py, pz, vx, vy, vz, ax, ay, az, dt=DT, vmax=VMAX):
+    out = [np.ascontiguousarray(a, np.float32).copy() for a in (px, py, pz, vx, vy, vz)]
+    acc = [np.ascontiguousarray(a, np.float32) for a in (ax, ay, az)]
+    lib().orc_integrate(*[_p(a) for a in out], *[_p(a) for a in acc], C.c_int64(len(px)), f32(dt), f32(vmax))
+    return out
+
+
+def reference_step(soa, nsteps=1, fixed=0, G_=G, theta=THETA, dt=DT, soft=SOFT, vmax=VMAX):
+    """Oracle-L (fixed=0) / id-fixed reference tree (fixed=1): nsteps of simulationStep() on copies."""
+    px, py, pz, vx, vy, vz, m = [np.ascontiguousarray(a, np.float32).copy() for a in soa]
+    n = len(px)
+    ax, ay, az = [np.zeros(n, np.float32) for _ in range(3)]
+    ph, info = np.zeros(6), np.zeros(3, np.int64)
+    keys, idx, b = np.zeros(n, np.uint32), np.zeros(n, np.int32), np.zeros(6, np.float32)
+    rc = lib().orc_reference_step(_p(px), _p(py), _p(pz), _p(vx), _p(vy), _p(vz), _p(ax), _p(ay), _p(az), _p(m),
+                                  C.c_int64(n), nsteps, fixed, f32(G_), f32(theta), f32(dt), f32(soft), f32(vmax),
+                                  _p(ph), _p(info), _p(keys), _p(idx), _p(b))
+    assert rc == 0
+    return dict(px=px, py=py, pz=pz, vx=vx, vy=vy, vz=vz, ax=ax, ay=ay, az=az, phase_ms=ph, nodes=int(info[0]),
+                interactions=int(info[1]), max_stack=int(info[2]), keys=keys, idx=idx, bounds=b)
+
+
+def tree_build(sorted_keys):
+    n = len(sorted_keys)
+    cap = max(n, 1)
+    meta, child = np.zeros((cap, 4), np.int32), np.zeros((cap, 8), np.int32)
+    root = C.c_int32(-1)
+    M = lib().orc_tree_build(_p(sorted_keys), C.c_int64(n), _p(meta), _p(child), C.c_int64(cap), C.byref(root))
+    assert M >= 0
+    return meta[:M].copy(), child[:M].copy(), int(root.value)
+
+
+def tree_com(posm, meta, child, root):
+    M = len(meta)
+    mom, com = np.zeros((max(M, 1), 4), np.float32), np.zeros((max(M, 1), 4), np.float32)
+    lib().orc_tree_com(_p(posm), C.c_int64(len(posm)), _p(meta), _p(child), C.c_int64(M), C.c_int32(root), _p(mom), _p(com))
+    return mom[:M], com[:M]
+
+
+def force_group(posm, b, meta, child, com, root, group=32, theta=THETA, soft=SOFT, G_=G):
+    n = len(posm)
+    acc, counts = np.zeros((n, 4), np.float32), np.zeros(2, np.int64)
+    lib().orc_force_group(_p(posm), C.c_int64(n), _p(b), _p(meta), _p(child), _p(com), C.c_int64(len(meta)),
+                          C.c_int32(root), group, f32(theta), f32(soft), f32(G_), _p(acc), _p(counts))
+    return acc, counts
+
+
+def force_body(posm, b, meta, child, com, root, theta=THETA, soft=SOFT, G_=G):
+    n = len(posm)
+    acc, counts = np.zeros((n, 4), np.float32), np.zeros(2, np.int64)
+    lib().orc_force_body(_p(posm), C.c_int64(n), _p(b), _p(meta), _p(child), _p(com), C.c_int64(len(meta)),
+                         C.c_int32(root), f32(theta), f32(soft), f32(G_), _p(acc), _p(counts))
+    return acc, counts
+
+
+def direct_sum(posm, sample, soft=SOFT, G_=G):
+    s = np.ascontiguousarray(sample, np.int32)
+    out = np.zeros((len(s), 3), np.float64)
+    lib().orc_direct_sum(_p(posm), C.c_int64(len(posm)), _p(s), len(s), f32(soft), f32(G_), _p(out))
+    return out
+
+
+def energy(posm, vel, soft=SOFT, G_=G):
+    ke, pe = C.c_double(), C.c_double()
+    lib().orc_energy(_p(posm), _p(vel), C.c_int64(len(posm)), f32(soft), f32(G_), C.byref(ke), C.byref(pe))
+    return ke.value, pe.value
+
+
+def engine_step(posm, vel, ids, nsteps=1, group=32, G_=G, theta=THETA, dt=DT, soft=SOFT, vmax=VMAX):
+    """Oracle-I: nsteps of the shipped algorithm on copies of the internal-layout state."""
+    posm, vel, ids = posm.copy(), vel.copy(), ids.copy()
+    n = len(posm)
+    acc, keys, perm = np.zeros((n, 4), np.float32), np.zeros(n, np.uint32), np.zeros(n, np.int32)
+    b, counts, ph = np.zeros(6, np.float32), np.zeros(3, np.int64), np.zeros(6)
+    rc = lib().orc_engine_step(_p(posm), _p(vel), _p(ids), C.c_int64(n), nsteps, f32(G_), f32(theta), f32(dt), f32(soft),
+                               f32(vmax), group, _p(acc), _p(keys), _p(perm), _p(b), _p(counts), _p(ph))
+    assert rc == 0
+    return dict(posm=posm, vel=vel, ids=ids, acc=acc, keys=keys, perm=perm, bounds=b, inter_cell=int(counts[0]),
+                inter_body=int(counts[1]), cells=int(counts[2]), phase_ms=ph)
+
+
+def soa_to_internal(soa):
+    px, py, pz, vx, vy, vz, m = soa
+    n = len(px)
+    posm = np.stack([px, py, pz, m], 1).astype(np.float32).copy()
+    vel = np.stack([vx, vy, vz, np.zeros(n, np.float32)], 1).astype(np.float32).copy()
+    return posm, vel, np.arange(n, dtype=np.int32)
+
+
+def rel_rms(a, ref):
+    a, ref = np.asarray(a, np.float64), np.asarray(ref, np.float64)
+    return float(np.sqrt(((a - ref) ** 2).sum() / (ref ** 2).sum()))
+
+
+def cell_tuples(meta, keys_sorted):
+    """numbering-independent view of a tree: set of (level, prefix, first, count)."""
+    out = set()
+    for first, count, lvflag, _parent in meta:
+        L = int(lvflag) & 0xFF
+        prefix = int(keys_sorted[first]) >> (30 - 3 * L) if L > 0 else 0
+        out.add((L, prefix, int(first), int(count)))
+    return out
