@@ -1,0 +1,310 @@
+#!/usr/bin/env python
+"""bench.py — body-steps/s and BH interactions/s of the Barnes-Hut step path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
+
+A "step" is one simulationStep() (nbody_v5_bench.cu:255-283) over the whole body set.
+Workloads (BASELINE.json configs): refdisk_1m = configs[1] (1,000,000-body reference disk,
+theta 0.5) is the N=1 default; plummer_16m = configs[3]; uniform_16k = configs[0];
+plummer_1m = configs[2].  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+LAUNCHES_PER_STEP = 20   # bounds 3, keys 1, sort 6, reorder 1, tree 5, com 1, force 2, integrate 1
+FLOP_PER_INTERACTION = 20  # SURVEY §8d (GPU-Gems convention; bench:205-213 op count)
+
+WORKLOADS = {
+    "uniform_16k": dict(n=16_384, ic="uniform", desc="configs[0]: 16,384-body uniform cube"),
+    "refdisk_1m": dict(n=1_000_000, ic="refdisk", desc="configs[1]: nbody_v5_bench disk (bench:294-308), 1,000,000 bodies"),
+    "refdisk_500k": dict(n=500_000, ic="refdisk", desc="reference code default N=500,000 (bench:31)"),
+    "plummer_1m": dict(n=1_000_000, ic="plummer", desc="configs[2]: 1,000,000-body Plummer sphere a=200 cut 10a"),
+    "plummer_16m": dict(n=16_000_000, ic="plummer", desc="configs[3]: 16,000,000-body Plummer sphere a=200 cut 10a"),
+}
+
+
+def make_ic(bh, w):
+    if w["ic"] == "refdisk":
+        return bh.ic_refdisk(w["n"], 42)
+    if w["ic"] == "uniform":
+        return bh.ic_uniform_cube(w["n"], 42, 1000.0)
+    return bh.ic_plummer(w["n"], 42, 200.0, 10.0, 4.5, 0.5)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 7 for i in range(4) if r[3 + i].lower().startswith("active")})
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_baseline(w, budget_steps=None):
+    """Oracle-L (OpenMP transliteration of the reference kernels, contract baseline (a)) on the host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import nbody_barnes_hut_cuda_b200 as bh
+    import oracle_lib as O
+
+    n = min(w["n"], 1_000_000)
+    soa = make_ic(bh, dict(w, n=n))
+    steps = budget_steps or (10 if n <= 100_000 else 4)
+    O.reference_step(soa, 1, fixed=0)  # warm the allocator / page cache
+    t0 = time.perf_counter()
+    r = O.reference_step(soa, steps, fixed=0)
+    dt = time.perf_counter() - t0
+    return {"value": n * steps / dt, "unit": "body-steps/s", "cores": O.num_threads(), "kind": "port",
+            "sample": f"Oracle-L (literal OpenMP transliteration, 1.00 interactions/body) {steps} steps at N={n} of the {w['ic']} input",
+            "phase_ms_per_step": {k: round(v / steps, 3) for k, v in zip(("keys", "sort", "insert", "com", "force", "integrate"), r["phase_ms"])}}
+
+
+def run_reference_arm(args, w):
+    """The reference's own kernels + simulationStep() (sm_100 recompile, oracle/_ref) when a GPU and the
+    prebuilt library are present — BASELINE.md B1 / north_star baseline (b); otherwise the OpenMP port."""
+    import ctypes as C
+
+    import numpy as np
+
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    import nbody_barnes_hut_cuda_b200 as bh
+
+    cpu = cpu_baseline(w)
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_step.so")
+    have_gpu = False
+    try:
+        import torch
+
+        have_gpu = torch.cuda.is_available()
+    except Exception:
+        pass
+    line = {"impl": "reference", "metric": "body-steps/s", "unit": "body-steps/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": {"workload": args.workload, "desc": w["desc"], "n_bodies": w["n"], "theta": 0.5}}
+    if have_gpu and os.path.exists(path):
+        L = C.CDLL(path)
+        soa = make_ic(bh, w)
+        p = lambda a: a.ctypes.data_as(C.c_void_p)
+        rc = L.ref_init(w["n"], *[p(np.ascontiguousarray(a, np.float32)) for a in soa])
+        assert rc == 0, f"ref_init {rc}"
+        ms = C.c_float()
+        clocks = ClockSampler()
+        assert L.ref_step(args.warmup, C.byref(ms)) == 0
+        clocks.start()
+        assert L.ref_step(args.steps, C.byref(ms)) == 0
+        ck = clocks.stop()
+        L.ref_free()
+        value = w["n"] * args.steps / (ms.value * 1e-3)
+        line.update({"value": value, "ms_per_step": ms.value / args.steps, "interactions_per_body": 1.0,
+                     "interactions_per_s": value, "clocks": ck, "gpu_launches": None,
+                     "reference_kind": "UNMODIFIED nbody_v5_bench.cu kernels + simulationStep() compiled -arch=sm_100 "
+                                       "(oracle/ref_wrap.cu includes the source in place), run on this B200; "
+                                       "the reference is CUDA-only, its OpenMP transliteration is in cpu_baseline",
+                     "cpu_baseline": cpu,
+                     "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    else:
+        line.update({"value": cpu["value"], "ms_per_step": 1e3 * min(w["n"], 1_000_000) / cpu["value"],
+                     "interactions_per_body": 1.0, "cpu_baseline": cpu,
+                     "reference_kind": "OpenMP transliteration (no GPU or oracle/_ref missing)",
+                     "e2e": {"value": cpu["value"], "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
+    return line
+
+
+def run_ours(args, w):
+    import numpy as np
+    import torch
+
+    import nbody_barnes_hut_cuda_b200 as bh
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
+    if world > 1:
+        from nbody_barnes_hut_cuda_b200.sliced import run_sliced_bench  # multi-GPU Morton slices
+
+        return run_sliced_bench(args, w, bh, dist, rank, world, local)
+
+    n = w["n"]
+    soa = make_ic(bh, w)
+    stream = torch.cuda.current_stream().cuda_stream
+    eng = bh.BHEngine(n, device=local)
+    eng.load_soa(*soa)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+
+    # ---- warm-up
+    eng.simulation_step(args.warmup, stream)
+    barrier()
+    eng.check_device_error()
+
+    # ---- timed: K steps, each bracketed by events, L2 flushed (untimed) between steps
+    clocks = ClockSampler(local)
+    clocks.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    inter = 0
+    barrier()
+    t_wall0 = time.perf_counter()
+    for a, b in evs:
+        flush.fill_(1)
+        a.record()
+        eng.simulation_step(1, stream)
+        b.record()
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    step_ms = [a.elapsed_time(b) for a, b in evs]
+    total_ms = sum(step_ms)
+    inter = eng.stat(bh.STAT.INTERACTIONS_CELL) + eng.stat(bh.STAT.INTERACTIONS_BODY)
+
+    # ---- same loop back to back (no flush): the natural simulation loop, for information
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    a.record()
+    eng.simulation_step(args.steps, stream)
+    b.record()
+    barrier()
+    warm_ms = a.elapsed_time(b)
+    ck = clocks.stop()
+    eng.check_device_error()
+    cells = eng.stat(bh.STAT.CELLS)
+    max_stack = eng.stat(bh.STAT.MAX_STACK)
+    eng.close()
+
+    # ---- per-phase breakdown (event between phases, direct launches) + roofline of the dominant kernel
+    engt = bh.BHEngine(n, device=local, flags=2)
+    engt.load_soa(*soa)
+    engt.simulation_step(args.warmup, stream)
+    psteps = max(3, min(args.steps, 20))
+    engt.simulation_step(psteps, stream)
+    phases = {k: v / psteps for k, v in engt.phase_ms().items()}
+    engt.close()
+    fp32_peak = bh.probe_fp32_tflops(local)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    force_tflops = FLOP_PER_INTERACTION * inter / (phases["force"] * 1e-3) / 1e12
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "force_traffic.json"))).get(args.workload)
+    except Exception:
+        pass
+    bytes_per_body = {"keys": 32.0, "sort": 68.0 + 64.0, "update": 60.0}   # SURVEY §8d algorithmic bytes
+    hbm_frac = {k: (bytes_per_body[k] * n / (phases[k] * 1e-3) / 1e9) / hbm_peak for k in bytes_per_body}
+
+    # ---- e2e: host SoA in (pinned) -> 1 step -> host SoA out, every copy inside the timed region
+    enge = bh.BHEngine(n, device=local)
+    pinned = [torch.from_numpy(x.copy()).pin_memory() for x in soa]
+    harr = [t.numpy() for t in pinned]
+    for _ in range(max(3, args.warmup)):
+        enge.step_host(*harr, nsteps=1)
+    esteps = max(3, min(args.steps, 20))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(esteps):
+        enge.step_host(*harr, nsteps=1)
+    barrier()
+    e2e_s = (time.perf_counter() - t0) / esteps
+    enge.close()
+
+    value = n * args.steps / (total_ms * 1e-3)
+    line = {
+        "metric": "body-steps/s", "value": value, "unit": "body-steps/s", "n_gpus": 1, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["desc"], "n_bodies": n, "theta": 0.5, "G": 0.5, "dt": 0.02,
+                   "softening": 50.0, "max_speed": 500.0, "group": 32,
+                   "l2": "flushed between timed steps (256 MiB fill, untimed); value_l2_warm is the back-to-back loop"},
+        "interactions_per_body": inter / n, "interactions_per_s": inter * args.steps / (total_ms * 1e-3),
+        "value_l2_warm": n * args.steps / (warm_ms * 1e-3), "ms_per_step_l2_warm": warm_ms / args.steps,
+        "wall_s_timed_loop": t_wall, "cells": cells, "max_stack": max_stack,
+        "phase_ms": {k: round(v, 4) for k, v in phases.items()},
+        "roofline": {"bound": "fp32", "kernel": "force_kernel", "achieved": force_tflops, "peak": fp32_peak,
+                     "unit": "TFLOP/s", "frac": force_tflops / fp32_peak if fp32_peak else None, "traffic": traffic,
+                     "peak_source": "bh_probe_fp32_tflops (FMA issue-rate probe run in this process)",
+                     "flop_per_interaction": FLOP_PER_INTERACTION,
+                     "hbm_frac_streaming_phases": {k: round(v, 4) for k, v in hbm_frac.items()},
+                     "hbm_peak_gbs": hbm_peak, "hbm_peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+        "e2e": {"value": n / e2e_s, "unit": "body-steps/s", "h2d_bytes_per_step": 28 * n, "d2h_bytes_per_step": 24 * n,
+                "ms_per_step": e2e_s * 1e3, "api": "bh_step_host (pinned host SoA in, 1 step, host SoA out)"},
+        "gpu_launches": LAUNCHES_PER_STEP * args.steps, "clocks": ck,
+    }
+    if not args.no_cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline(w)
+    return line
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.workload is None:
+        args.workload = "refdisk_1m" if args.gpus == 1 else "plummer_16m"
+    w = WORKLOADS[args.workload]
+    line = run_reference_arm(args, w) if args.impl == "reference" else run_ours(args, w)
+    if line is not None:
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()
