@@ -48,6 +48,8 @@ typedef struct bh_params {
     int   key_bits;   /* 30: 10 bits/axis Morton key, nbody_v5_bench.cu:58-61 */
     int   leaf_cap;   /* 1: one body per leaf, as nbody_v5_bench.cu:100-104   */
     int   flags;      /* BH_FLAG_* */
+    float group_split;/* 0.5: a 32-body traversal group is cut at its coarsest key
+                         boundary while ext(A)+ext(B) < group_split*ext(AuB); 0 = never */
 } bh_params;
 
 #define BH_FLAG_NO_GRAPH    1  /* launch kernels directly instead of a CUDA graph  */

@@ -86,9 +86,9 @@ int bh_tree_launch(const uint32_t* keys, int64_t n, int2* pair_info, int32_t* pa
 int bh_com_launch(const float4* posm, int64_t n, const int4* cell_meta, const int32_t* cell_child,
                   int32_t* cell_arrive, float4* cell_mom, float4* cell_com,
                   BhDevScalars* sc, cudaStream_t st);
-int bh_force_launch(const float4* posm, int64_t n, int64_t first_body, int64_t body_count,
+int bh_force_launch(const float4* posm, const uint32_t* keys, int64_t n, int64_t first_body, int64_t body_count,
                     const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
-                    float4* acc, BhDevScalars* sc, float theta, float softening, float G,
+                    float4* acc, BhDevScalars* sc, float theta, float softening, float G, float split_alpha,
                     int num_sms, cudaStream_t st);
 int bh_force_prepare();
 int bh_integrate_launch(const float4* posm_s, const float4* vel_s, const int32_t* ids_s, const float4* acc,

@@ -108,8 +108,9 @@ int phase_com(bh_ctx* c, cudaStream_t st) {
 }
 
 int phase_force(bh_ctx* c, cudaStream_t st) {
-    return bh_force_launch(c->posm_s, c->n, c->slice_first, c->slice_count, c->cell_meta, c->cell_child, c->cell_com,
-                           c->acc, c->sc, c->prm.theta, c->prm.softening, c->prm.G, c->num_sms, st);
+    return bh_force_launch(c->posm_s, c->keys0, c->n, c->slice_first, c->slice_count, c->cell_meta, c->cell_child,
+                           c->cell_com, c->acc, c->sc, c->prm.theta, c->prm.softening, c->prm.G, c->prm.group_split,
+                           c->num_sms, st);
 }
 
 int phase_update(bh_ctx* c, cudaStream_t st) {
@@ -157,7 +158,7 @@ extern "C" {
 void bh_default_params(bh_params* p) {
     if (!p) return;
     p->theta = 0.5f; p->G = 0.5f; p->dt = 0.02f; p->softening = 50.0f; p->max_speed = 500.0f;
-    p->key_bits = BH_KEY_BITS; p->leaf_cap = 1; p->flags = 0;
+    p->key_bits = BH_KEY_BITS; p->leaf_cap = 1; p->flags = 0; p->group_split = 0.5f;
 }
 
 int bh_abi_version(void) { return BH_ABI_VERSION; }
@@ -181,6 +182,7 @@ int bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device) 
     if (params) prm = *params; else bh_default_params(&prm);
     if (prm.key_bits != BH_KEY_BITS || prm.leaf_cap != 1) return BH_E_UNSUPPORTED;
     if (!(prm.softening > 0.0f) || !(prm.theta >= 0.0f) || !(prm.max_speed > 0.0f)) return BH_E_INVAL;
+    if (!(prm.group_split >= 0.0f) || prm.group_split > 1.0f) return BH_E_INVAL;
     BH_CUDA_TRY(cudaSetDevice(device));
     { int e0 = bh_force_prepare(); if (e0) return e0; }
     bh_ctx* c = new (std::nothrow) bh_ctx();

@@ -16,6 +16,13 @@
 //   - whenever a list holds 32 entries the warp evaluates a 32x32 tile: each lane keeps its own
 //     body in registers and reads the 32 sources as shared-memory broadcasts (LDS.128), doing
 //     bench:205-213's arithmetic with rsqrtf.
+// Group splitting: a 32-slot chunk of the Morton order that straddles a coarse cell boundary would
+// get a huge bounding box (measured on the 1M reference disk: median list 1,088 entries, worst
+// chunk 61,493 — one warp then outlives the whole grid).  The warp therefore cuts its chunk at the
+// coarsest key boundary whenever  ext(A) + ext(B) < alpha * ext(A u B)  (ext = sum of the box
+// edges; redux.sync min/max on order-preserving integer images of the coordinates), recursively,
+// and traverses each sub-group with all 32 lanes testing cells but only the sub-group's lanes
+// keeping the result.  oracle/bh_oracle.cpp:orc_make_groups is the CPU restatement of the rule.
 // The tree (32-byte records + 32-byte child tables) and the positions stay L2-resident at
 // 1M bodies; shared memory holds only per-warp traversal state.
 #include "bh_common.cuh"
@@ -37,6 +44,14 @@ struct __align__(16) WarpScratch {
     int dlist[DLIST_CAP];      // body slots awaiting direct evaluation
 };
 
+// r2 >= SOFTENING > 0, never denormal: the flush-to-zero form is a bare MUFU.RSQ (the default
+// rsqrtf adds a denormal rescue of three instructions per interaction).
+__device__ __forceinline__ float rsqrt_fast(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // 32 sources against this lane's body.  bench:205-213 with dist^-3 from one rsqrt.
 __device__ __forceinline__ void eval_tile(const float4* __restrict__ src, float px, float py, float pz,
                                           float soft, float& ax, float& ay, float& az) {
@@ -45,7 +60,7 @@ __device__ __forceinline__ void eval_tile(const float4* __restrict__ src, float 
         const float4 s = src[k];  // same address in every lane: shared-memory broadcast
         const float dx = s.x - px, dy = s.y - py, dz = s.z - pz;
         const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, soft)));
-        const float rinv = rsqrtf(r2);
+        const float rinv = rsqrt_fast(r2);
         const float f = (s.w * rinv) * (rinv * rinv);
         ax = fmaf(f, dx, ax);
         ay = fmaf(f, dy, ay);
@@ -53,12 +68,13 @@ __device__ __forceinline__ void eval_tile(const float4* __restrict__ src, float 
     }
 }
 
-__global__ void __launch_bounds__(FORCE_THREADS) force_kernel(const float4* __restrict__ posm, int64_t first_body,
+__global__ void __launch_bounds__(FORCE_THREADS, 6) force_kernel(const float4* __restrict__ posm,
+                                                             const uint32_t* __restrict__ keys, int64_t first_body,
                                                              int64_t body_count, const int4* __restrict__ cell_meta,
                                                              const int32_t* __restrict__ cell_child,
                                                              const float4* __restrict__ cell_com,
                                                              float4* __restrict__ acc, BhDevScalars* sc, float theta,
-                                                             float soft, float G) {
+                                                             float soft, float G, float split_alpha) {
     __shared__ WarpScratch s_warp[FORCE_WARPS];
     __shared__ float s_w2[BH_MAX_LEVEL + 1];
 
@@ -92,22 +108,61 @@ __global__ void __launch_bounds__(FORCE_THREADS) force_kernel(const float4* __re
         const int nb = (int)min((int64_t)BH_GROUP, end_body - (first_body + (int64_t)g * BH_GROUP));
         const float4 me = __ldg(posm + (valid ? my : end_body - 1));
 
-        // exact AABB of the group
-        float lox = me.x, loy = me.y, loz = me.z, hix = me.x, hiy = me.y, hiz = me.z;
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            lox = fminf(lox, __shfl_xor_sync(0xffffffffu, lox, o));
-            loy = fminf(loy, __shfl_xor_sync(0xffffffffu, loy, o));
-            loz = fminf(loz, __shfl_xor_sync(0xffffffffu, loz, o));
-            hix = fmaxf(hix, __shfl_xor_sync(0xffffffffu, hix, o));
-            hiy = fmaxf(hiy, __shfl_xor_sync(0xffffffffu, hiy, o));
-            hiz = fmaxf(hiz, __shfl_xor_sync(0xffffffffu, hiz, o));
+        // ---- split the chunk into spatially compact sub-groups (see the file header) ----
+        const uint32_t mykey = __ldg(keys + (valid ? my : end_body - 1));
+        const uint32_t nextkey = __shfl_down_sync(0xffffffffu, mykey, 1);
+        const int lvp = (lane + 1 < nb) ? bh_shared_digits(mykey, nextkey) : 99;   // pair (lane, lane+1)
+        const unsigned ox = bh_f2ord(me.x), oy = bh_f2ord(me.y), oz = bh_f2ord(me.z);
+        float ax = 0.f, ay = 0.f, az = 0.f;      // this lane's body, final
+        unsigned cuts = 0;                        // bit j: boundary between lanes j and j+1
+        unsigned acc_cells_w = 0, dir_bodies_w = 0;   // weighted by sub-group size
+        int ga = 0;
+        while (ga < nb) {
+        const unsigned pending = cuts >> ga;
+        int gb = pending ? ga + __ffs(pending) : nb;
+        float lox, loy, loz, hix, hiy, hiz;
+        {
+            const bool in = lane >= ga && lane < gb;
+            lox = bh_ord2f(__reduce_min_sync(0xffffffffu, in ? ox : 0xFFFFFFFFu));
+            loy = bh_ord2f(__reduce_min_sync(0xffffffffu, in ? oy : 0xFFFFFFFFu));
+            loz = bh_ord2f(__reduce_min_sync(0xffffffffu, in ? oz : 0xFFFFFFFFu));
+            hix = bh_ord2f(__reduce_max_sync(0xffffffffu, in ? ox : 0u));
+            hiy = bh_ord2f(__reduce_max_sync(0xffffffffu, in ? oy : 0u));
+            hiz = bh_ord2f(__reduce_max_sync(0xffffffffu, in ? oz : 0u));
         }
+        while (gb - ga >= 2 && split_alpha > 0.0f) {
+            const int cand = (lane >= ga && lane + 1 < gb) ? ((lvp << 5) | lane) : 0x7FFFFFFF;
+            const int best = __reduce_min_sync(0xffffffffu, cand);   // fewest shared digits, first such pair
+            if ((best >> 5) >= BH_MAX_LEVEL) break;
+            const int gk = (best & 31) + 1;
+            const bool inA = lane >= ga && lane < gk, inB = lane >= gk && lane < gb;
+            const float alx = bh_ord2f(__reduce_min_sync(0xffffffffu, inA ? ox : 0xFFFFFFFFu));
+            const float aly = bh_ord2f(__reduce_min_sync(0xffffffffu, inA ? oy : 0xFFFFFFFFu));
+            const float alz = bh_ord2f(__reduce_min_sync(0xffffffffu, inA ? oz : 0xFFFFFFFFu));
+            const float ahx = bh_ord2f(__reduce_max_sync(0xffffffffu, inA ? ox : 0u));
+            const float ahy = bh_ord2f(__reduce_max_sync(0xffffffffu, inA ? oy : 0u));
+            const float ahz = bh_ord2f(__reduce_max_sync(0xffffffffu, inA ? oz : 0u));
+            const float blx = bh_ord2f(__reduce_min_sync(0xffffffffu, inB ? ox : 0xFFFFFFFFu));
+            const float bly = bh_ord2f(__reduce_min_sync(0xffffffffu, inB ? oy : 0xFFFFFFFFu));
+            const float blz = bh_ord2f(__reduce_min_sync(0xffffffffu, inB ? oz : 0xFFFFFFFFu));
+            const float bhx = bh_ord2f(__reduce_max_sync(0xffffffffu, inB ? ox : 0u));
+            const float bhy = bh_ord2f(__reduce_max_sync(0xffffffffu, inB ? oy : 0u));
+            const float bhz = bh_ord2f(__reduce_max_sync(0xffffffffu, inB ? oz : 0u));
+            const float eA = __fadd_rn(__fadd_rn(__fsub_rn(ahx, alx), __fsub_rn(ahy, aly)), __fsub_rn(ahz, alz));
+            const float eB = __fadd_rn(__fadd_rn(__fsub_rn(bhx, blx), __fsub_rn(bhy, bly)), __fsub_rn(bhz, blz));
+            const float eAB = __fadd_rn(__fadd_rn(__fsub_rn(hix, lox), __fsub_rn(hiy, loy)), __fsub_rn(hiz, loz));
+            if (!(__fadd_rn(eA, eB) < __fmul_rn(split_alpha, eAB))) break;
+            cuts |= 1u << (gk - 1);
+            gb = gk;
+            lox = alx; loy = aly; loz = alz; hix = ahx; hiy = ahy; hiz = ahz;
+        }
+        const bool in_group = lane >= ga && lane < gb;
+        const int gsize = gb - ga;
         const float cx = __fmul_rn(__fadd_rn(lox, hix), 0.5f), hx = __fmul_rn(__fsub_rn(hix, lox), 0.5f);
         const float cy = __fmul_rn(__fadd_rn(loy, hiy), 0.5f), hy = __fmul_rn(__fsub_rn(hiy, loy), 0.5f);
         const float cz = __fmul_rn(__fadd_rn(loz, hiz), 0.5f), hz = __fmul_rn(__fsub_rn(hiz, loz), 0.5f);
 
-        float ax = 0.f, ay = 0.f, az = 0.f;
+        float tx = 0.f, ty = 0.f, tz = 0.f;      // this sub-group's pass (kept only by its lanes)
         int sp = 0, na = 0, nd = 0;
         unsigned acc_cells = 0, dir_bodies = 0;
         if (root >= 0) {
@@ -148,7 +203,7 @@ __global__ void __launch_bounds__(FORCE_THREADS) force_kernel(const float4* __re
             __syncwarp();
             if (na >= 32) {
                 na -= 32;
-                eval_tile(W.alist + na, me.x, me.y, me.z, soft, ax, ay, az);
+                eval_tile(W.alist + na, me.x, me.y, me.z, soft, tx, ty, tz);
                 __syncwarp();
             }
 
@@ -193,7 +248,7 @@ __global__ void __launch_bounds__(FORCE_THREADS) force_kernel(const float4* __re
                 nd -= 32;
                 W.tile[lane] = __ldg(posm + W.dlist[nd + lane]);
                 __syncwarp();
-                eval_tile(W.tile, me.x, me.y, me.z, soft, ax, ay, az);
+                eval_tile(W.tile, me.x, me.y, me.z, soft, tx, ty, tz);
                 __syncwarp();
             }
 
@@ -214,7 +269,7 @@ __global__ void __launch_bounds__(FORCE_THREADS) force_kernel(const float4* __re
                         nd -= 32;
                         W.tile[lane] = __ldg(posm + W.dlist[nd + lane]);
                         __syncwarp();
-                        eval_tile(W.tile, me.x, me.y, me.z, soft, ax, ay, az);
+                        eval_tile(W.tile, me.x, me.y, me.z, soft, tx, ty, tz);
                         __syncwarp();
                     }
                 }
@@ -225,19 +280,25 @@ __global__ void __launch_bounds__(FORCE_THREADS) force_kernel(const float4* __re
         if (na > 0) {
             if (lane >= na) W.alist[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
             __syncwarp();
-            eval_tile(W.alist, me.x, me.y, me.z, soft, ax, ay, az);
+            eval_tile(W.alist, me.x, me.y, me.z, soft, tx, ty, tz);
             __syncwarp();
         }
         if (nd > 0) {
             W.tile[lane] = lane < nd ? __ldg(posm + W.dlist[lane]) : make_float4(0.f, 0.f, 0.f, 0.f);
             __syncwarp();
-            eval_tile(W.tile, me.x, me.y, me.z, soft, ax, ay, az);
+            eval_tile(W.tile, me.x, me.y, me.z, soft, tx, ty, tz);
             __syncwarp();
         }
 
+        if (in_group) { ax = tx; ay = ty; az = tz; }
+        acc_cells_w += acc_cells * gsize;
+        dir_bodies_w += dir_bodies * gsize;
+        ga = gb;
+        }   // sub-groups of the chunk
+
         if (valid) acc[my] = make_float4(G * ax, G * ay, G * az, 0.f);
-        tot_cell += (unsigned long long)acc_cells * nb;
-        tot_body += (unsigned long long)dir_bodies * nb;
+        tot_cell += acc_cells_w;
+        tot_body += dir_bodies_w;
     }
 
     if (lane == 0) {
@@ -274,9 +335,9 @@ int bh_force_prepare() {
     return 0;
 }
 
-int bh_force_launch(const float4* posm, int64_t n, int64_t first_body, int64_t body_count,
+int bh_force_launch(const float4* posm, const uint32_t* keys, int64_t n, int64_t first_body, int64_t body_count,
                     const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
-                    float4* acc, BhDevScalars* sc, float theta, float softening, float G,
+                    float4* acc, BhDevScalars* sc, float theta, float softening, float G, float split_alpha,
                     int num_sms, cudaStream_t st) {
     if (body_count <= 0) return 0;
     reset_force_scalars<<<1, 32, 0, st>>>(sc);
@@ -290,7 +351,7 @@ int bh_force_launch(const float4* posm, int64_t n, int64_t first_body, int64_t b
     int64_t want = (ngroups + FORCE_WARPS - 1) / FORCE_WARPS;
     int64_t grid = (int64_t)(num_sms > 0 ? num_sms : BH_NUM_SMS_FALLBACK) * max_ctas;  // persistent: fill the chip once
     if (grid > want) grid = want;
-    force_kernel<<<(int)grid, FORCE_THREADS, 0, st>>>(posm, first_body, body_count, cell_meta, cell_child, cell_com, acc, sc,
-                                                     theta, softening, G);
+    force_kernel<<<(int)grid, FORCE_THREADS, 0, st>>>(posm, keys, first_body, body_count, cell_meta, cell_child, cell_com, acc,
+                                                     sc, theta, softening, G, split_alpha);
     return (int)cudaGetLastError();
 }

@@ -33,6 +33,7 @@ class BHParams(C.Structure):
         ("key_bits", C.c_int),
         ("leaf_cap", C.c_int),
         ("flags", C.c_int),
+        ("group_split", C.c_float),
     ]
 
 

@@ -498,20 +498,38 @@ void orc_tree_com(const float* posm, int64_t /*n*/, const int32_t* meta, const i
 // The interaction itself is bench:205-213 (f = G m / dist^3 with dist = sqrt(d2+soft)),
 // evaluated in float, accumulated in double.  acc: float4 per body (sorted order).
 // counts[0] = accepted (body,cell) pairs, counts[1] = direct (body,body) pairs.
+void orc_force_groups(const float* posm, int64_t n64, const float* bounds,
+                      const int32_t* meta, const int32_t* child, const float* com,
+                      int64_t M64, int32_t root, const int32_t* gstart, int ngroups, float theta, float soft, float G,
+                      float* acc, int64_t* counts, int32_t* group_entries /*nullable: list length per group*/);
+
 void orc_force_group(const float* posm, int64_t n64, const float* bounds,
                      const int32_t* meta, const int32_t* child, const float* com,
                      int64_t M64, int32_t root, int group, float theta, float soft, float G,
-                     float* acc, int64_t* counts) {
+                     float* acc, int64_t* counts, int32_t* group_entries) {
     const int n = (int)n64;
+    const int ngroups = (n + group - 1) / group;
+    std::vector<int32_t> gstart(ngroups + 1);
+    for (int g = 0; g <= ngroups; ++g) gstart[g] = std::min(n, g * group);
+    orc_force_groups(posm, n64, bounds, meta, child, com, M64, root, gstart.data(), ngroups, theta, soft, G, acc,
+                     counts, group_entries);
+}
+
+// Same, for explicit groups: group g = sorted bodies [gstart[g], gstart[g+1]).
+void orc_force_groups(const float* posm, int64_t n64, const float* bounds,
+                      const int32_t* meta, const int32_t* child, const float* com,
+                      int64_t M64, int32_t root, const int32_t* gstart, int ngroups, float theta, float soft, float G,
+                      float* acc, int64_t* counts, int32_t* group_entries) {
+    const int n = (int)n64; (void)n;
     const float root_w = bounds[3] - bounds[0];
     const float theta2 = theta * theta;
     float w2[MAX_LEVEL + 1];
     for (int L = 0; L <= MAX_LEVEL; ++L) w2[L] = w2_of_level(root_w, L);
-    const int ngroups = (n + group - 1) / group;
     int64_t ncell = 0, nbody = 0;
 #pragma omp parallel for schedule(dynamic, 16) reduction(+ : ncell, nbody)
     for (int g = 0; g < ngroups; ++g) {
-        const int b0 = g * group, b1 = std::min(n, b0 + group), nb = b1 - b0;
+        const int b0 = gstart[g], b1 = gstart[g + 1], nb = b1 - b0;
+        if (nb <= 0) continue;
         float lo[3] = {posm[4 * (int64_t)b0], posm[4 * (int64_t)b0 + 1], posm[4 * (int64_t)b0 + 2]};
         float hi[3] = {lo[0], lo[1], lo[2]};
         for (int i = b0 + 1; i < b1; ++i)
@@ -533,6 +551,7 @@ void orc_force_group(const float* posm, int64_t n64, const float* bounds,
             }
         };
         std::vector<int> stack;
+        int64_t entries = 0;
         if (root >= 0) stack.push_back(root);
         while (!stack.empty()) {
             int c = stack.back();
@@ -547,13 +566,13 @@ void orc_force_group(const float* posm, int64_t n64, const float* bounds,
             float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
             if (w2[L] < theta2 * (d2 + soft)) {
                 interact(cm[0], cm[1], cm[2], cm[3]);
-                ncell += nb;
+                ncell += nb; ++entries;
             } else if (bucket) {
                 for (int j = mt[0]; j < mt[0] + mt[1]; ++j) {
                     const float* q = posm + 4 * (int64_t)j;
                     interact(q[0], q[1], q[2], q[3]);
                 }
-                nbody += (int64_t)nb * mt[1];
+                nbody += (int64_t)nb * mt[1]; entries += mt[1];
             } else {
                 const int32_t* ch = child + 8 * (int64_t)c;
                 for (int q = 0; q < 8; ++q) {
@@ -562,7 +581,7 @@ void orc_force_group(const float* posm, int64_t n64, const float* bounds,
                     if (e < 0) {
                         const float* s = posm + 4 * (int64_t)(e & 0x7FFFFFFF);
                         interact(s[0], s[1], s[2], s[3]);
-                        nbody += nb;
+                        nbody += nb; ++entries;
                     } else stack.push_back(e);
                 }
             }
@@ -571,8 +590,61 @@ void orc_force_group(const float* posm, int64_t n64, const float* bounds,
             float* o = acc + 4 * (int64_t)(b0 + i);
             o[0] = (float)f[3 * i]; o[1] = (float)f[3 * i + 1]; o[2] = (float)f[3 * i + 2]; o[3] = 0.f;
         }
+        if (group_entries) group_entries[g] = (int32_t)std::min<int64_t>(entries, 0x7FFFFFFF);
     }
     if (counts) { counts[0] = ncell; counts[1] = nbody; }
+}
+
+// Traversal groups (engine: bh_force.cu "group splitting").  Bodies are taken in chunks of `chunk`
+// Morton-consecutive slots; a chunk that straddles a high-level cell boundary would get a huge
+// bounding box, so it is split recursively: cut the range at its coarsest key boundary (first
+// pair with the fewest shared digits) and keep the cut iff
+//     ext(A) + ext(B) < alpha * ext(A u B),   ext(box) = (hi-lo).x + (hi-lo).y + (hi-lo).z.
+// Returns the number of groups; gstart gets ngroups+1 entries.
+static float range_ext(const float* posm, int a, int b) {
+    float lo[3], hi[3];
+    for (int k = 0; k < 3; ++k) lo[k] = hi[k] = posm[4 * (int64_t)a + k];
+    for (int i = a + 1; i < b; ++i)
+        for (int k = 0; k < 3; ++k) {
+            lo[k] = fminf(lo[k], posm[4 * (int64_t)i + k]);
+            hi[k] = fmaxf(hi[k], posm[4 * (int64_t)i + k]);
+        }
+    return ((hi[0] - lo[0]) + (hi[1] - lo[1])) + (hi[2] - lo[2]);
+}
+
+int orc_make_groups(const float* posm, const uint32_t* keys, int64_t n64, int chunk, float alpha,
+                    int32_t* gstart) {
+    const int n = (int)n64;
+    int ng = 0;
+    for (int c0 = 0; c0 < n; c0 += chunk) {
+        const int c1 = std::min(n, c0 + chunk);
+        std::vector<std::pair<int, int>> todo;   // LIFO of ranges, processed left to right
+        todo.push_back({c0, c1});
+        while (!todo.empty()) {
+            auto [a, b] = todo.back();
+            todo.pop_back();
+            bool split = false;
+            if (b - a >= 2) {
+                int best = a, bestlv = 99;
+                for (int j = a; j < b - 1; ++j) {
+                    int lv = shared_digits(keys[j], keys[j + 1]);
+                    if (lv < bestlv) { bestlv = lv; best = j; }
+                }
+                const int k = best + 1;
+                if (bestlv < MAX_LEVEL) {
+                    float eA = range_ext(posm, a, k), eB = range_ext(posm, k, b), eAB = range_ext(posm, a, b);
+                    if (eA + eB < alpha * eAB) {
+                        split = true;
+                        todo.push_back({k, b});
+                        todo.push_back({a, k});
+                    }
+                }
+            }
+            if (!split) gstart[ng++] = a;
+        }
+    }
+    gstart[ng] = n;
+    return ng;
 }
 
 // Same tree, the reference's PER-BODY test exactly as bench:205-208 (accuracy study only).
@@ -671,7 +743,7 @@ void orc_energy(const float* posm, const float* vel, int64_t n, float soft, floa
 // One call = bounds, keys, stable sort, reorder, tree, com, group force, kick-drift-clamp.
 // Scratch outputs (any may be NULL) expose the intermediates of the LAST step.
 int orc_engine_step(float* posm, float* vel, int32_t* ids, int64_t n64, int nsteps,
-                    float G, float theta, float dt, float soft, float max_speed, int group,
+                    float G, float theta, float dt, float soft, float max_speed, int group, float split_alpha,
                     float* acc_out, uint32_t* keys_out, int32_t* perm_out, float* bounds_out,
                     int64_t* counts_out, double* phase_ms) {
     if (n64 <= 0 || n64 > (1 << 30)) return -1;
@@ -707,8 +779,10 @@ int orc_engine_step(float* posm, float* vel, int32_t* ids, int64_t n64, int nste
         double t4 = now_ms();
         int64_t counts[2] = {0, 0};
         std::fill(acc.begin(), acc.end(), 0.f);
-        orc_force_group(posm, n, b, meta.data(), child.data(), com.data(), M, root, group,
-                        theta, soft, G, acc.data(), counts);
+        std::vector<int32_t> gstart((size_t)n + 1);
+        const int ng = orc_make_groups(posm, keys.data(), n, group, split_alpha, gstart.data());
+        orc_force_groups(posm, n, b, meta.data(), child.data(), com.data(), M, root, gstart.data(), ng,
+                         theta, soft, G, acc.data(), counts, nullptr);
         double t5 = now_ms();
         if (s == nsteps - 1) {
             if (acc_out) std::memcpy(acc_out, acc.data(), 16 * (size_t)n);

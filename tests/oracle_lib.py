@@ -93,11 +93,31 @@ def tree_com(posm, meta, child, root):
     return mom[:M], com[:M]
 
 
-def force_group(posm, b, meta, child, com, root, group=32, theta=THETA, soft=SOFT, G_=G):
+def force_group(posm, b, meta, child, com, root, group=32, theta=THETA, soft=SOFT, G_=G, entries=None):
     n = len(posm)
     acc, counts = np.zeros((n, 4), np.float32), np.zeros(2, np.int64)
     lib().orc_force_group(_p(posm), C.c_int64(n), _p(b), _p(meta), _p(child), _p(com), C.c_int64(len(meta)),
-                          C.c_int32(root), group, f32(theta), f32(soft), f32(G_), _p(acc), _p(counts))
+                          C.c_int32(root), group, f32(theta), f32(soft), f32(G_), _p(acc), _p(counts), _p(entries))
+    return acc, counts
+
+
+SPLIT = 0.5   # bh_params.group_split default
+
+
+def make_groups(posm, sorted_keys, chunk=32, alpha=SPLIT):
+    """Traversal groups of the engine: chunks of the Morton order, cut at coarse key boundaries."""
+    n = len(posm)
+    gs = np.zeros(n + 1, np.int32)
+    ng = lib().orc_make_groups(_p(posm), _p(sorted_keys), C.c_int64(n), chunk, f32(alpha), _p(gs))
+    return gs[: ng + 1].copy()
+
+
+def force_groups(posm, b, meta, child, com, root, gstart, theta=THETA, soft=SOFT, G_=G, entries=None):
+    n = len(posm)
+    acc, counts = np.zeros((n, 4), np.float32), np.zeros(2, np.int64)
+    lib().orc_force_groups(_p(posm), C.c_int64(n), _p(b), _p(meta), _p(child), _p(com), C.c_int64(len(meta)),
+                           C.c_int32(root), _p(gstart), len(gstart) - 1, f32(theta), f32(soft), f32(G_), _p(acc),
+                           _p(counts), _p(entries))
     return acc, counts
 
 
@@ -122,14 +142,14 @@ def energy(posm, vel, soft=SOFT, G_=G):
     return ke.value, pe.value
 
 
-def engine_step(posm, vel, ids, nsteps=1, group=32, G_=G, theta=THETA, dt=DT, soft=SOFT, vmax=VMAX):
+def engine_step(posm, vel, ids, nsteps=1, group=32, G_=G, theta=THETA, dt=DT, soft=SOFT, vmax=VMAX, alpha=SPLIT):
     """Oracle-I: nsteps of the shipped algorithm on copies of the internal-layout state."""
     posm, vel, ids = posm.copy(), vel.copy(), ids.copy()
     n = len(posm)
     acc, keys, perm = np.zeros((n, 4), np.float32), np.zeros(n, np.uint32), np.zeros(n, np.int32)
     b, counts, ph = np.zeros(6, np.float32), np.zeros(3, np.int64), np.zeros(6)
     rc = lib().orc_engine_step(_p(posm), _p(vel), _p(ids), C.c_int64(n), nsteps, f32(G_), f32(theta), f32(dt), f32(soft),
-                               f32(vmax), group, _p(acc), _p(keys), _p(perm), _p(b), _p(counts), _p(ph))
+                               f32(vmax), group, f32(alpha), _p(acc), _p(keys), _p(perm), _p(b), _p(counts), _p(ph))
     assert rc == 0
     return dict(posm=posm, vel=vel, ids=ids, acc=acc, keys=keys, perm=perm, bounds=b, inter_cell=int(counts[0]),
                 inter_body=int(counts[1]), cells=int(counts[2]), phase_ms=ph)

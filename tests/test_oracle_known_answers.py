@@ -254,3 +254,41 @@ def test_energy_matches_numpy():
     want_pe = -0.5 * (np.triu(m[:, None] * m[None, :] / np.sqrt(d2), 1)).sum()
     want_ke = 0.5 * (m * (vel[:, :3].astype(np.float64) ** 2).sum(1)).sum()
     assert abs(pe - want_pe) / abs(want_pe) < 1e-12 and abs(ke - want_ke) / want_ke < 1e-12
+
+
+def test_group_splitting_rule():
+    """orc_make_groups: chunks are cut at their coarsest key boundary only when the parts are compact."""
+    # two tight clusters far apart, 16 bodies each, inside one 32-slot chunk -> exactly one cut at 16
+    rng = np.random.default_rng(3)
+    a = rng.uniform(0, 1, (16, 3)).astype(f)
+    b_ = (rng.uniform(0, 1, (16, 3)) + 900.0).astype(f)
+    pos = np.concatenate([a, b_])
+    soa = [pos[:, 0].copy(), pos[:, 1].copy(), pos[:, 2].copy(), np.zeros(32, f), np.zeros(32, f), np.zeros(32, f), np.ones(32, f)]
+    posm, vel, ids = O.soa_to_internal(soa)
+    bb = O.bounds(*soa[:3])
+    keys, idx = O.morton_keys(*soa[:3], bb)
+    ks, perm = O.stable_sort(keys, idx)
+    ps = np.ascontiguousarray(posm[perm])
+    assert O.make_groups(ps, ks, 32, 0.5).tolist() == [0, 16, 32]
+    assert O.make_groups(ps, ks, 32, 0.0).tolist() == [0, 32]          # alpha 0 disables the rule
+    # a uniform blob is left alone
+    soa2 = [rng.uniform(-1, 1, 64).astype(f) for _ in range(3)] + [np.zeros(64, f)] * 3 + [np.ones(64, f)]
+    posm2, _, _ = O.soa_to_internal(soa2)
+    b2 = O.bounds(*soa2[:3])
+    k2, i2 = O.morton_keys(*soa2[:3], b2)
+    ks2, p2 = O.stable_sort(k2, i2)
+    g = O.make_groups(np.ascontiguousarray(posm2[p2]), ks2, 32, 0.5)
+    assert g[0] == 0 and g[-1] == 64 and len(g) <= 4
+    # splitting never changes which sources a body sees by more than the acceptance test allows:
+    # forces with and without the rule agree to the multipole error
+    soa3 = _random_soa(3000, 5, clustered=True)
+    posm3, _, _ = O.soa_to_internal(soa3)
+    b3 = O.bounds(*soa3[:3])
+    k3, i3 = O.morton_keys(*soa3[:3], b3)
+    ks3, p3 = O.stable_sort(k3, i3)
+    ps3 = np.ascontiguousarray(posm3[p3])
+    meta, child, root = O.tree_build(ks3)
+    mom, com = O.tree_com(ps3, meta, child, root)
+    a0, c0 = O.force_groups(ps3, b3, meta, child, com, root, O.make_groups(ps3, ks3, 32, 0.0))
+    a1, c1 = O.force_groups(ps3, b3, meta, child, com, root, O.make_groups(ps3, ks3, 32, 0.5))
+    assert O.rel_rms(a1[:, :3], a0[:, :3]) < 5e-3
