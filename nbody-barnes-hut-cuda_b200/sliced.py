@@ -1,0 +1,173 @@
+"""Multi-GPU Morton-range slices (BASELINE.json north_star, SURVEY §8e "replicated tree").
+
+One process per GPU (torchrun).  Every rank holds the full state; each step every rank
+  1. runs the step graph: bounds, keys, sort, reorder and tree on ALL bodies (deterministic, so the
+     trees are identical without a broadcast), traversal + kick-drift only on its own slice of the
+     freshly sorted order, written into the current-state arrays;
+  2. all-gathers the updated slices (posm 16 B, vel 16 B, ids 4 B per body) in place over
+     NCCL/NVLink so every rank again holds the full state.
+Slices are whole 32-body chunks, so chunk boundaries — and therefore every acceptance decision and
+every float — are identical to the single-GPU run.
+
+torch / torch.distributed are plumbing only (device views of the context's buffers + the collective).
+"""
+from __future__ import annotations
+
+import time
+
+import numpy as np
+
+GROUP = 32
+
+
+def slice_bounds(n: int, rank: int, world: int):
+    """Mirror of default_slice() in csrc/bh_engine.cu: (first, count, padded_per_rank)."""
+    groups = (n + GROUP - 1) // GROUP
+    per = (groups + world - 1) // world * GROUP
+    first = min(n, rank * per)
+    last = min(n, (rank + 1) * per)
+    return first, last - first, per
+
+
+class _DevView:
+    """Zero-copy torch view of a raw device pointer via the CUDA array interface."""
+
+    def __init__(self, ptr: int, shape, typestr: str):
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": typestr, "data": (int(ptr), False), "version": 3}
+
+
+def device_views(torch, state: dict, per: int, world: int, device):
+    total = per * world
+    posm = torch.as_tensor(_DevView(state["posm"], (total, 4), "<f4"), device=device)
+    vel = torch.as_tensor(_DevView(state["vel"], (total, 4), "<f4"), device=device)
+    ids = torch.as_tensor(_DevView(state["ids"], (total,), "<i4"), device=device)
+    return posm, vel, ids
+
+
+def allgather_slices(dist, tensors, rank: int, per: int):
+    """In-place all-gather: rank r's rows [r*per, (r+1)*per) of each full tensor."""
+    for full in tensors:
+        dist.all_gather_into_tensor(full, full[rank * per:(rank + 1) * per])
+
+
+class SlicedSimulation:
+    def __init__(self, bh, soa, rank: int, world: int, local: int, dist, flags: int = 0, **params):
+        import torch
+
+        self.torch, self.dist, self.rank, self.world = torch, dist, rank, world
+        self.n = len(soa[0])
+        self.first, self.count, self.per = slice_bounds(self.n, rank, world)
+        self.device = torch.device(f"cuda:{local}")
+        self.eng = bh.BHEngine(self.n, device=local, flags=flags, **params)
+        self.eng.set_slice(rank, world)
+        self.eng.load_soa(*soa)
+        st = self.eng.state_ptrs()
+        assert (st["first"], st["count"]) == (self.first, self.count), "slice arithmetic differs from the C side"
+        self.views = device_views(torch, st, self.per, world, self.device)
+
+    def step(self, nsteps: int = 1):
+        stream = self.torch.cuda.current_stream().cuda_stream
+        for _ in range(nsteps):
+            self.eng.simulation_step(1, stream)
+            allgather_slices(self.dist, self.views, self.rank, self.per)
+
+    def close(self):
+        self.eng.close()
+
+
+def run_sliced_bench(args, w, bh, dist, rank, world, local):
+    import torch
+
+    import bench
+
+    soa = bench.make_ic(bh, w)
+    n = w["n"]
+    sim = SlicedSimulation(bh, soa, rank, world, local, dist)
+    dev = sim.device
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    sim.step(args.warmup)
+    barrier()
+    sim.eng.check_device_error()
+    clocks = bench.ClockSampler(local)
+    clocks.start()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    a.record()
+    sim.step(args.steps)
+    b.record()
+    barrier()
+    ms = torch.tensor([a.elapsed_time(b)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ck = clocks.stop()
+    inter = torch.tensor([float(sim.eng.stat(bh.STAT.INTERACTIONS_CELL) + sim.eng.stat(bh.STAT.INTERACTIONS_BODY))],
+                         device=dev, dtype=torch.float64)
+    dist.all_reduce(inter)
+
+    # per-phase split on this rank (timer mode, separate context) — shows the replicated (Amdahl) part
+    simt = SlicedSimulation(bh, soa, rank, world, local, dist, flags=2)
+    simt.step(3)
+    psteps = 5
+    acc = {}
+    for _ in range(psteps):
+        simt.eng.simulation_step(1, torch.cuda.current_stream().cuda_stream)
+        for k, v in simt.eng.phase_ms().items():
+            acc[k] = acc.get(k, 0.0) + v / psteps
+        allgather_slices(dist, simt.views, rank, simt.per)
+    simt.close()
+    ag0, ag1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ag0.record()
+    for _ in range(10):
+        allgather_slices(dist, sim.views, rank, sim.per)
+    ag1.record()
+    barrier()
+    allgather_ms = ag0.elapsed_time(ag1) / 10
+
+    # e2e: every rank uploads the full host state (its own PCIe link), one sliced step, all-gather,
+    # rank 0 reads the full state back
+    pinned = [torch.from_numpy(x.copy()).pin_memory() for x in soa]
+    harr = [t.numpy() for t in pinned]
+    out = [np.zeros(n, np.float32) for _ in range(6)]
+    esteps = 5
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def e2e_once():
+        sim.eng.load_soa(*harr)
+        sim.eng.simulation_step(1, stream)
+        allgather_slices(dist, sim.views, rank, sim.per)
+        torch.cuda.synchronize()
+        if rank == 0:
+            sim.eng.read_soa(want_acc=False)
+
+    e2e_once()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(esteps):
+        e2e_once()
+    barrier()
+    e2e_s = torch.tensor([(time.perf_counter() - t0) / esteps], device=dev, dtype=torch.float64)
+    dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    sim.close()
+    total_ms = float(ms.item())
+    line = {
+        "metric": "body-steps/s", "value": n * args.steps / (total_ms * 1e-3), "unit": "body-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["desc"], "n_bodies": n, "theta": 0.5, "G": 0.5, "dt": 0.02,
+                   "softening": 50.0, "max_speed": 500.0, "group": 32,
+                   "parallelism": f"morton-slices x{world}: replicated sort+tree, sliced traversal, in-place NCCL all-gather of 36 B/body",
+                   "l2": "state larger than L2 at 16M bodies (3.2 GB context); no flush between steps"},
+        "interactions_per_body": float(inter.item()) / n,
+        "interactions_per_s": float(inter.item()) * args.steps / (total_ms * 1e-3),
+        "phase_ms_rank0": {k: round(v, 4) for k, v in acc.items()}, "allgather_ms": allgather_ms,
+        "e2e": {"value": n / float(e2e_s.item()), "unit": "body-steps/s", "h2d_bytes_per_step": 28 * n * world,
+                "d2h_bytes_per_step": 24 * n, "ms_per_step": float(e2e_s.item()) * 1e3,
+                "api": "every rank bh_import_soa_host(full state), 1 sliced step, all-gather, rank 0 bh_export_soa_host"},
+        "gpu_launches": bench.LAUNCHES_PER_STEP * args.steps * world, "clocks": ck,
+    }
+    dist.destroy_process_group()
+    return line if rank == 0 else None

@@ -745,7 +745,11 @@ void orc_energy(const float* posm, const float* vel, int64_t n, float soft, floa
 int orc_engine_step(float* posm, float* vel, int32_t* ids, int64_t n64, int nsteps,
                     float G, float theta, float dt, float soft, float max_speed, int group, float split_alpha,
                     float* acc_out, uint32_t* keys_out, int32_t* perm_out, float* bounds_out,
-                    int64_t* counts_out, double* phase_ms) {
+                    int64_t* counts_out, double* phase_ms, int64_t slice_first, int64_t slice_count) {
+    // slice_count < 0: the whole range.  Otherwise only sorted slots [slice_first, slice_first+slice_count)
+    // are traversed and integrated (multi-GPU Morton slices, engine: bh_set_slice); the other slots of
+    // posm/vel/ids are left holding this step's sorted pre-drift state, to be overwritten by the
+    // owners' all-gather.  slice_first must be a multiple of `group`.
     if (n64 <= 0 || n64 > (1 << 30)) return -1;
     const int n = (int)n64;
     std::vector<float> sx(n), sy(n), sz(n), p2(4 * (size_t)n), v2(4 * (size_t)n), acc(4 * (size_t)n);
@@ -780,8 +784,13 @@ int orc_engine_step(float* posm, float* vel, int32_t* ids, int64_t n64, int nste
         int64_t counts[2] = {0, 0};
         std::fill(acc.begin(), acc.end(), 0.f);
         std::vector<int32_t> gstart((size_t)n + 1);
-        const int ng = orc_make_groups(posm, keys.data(), n, group, split_alpha, gstart.data());
-        orc_force_groups(posm, n, b, meta.data(), child.data(), com.data(), M, root, gstart.data(), ng,
+        int ng = orc_make_groups(posm, keys.data(), n, group, split_alpha, gstart.data());
+        const int s0 = slice_count < 0 ? 0 : (int)slice_first;
+        const int s1 = slice_count < 0 ? n : (int)(slice_first + slice_count);
+        int g0 = 0, g1 = ng;
+        while (g0 < ng && gstart[g0] < s0) ++g0;
+        while (g1 > g0 && gstart[g1 - 1] >= s1) --g1;
+        orc_force_groups(posm, n, b, meta.data(), child.data(), com.data(), M, root, gstart.data() + g0, g1 - g0,
                          theta, soft, G, acc.data(), counts, nullptr);
         double t5 = now_ms();
         if (s == nsteps - 1) {
@@ -793,7 +802,7 @@ int orc_engine_step(float* posm, float* vel, int32_t* ids, int64_t n64, int nste
         }
         const float vmax2 = max_speed * max_speed;
 #pragma omp parallel for schedule(static)
-        for (int i = 0; i < n; ++i) {  // bench:227-249, FMA pattern of SURVEY R12
+        for (int i = s0; i < s1; ++i) {  // bench:227-249, FMA pattern of SURVEY R12
             float* p = posm + 4 * (size_t)i; float* v = vel + 4 * (size_t)i; const float* a = &acc[4 * (size_t)i];
             float x = fmaf(a[0], dt, v[0]), y = fmaf(a[1], dt, v[1]), z = fmaf(a[2], dt, v[2]);
             float q = fmaf(z, z, fmaf(x, x, y * y));

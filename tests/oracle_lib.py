@@ -142,14 +142,16 @@ def energy(posm, vel, soft=SOFT, G_=G):
     return ke.value, pe.value
 
 
-def engine_step(posm, vel, ids, nsteps=1, group=32, G_=G, theta=THETA, dt=DT, soft=SOFT, vmax=VMAX, alpha=SPLIT):
+def engine_step(posm, vel, ids, nsteps=1, group=32, G_=G, theta=THETA, dt=DT, soft=SOFT, vmax=VMAX, alpha=SPLIT,
+                slice_first=0, slice_count=-1):
     """Oracle-I: nsteps of the shipped algorithm on copies of the internal-layout state."""
     posm, vel, ids = posm.copy(), vel.copy(), ids.copy()
     n = len(posm)
     acc, keys, perm = np.zeros((n, 4), np.float32), np.zeros(n, np.uint32), np.zeros(n, np.int32)
     b, counts, ph = np.zeros(6, np.float32), np.zeros(3, np.int64), np.zeros(6)
     rc = lib().orc_engine_step(_p(posm), _p(vel), _p(ids), C.c_int64(n), nsteps, f32(G_), f32(theta), f32(dt), f32(soft),
-                               f32(vmax), group, f32(alpha), _p(acc), _p(keys), _p(perm), _p(b), _p(counts), _p(ph))
+                               f32(vmax), group, f32(alpha), _p(acc), _p(keys), _p(perm), _p(b), _p(counts), _p(ph),
+                               C.c_int64(slice_first), C.c_int64(slice_count))
     assert rc == 0
     return dict(posm=posm, vel=vel, ids=ids, acc=acc, keys=keys, perm=perm, bounds=b, inter_cell=int(counts[0]),
                 inter_body=int(counts[1]), cells=int(counts[2]), phase_ms=ph)

@@ -219,3 +219,49 @@ def test_million_body_invariants(bh):
         out = eng.read_soa()
         err = O.rel_rms(np.stack(out[6:9], 1)[sample], eng.direct_sample(sample))
         assert err < 1.3e-2                                        # 1.3e-2 per-body test on this disk
+
+
+def test_two_morton_slices_emulated_on_one_gpu_equal_the_full_run(bh):
+    """Multi-GPU path with fewer GPUs than ranks: two contexts on one device play ranks 0 and 1 of 2;
+    the all-gather is emulated by device copies.  Must equal the single-context run bit for bit."""
+    import torch
+
+    from nbody_barnes_hut_cuda_b200.sliced import device_views, slice_bounds
+
+    n, steps = 50001, 3
+    soa = make_case(bh, "disk", n)
+    with bh.BHEngine(n) as ref:
+        ref.load_soa(*soa)
+        ref.simulation_step(steps)
+        want = (ref.debug_get(bh.DBG.POSM), ref.debug_get(bh.DBG.VEL), ref.debug_get(bh.DBG.IDS))
+        want_inter = ref.stat(bh.STAT.INTERACTIONS_CELL) + ref.stat(bh.STAT.INTERACTIONS_BODY)
+    dev = torch.device("cuda:0")
+    engs, views, bounds = [], [], []
+    for r in range(2):
+        e = bh.BHEngine(n)
+        e.set_slice(r, 2)
+        e.load_soa(*soa)
+        st = e.state_ptrs()
+        first, count, per = slice_bounds(n, r, 2)
+        assert (st["first"], st["count"]) == (first, count)
+        engs.append(e)
+        bounds.append((first, count, per))
+        views.append(device_views(torch, st, per, 2, dev))
+    inter = 0
+    for s in range(steps):
+        for e in engs:
+            e.simulation_step(1)
+        torch.cuda.synchronize()
+        for r in range(2):
+            first, count, per = bounds[r]
+            for mine, other in zip(views[r], views[1 - r]):
+                other[first:first + count] = mine[first:first + count]
+        torch.cuda.synchronize()
+    inter = sum(e.stat(bh.STAT.INTERACTIONS_CELL) + e.stat(bh.STAT.INTERACTIONS_BODY) for e in engs)
+    for e in engs:
+        e.check_device_error()
+        got = (e.debug_get(bh.DBG.POSM), e.debug_get(bh.DBG.VEL), e.debug_get(bh.DBG.IDS))
+        assert got[0].tobytes() == want[0].tobytes() and got[1].tobytes() == want[1].tobytes()
+        assert (got[2] == want[2]).all()
+        e.close()
+    assert inter == want_inter
