@@ -208,6 +208,8 @@ int  bh_ic_plummer(int64_t n, uint64_t seed, float scale_a, float rcut_in_a,
 
 /* Box probes used as roofline denominators by bench.py. */
 int  bh_probe_fp32_tflops(int device, float* tflops);
+/* same with packed fma.rn.f32x2 (two FMAs per issued instruction) */
+int  bh_probe_fp32x2_tflops(int device, float* tflops);
 int  bh_probe_hbm_gbs(int device, float* gbs);
 
 #ifdef __cplusplus

@@ -20,6 +20,7 @@ from .engine import (  # noqa: F401
     lib,
     library_path,
     probe_fp32_tflops,
+    probe_fp32x2_tflops,
     probe_hbm_gbs,
     sort_pairs_u32,
 )

@@ -29,7 +29,12 @@ struct BhDevScalars {        // one small device struct, zeroed/filled by kernel
     unsigned long long inter_body;
     unsigned int max_stack;
     unsigned int bbox_enc[6];    // order-preserving uint encoding of min/max during reduction
-    unsigned int pad;
+    // heavy-first scheduling of traversal chunks (bh_force.cu): chunks whose interaction list was long
+    // in the previous step are handed out first in this one (costs are temporally coherent)
+    unsigned int epoch;          // force launches since import; parity selects the list being read
+    unsigned int heavy_n[2];
+    unsigned int heavy_thresh;   // list entries above which a chunk is recorded as heavy
+    unsigned long long entries_total;   // list entries of the last force launch (all sub-groups)
 };
 
 // ---- small device helpers ---------------------------------------------------------------
@@ -86,10 +91,11 @@ int bh_tree_launch(const uint32_t* keys, int64_t n, int2* pair_info, int32_t* pa
 int bh_com_launch(const float4* posm, int64_t n, const int4* cell_meta, const int32_t* cell_child,
                   int32_t* cell_arrive, float4* cell_mom, float4* cell_com,
                   BhDevScalars* sc, cudaStream_t st);
+// heavy_list: 2 * max_chunks u32, heavy_flag: 2 * max_chunks bytes (see BhDevScalars::epoch)
 int bh_force_launch(const float4* posm, const uint32_t* keys, int64_t n, int64_t first_body, int64_t body_count,
                     const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
-                    float4* acc, BhDevScalars* sc, float theta, float softening, float G, float split_alpha,
-                    int num_sms, cudaStream_t st);
+                    float4* acc, BhDevScalars* sc, uint32_t* heavy_list, uint8_t* heavy_flag, int64_t max_chunks,
+                    float theta, float softening, float G, float split_alpha, int num_sms, cudaStream_t st);
 int bh_force_prepare();
 int bh_integrate_launch(const float4* posm_s, const float4* vel_s, const int32_t* ids_s, const float4* acc,
                         float4* posm, float4* vel, int32_t* ids, int64_t first_body, int64_t body_count,

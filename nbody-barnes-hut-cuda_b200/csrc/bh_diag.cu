@@ -79,6 +79,33 @@ __global__ void __launch_bounds__(256) fma_probe_kernel(float* out, int iters, f
     if (s == 12345.678f) out[0] = s;  // keep the chains alive
 }
 
+// same with packed fma.rn.f32x2 (sm_100 FFMA2): two FMAs per issued instruction
+__global__ void __launch_bounds__(256) fma2_probe_kernel(float* out, int iters, float a, float b) {
+    unsigned long long pa, pb, r[8];
+    asm("mov.b64 %0, {%1, %1};" : "=l"(pa) : "f"(a));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(pb) : "f"(b));
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float v = (float)(threadIdx.x + k);
+        asm("mov.b64 %0, {%1, %1};" : "=l"(r[k]) : "f"(v));
+    }
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 16; ++u) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) asm volatile("fma.rn.f32x2 %0, %0, %1, %2;" : "+l"(r[k]) : "l"(pa), "l"(pb));
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        float lo, hi;
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(r[k]));
+        s += lo + hi;
+    }
+    if (s == 12345.678f) out[0] = s;
+}
+
 __global__ void __launch_bounds__(256) copy_probe_kernel(const float4* __restrict__ src, float4* __restrict__ dst, int64_t n4) {
     for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n4; i += (int64_t)gridDim.x * 256) dst[i] = src[i];
 }
@@ -121,6 +148,35 @@ extern "C" int bh_probe_fp32_tflops(int device, float* tflops) {
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
         double flops = 2.0 * 8 * 16 * (double)iters * 256.0 * blocks;
+        float tf = (float)(flops / (ms * 1e-3) / 1e12);
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(d_out);
+    *tflops = best;
+    return 0;
+}
+
+extern "C" int bh_probe_fp32x2_tflops(int device, float* tflops) {
+    if (!tflops) return BH_E_INVAL;
+    BH_CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    BH_CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    float* d_out = nullptr;
+    BH_CUDA_TRY(cudaMalloc(&d_out, 4));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    const int blocks = prop.multiProcessorCount * 8, iters = 4096;
+    float best = 0.f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        fma2_probe_kernel<<<blocks, 256>>>(d_out, iters, 1.0000001f, 1e-7f);
+        cudaEventRecord(e1);
+        cudaError_t e = cudaEventSynchronize(e1);
+        if (e != cudaSuccess) { cudaFree(d_out); return (int)e; }
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        double flops = 2.0 * 2 * 8 * 16 * (double)iters * 256.0 * blocks;
         float tf = (float)(flops / (ms * 1e-3) / 1e12);
         if (rep > 0 && tf > best) best = tf;
     }

@@ -42,6 +42,9 @@ struct bh_ctx {
     int4* cell_meta = nullptr;
     int32_t *cell_child = nullptr, *cell_arrive = nullptr;
     float4 *cell_mom = nullptr, *cell_com = nullptr;
+    uint32_t* heavy_list = nullptr;   // 2 * max_chunks
+    uint8_t* heavy_flag = nullptr;    // 2 * max_chunks
+    int64_t max_chunks = 0;
     BhDevScalars* sc = nullptr;
     float* stage = nullptr;  // 10 * n_alloc floats, lazily allocated for the host-pointer entry points
     double* d_scratch = nullptr;
@@ -66,7 +69,7 @@ void free_all(bh_ctx* c) {
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     void* ptrs[] = {c->posm, c->vel, c->posm_s, c->vel_s, c->acc, c->ids, c->ids_s, c->keys0, c->keys1, c->vals0,
                     c->vals1, c->sort_tmp, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
-                    c->cell_arrive, c->cell_mom, c->cell_com, c->sc, c->stage, c->d_scratch};
+                    c->cell_arrive, c->cell_mom, c->cell_com, c->sc, c->stage, c->d_scratch, c->heavy_list, c->heavy_flag};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -109,8 +112,8 @@ int phase_com(bh_ctx* c, cudaStream_t st) {
 
 int phase_force(bh_ctx* c, cudaStream_t st) {
     return bh_force_launch(c->posm_s, c->keys0, c->n, c->slice_first, c->slice_count, c->cell_meta, c->cell_child,
-                           c->cell_com, c->acc, c->sc, c->prm.theta, c->prm.softening, c->prm.G, c->prm.group_split,
-                           c->num_sms, st);
+                           c->cell_com, c->acc, c->sc, c->heavy_list, c->heavy_flag, c->max_chunks, c->prm.theta,
+                           c->prm.softening, c->prm.G, c->prm.group_split, c->num_sms, st);
 }
 
 int phase_update(bh_ctx* c, cudaStream_t st) {
@@ -204,11 +207,14 @@ int bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device) 
     TRYA(dev_alloc(&c->cell_meta, na)); TRYA(dev_alloc(&c->cell_child, na * 8)); TRYA(dev_alloc(&c->cell_arrive, na));
     TRYA(dev_alloc(&c->cell_mom, na)); TRYA(dev_alloc(&c->cell_com, na));
     TRYA(dev_alloc(&c->sc, 1)); TRYA(dev_alloc(&c->d_scratch, 8));
+    c->max_chunks = (int64_t)(na / BH_GROUP + 1);
+    TRYA(dev_alloc(&c->heavy_list, 2 * (size_t)c->max_chunks)); TRYA(dev_alloc(&c->heavy_flag, 2 * (size_t)c->max_chunks));
     TRYA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
     for (auto& ev : c->ev) TRYA(cudaEventCreate(&ev));
 #undef TRYA
     if (e == cudaSuccess) e = cudaMemset(c->sc, 0, sizeof(BhDevScalars));
     if (e == cudaSuccess) e = cudaMemset(c->acc, 0, na * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMemset(c->heavy_flag, 0, 2 * (size_t)c->max_chunks);
     if (e != cudaSuccess) { free_all(c); delete c; return (int)e; }
     *out = c;
     return 0;
@@ -228,6 +234,10 @@ int bh_import_soa(bh_ctx* c, const float* px, const float* py, const float* pz, 
     BH_CUDA_TRY(cudaSetDevice(c->device));
     c->n = n; c->steps = 0; c->have_sorted = false;
     default_slice(c);
+    // scheduling history of the previous body set is meaningless now
+    BH_CUDA_TRY(cudaMemsetAsync((char*)c->sc + offsetof(BhDevScalars, epoch), 0,
+                                sizeof(BhDevScalars) - offsetof(BhDevScalars, epoch), (cudaStream_t)stream));
+    BH_CUDA_TRY(cudaMemsetAsync(c->heavy_flag, 0, 2 * (size_t)c->max_chunks, (cudaStream_t)stream));
     int e = bh_import_launch(px, py, pz, vx, vy, vz, mass, n, c->posm, c->vel, c->ids, (cudaStream_t)stream);
     if (e) return e;
     c->have_state = true;
@@ -260,7 +270,14 @@ int bh_import_soa_host(bh_ctx* c, const float* px, const float* py, const float*
 int bh_set_slice(bh_ctx* c, int rank, int world) {
     if (!c || world < 1 || rank < 0 || rank >= world) return BH_E_INVAL;
     c->rank = rank; c->world = world;
-    if (c->have_state) default_slice(c);
+    if (c->have_state) {
+        default_slice(c);
+        BH_CUDA_TRY(cudaSetDevice(c->device));
+        BH_CUDA_TRY(cudaDeviceSynchronize());
+        // chunk indices are relative to the slice: drop the heavy-chunk history
+        BH_CUDA_TRY(cudaMemset((char*)c->sc + offsetof(BhDevScalars, epoch), 0, sizeof(BhDevScalars) - offsetof(BhDevScalars, epoch)));
+        BH_CUDA_TRY(cudaMemset(c->heavy_flag, 0, 2 * (size_t)c->max_chunks));
+    }
     return 0;
 }
 

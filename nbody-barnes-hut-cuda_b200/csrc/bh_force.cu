@@ -73,8 +73,10 @@ __global__ void __launch_bounds__(FORCE_THREADS, 6) force_kernel(const float4* _
                                                              int64_t body_count, const int4* __restrict__ cell_meta,
                                                              const int32_t* __restrict__ cell_child,
                                                              const float4* __restrict__ cell_com,
-                                                             float4* __restrict__ acc, BhDevScalars* sc, float theta,
-                                                             float soft, float G, float split_alpha) {
+                                                             float4* __restrict__ acc, BhDevScalars* sc,
+                                                             uint32_t* __restrict__ heavy_list,
+                                                             uint8_t* __restrict__ heavy_flag, int64_t max_chunks,
+                                                             float theta, float soft, float G, float split_alpha) {
     __shared__ WarpScratch s_warp[FORCE_WARPS];
     __shared__ float s_w2[BH_MAX_LEVEL + 1];
 
@@ -94,12 +96,29 @@ __global__ void __launch_bounds__(FORCE_THREADS, 6) force_kernel(const float4* _
     const int64_t ngroups = (body_count + BH_GROUP - 1) / BH_GROUP;
     const int64_t end_body = first_body + body_count;
 
-    unsigned long long tot_cell = 0, tot_body = 0;
+    unsigned long long tot_cell = 0, tot_body = 0, tot_entries = 0;
     unsigned max_sp = 0;
+
+    // heavy-first scheduling: tickets [0, heavy_n) replay last step's heavy chunks, the rest walk the
+    // chunks in Morton order and skip the ones already handed out
+    const unsigned cur = sc->epoch & 1u, nxt = cur ^ 1u;
+    const unsigned heavy_n = min(sc->heavy_n[cur], (unsigned)min(ngroups, max_chunks));
+    const unsigned heavy_thresh = sc->heavy_thresh;
+    const uint32_t* list_cur = heavy_list + (size_t)cur * max_chunks;
+    const uint8_t* flag_cur = heavy_flag + (size_t)cur * max_chunks;
+    uint32_t* list_nxt = heavy_list + (size_t)nxt * max_chunks;
+    uint8_t* flag_nxt = heavy_flag + (size_t)nxt * max_chunks;
 
     for (;;) {
         unsigned g = 0;
-        if (lane == 0) g = atomicAdd(&sc->group_ticket, 1u);
+        if (lane == 0) {
+            for (;;) {
+                const unsigned t = atomicAdd(&sc->group_ticket, 1u);
+                if (t < heavy_n) { g = list_cur[t]; break; }
+                g = t - heavy_n;
+                if ((int64_t)g >= ngroups || !flag_cur[g]) break;   // flagged chunks were served from the list
+            }
+        }
         g = __shfl_sync(0xffffffffu, g, 0);
         if ((int64_t)g >= ngroups) break;
 
@@ -116,6 +135,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, 6) force_kernel(const float4* _
         float ax = 0.f, ay = 0.f, az = 0.f;      // this lane's body, final
         unsigned cuts = 0;                        // bit j: boundary between lanes j and j+1
         unsigned acc_cells_w = 0, dir_bodies_w = 0;   // weighted by sub-group size
+        unsigned chunk_entries = 0;
         int ga = 0;
         while (ga < nb) {
         const unsigned pending = cuts >> ga;
@@ -293,8 +313,14 @@ __global__ void __launch_bounds__(FORCE_THREADS, 6) force_kernel(const float4* _
         if (in_group) { ax = tx; ay = ty; az = tz; }
         acc_cells_w += acc_cells * gsize;
         dir_bodies_w += dir_bodies * gsize;
+        chunk_entries += acc_cells + dir_bodies;
         ga = gb;
         }   // sub-groups of the chunk
+        tot_entries += chunk_entries;
+        if (lane == 0 && chunk_entries > heavy_thresh && (int64_t)g < max_chunks) {
+            const unsigned slot = atomicAdd(&sc->heavy_n[nxt], 1u);
+            if ((int64_t)slot < max_chunks) { list_nxt[slot] = g; flag_nxt[g] = 1; }
+        }
 
         if (valid) acc[my] = make_float4(G * ax, G * ay, G * az, 0.f);
         tot_cell += acc_cells_w;
@@ -304,17 +330,35 @@ __global__ void __launch_bounds__(FORCE_THREADS, 6) force_kernel(const float4* _
     if (lane == 0) {
         if (tot_cell) atomicAdd(&sc->inter_cell, tot_cell);
         if (tot_body) atomicAdd(&sc->inter_body, tot_body);
+        if (tot_entries) atomicAdd(&sc->entries_total, tot_entries);
         atomicMax(&sc->max_stack, max_sp);
     }
 }
 
-__global__ void reset_force_scalars(BhDevScalars* sc) {
+__global__ void __launch_bounds__(256) reset_force_scalars(BhDevScalars* sc, uint8_t* heavy_flag, int64_t max_chunks,
+                                                          int64_t ngroups) {
+    // one CTA: advance the epoch, derive the heavy threshold from the previous launch, clear the list
+    // and flags that this launch will fill
+    __shared__ unsigned s_nxt;
     if (threadIdx.x == 0) {
+        sc->epoch += 1u;
+        const unsigned nxt = (sc->epoch & 1u) ^ 1u;
+        s_nxt = nxt;
+        const unsigned long long prev = sc->entries_total;
+        // 2.5x the mean list length of the previous launch; nothing is heavy on the first one
+        sc->heavy_thresh = prev ? (unsigned)min((unsigned long long)0x7FFFFFFF, prev * 5ull / (2ull * (unsigned long long)ngroups) + 1ull)
+                                : 0x7FFFFFFFu;
+        sc->heavy_n[nxt] = 0;
+        sc->entries_total = 0;
         sc->group_ticket = 0;
         sc->inter_cell = 0;
         sc->inter_body = 0;
         sc->max_stack = 0;
     }
+    __syncthreads();
+    uint8_t* f = heavy_flag + (size_t)s_nxt * max_chunks;
+    const int64_t lim = ngroups < max_chunks ? ngroups : max_chunks;
+    for (int64_t i = threadIdx.x; i < lim; i += blockDim.x) f[i] = 0;
 }
 
 __global__ void __launch_bounds__(256) zero_acc_kernel(float4* acc, int64_t first, int64_t count) {
@@ -337,10 +381,10 @@ int bh_force_prepare() {
 
 int bh_force_launch(const float4* posm, const uint32_t* keys, int64_t n, int64_t first_body, int64_t body_count,
                     const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
-                    float4* acc, BhDevScalars* sc, float theta, float softening, float G, float split_alpha,
-                    int num_sms, cudaStream_t st) {
+                    float4* acc, BhDevScalars* sc, uint32_t* heavy_list, uint8_t* heavy_flag, int64_t max_chunks,
+                    float theta, float softening, float G, float split_alpha, int num_sms, cudaStream_t st) {
     if (body_count <= 0) return 0;
-    reset_force_scalars<<<1, 32, 0, st>>>(sc);
+    reset_force_scalars<<<1, 256, 0, st>>>(sc, heavy_flag, max_chunks, (body_count + BH_GROUP - 1) / BH_GROUP);
     if (n < 2) {  // a single body feels nothing (its self term is exactly zero, bench:205-213)
         zero_acc_kernel<<<1, 256, 0, st>>>(acc, first_body, body_count);
         return (int)cudaGetLastError();
@@ -352,6 +396,6 @@ int bh_force_launch(const float4* posm, const uint32_t* keys, int64_t n, int64_t
     int64_t grid = (int64_t)(num_sms > 0 ? num_sms : BH_NUM_SMS_FALLBACK) * max_ctas;  // persistent: fill the chip once
     if (grid > want) grid = want;
     force_kernel<<<(int)grid, FORCE_THREADS, 0, st>>>(posm, keys, first_body, body_count, cell_meta, cell_child, cell_com, acc,
-                                                     sc, theta, softening, G, split_alpha);
+                                                     sc, heavy_list, heavy_flag, max_chunks, theta, softening, G, split_alpha);
     return (int)cudaGetLastError();
 }

@@ -125,6 +125,7 @@ def lib() -> C.CDLL:
     L.bh_ic_plummer.argtypes = [i64, C.c_uint64, f32, f32, f32, f32] + [vp] * 7
     L.bh_probe_fp32_tflops.argtypes = [i32, C.POINTER(f32)]
     L.bh_probe_hbm_gbs.argtypes = [i32, C.POINTER(f32)]
+    L.bh_probe_fp32x2_tflops.argtypes = [i32, C.POINTER(f32)]
     _lib = L
     return L
 
@@ -163,6 +164,12 @@ def ic_plummer(n: int, seed: int = 42, scale_a: float = 200.0, rcut_in_a: float 
 def probe_fp32_tflops(device: int = 0) -> float:
     v = C.c_float()
     _check(lib().bh_probe_fp32_tflops(device, C.byref(v)), "bh_probe_fp32_tflops")
+    return float(v.value)
+
+
+def probe_fp32x2_tflops(device: int = 0) -> float:
+    v = C.c_float()
+    _check(lib().bh_probe_fp32x2_tflops(device, C.byref(v)), "bh_probe_fp32x2_tflops")
     return float(v.value)
 
 
