@@ -31,6 +31,9 @@ namespace {
 
 constexpr int FORCE_WARPS = 4;
 constexpr int FORCE_THREADS = FORCE_WARPS * 32;
+#ifndef FORCE_MIN_CTAS
+#define FORCE_MIN_CTAS 5
+#endif
 constexpr int STACK_CAP = 1024;
 constexpr int STACK_RESERVE = 384;   // >= 224 (one wide pop/push) + 7 * deepest level, see DESIGN.md
 constexpr int ALIST_CAP = 64;
@@ -38,8 +41,8 @@ constexpr int DLIST_CAP = 352;
 constexpr unsigned LOOP_GUARD = 1u << 24;
 
 struct __align__(16) WarpScratch {
-    float4 alist[ALIST_CAP];   // accepted cells: com.xyz, mass
-    float4 tile[32];           // gathered bodies for one direct tile
+    float4 alist[ALIST_CAP];   // accepted cells (com.xyz, mass) as a 2x32 ring of source PAIRS
+    float4 tile[32];           // gathered bodies for one direct tile, same pair layout
     int stack[STACK_CAP];
     int dlist[DLIST_CAP];      // body slots awaiting direct evaluation
 };
@@ -52,23 +55,94 @@ __device__ __forceinline__ float rsqrt_fast(float x) {
     return r;
 }
 
-// 32 sources against this lane's body.  bench:205-213 with dist^-3 from one rsqrt.
-__device__ __forceinline__ void eval_tile(const float4* __restrict__ src, float px, float py, float pz,
-                                          float soft, float& ax, float& ay, float& az) {
-#pragma unroll 8
-    for (int k = 0; k < 32; ++k) {
-        const float4 s = src[k];  // same address in every lane: shared-memory broadcast
-        const float dx = s.x - px, dy = s.y - py, dz = s.z - pz;
-        const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, soft)));
-        const float rinv = rsqrt_fast(r2);
-        const float f = (s.w * rinv) * (rinv * rinv);
-        ax = fmaf(f, dx, ax);
-        ay = fmaf(f, dy, ay);
-        az = fmaf(f, dz, az);
+// ---- packed FP32 (sm_100 FFMA2/FADD2/FMUL2): one issued instruction does two lanes' worth of work.
+// The FMA pipe's flop rate is the same as with scalar FFMA (bh_probe_fp32x2_tflops: 73.8 vs 72.1
+// TFLOP/s) but the traversal kernel is ISSUE bound, and the packed form halves the issue slots of the
+// interaction arithmetic.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+
+// Source lists live in shared memory as PAIRS: 32 bytes {x0,x1,y0,y1 | z0,z1,m0,m1} per two sources,
+// so two LDS.128 broadcasts feed one packed interaction step.
+struct __align__(16) SrcPair { float4 xy, zm; };
+__device__ __forceinline__ void store_source(SrcPair* list, int idx, const float4 v) {
+    float* f = reinterpret_cast<float*>(list + (idx >> 1)) + (idx & 1);
+    f[0] = v.x; f[2] = v.y; f[4] = v.z; f[6] = v.w;
+}
+
+// 32 sources (16 pairs) against this lane's body.  bench:205-213 with dist^-3 from one rsqrt:
+// per pair 3 FADD2 + 3 FFMA2 (r^2 + soft) + 2 MUFU.RSQ + 3 FMUL2 (m r^-3) + 3 FFMA2 (accumulate).
+// Four pairs (8 sources) are kept in flight per step, stage by stage, so the dependent chains
+// (3 FFMA2 -> MUFU -> 2 FMUL2 -> FFMA2) of one pair are covered by the other three: the in-order issue
+// of a single warp no longer waits on its own latency.
+struct Accum { f32x2 x, y, z; };
+#ifndef EVAL_ILP_N
+#define EVAL_ILP_N 4
+#endif
+constexpr int EVAL_ILP = EVAL_ILP_N;
+__device__ __forceinline__ void eval_tile(const SrcPair* __restrict__ src, f32x2 npx, f32x2 npy, f32x2 npz,
+                                          f32x2 soft2, Accum& a) {
+#pragma unroll 1
+    for (int k = 0; k < 16; k += EVAL_ILP) {
+        f32x2 dx[EVAL_ILP], dy[EVAL_ILP], dz[EVAL_ILP], r[EVAL_ILP], m[EVAL_ILP];
+#pragma unroll
+        for (int j = 0; j < EVAL_ILP; ++j) {
+            const float4 xy = src[k + j].xy, zm = src[k + j].zm;   // uniform address: LDS.128 broadcast
+            dx[j] = add2(pack2(xy.x, xy.y), npx);
+            dy[j] = add2(pack2(xy.z, xy.w), npy);
+            dz[j] = add2(pack2(zm.x, zm.y), npz);
+            m[j] = pack2(zm.z, zm.w);
+        }
+#pragma unroll
+        for (int j = 0; j < EVAL_ILP; ++j) r[j] = fma2(dx[j], dx[j], soft2);
+#pragma unroll
+        for (int j = 0; j < EVAL_ILP; ++j) r[j] = fma2(dy[j], dy[j], r[j]);
+#pragma unroll
+        for (int j = 0; j < EVAL_ILP; ++j) r[j] = fma2(dz[j], dz[j], r[j]);
+#pragma unroll
+        for (int j = 0; j < EVAL_ILP; ++j) {
+            float r0, r1;
+            unpack2(r[j], r0, r1);
+            r[j] = pack2(rsqrt_fast(r0), rsqrt_fast(r1));
+        }
+#pragma unroll
+        for (int j = 0; j < EVAL_ILP; ++j) m[j] = mul2(m[j], r[j]);
+#pragma unroll
+        for (int j = 0; j < EVAL_ILP; ++j) r[j] = mul2(r[j], r[j]);
+#pragma unroll
+        for (int j = 0; j < EVAL_ILP; ++j) m[j] = mul2(m[j], r[j]);
+#pragma unroll
+        for (int j = 0; j < EVAL_ILP; ++j) {
+            a.x = fma2(m[j], dx[j], a.x);
+            a.y = fma2(m[j], dy[j], a.y);
+            a.z = fma2(m[j], dz[j], a.z);
+        }
     }
 }
 
-__global__ void __launch_bounds__(FORCE_THREADS, 6) force_kernel(const float4* __restrict__ posm,
+__global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(const float4* __restrict__ posm,
                                                              const uint32_t* __restrict__ keys, int64_t first_body,
                                                              int64_t body_count, const int4* __restrict__ cell_meta,
                                                              const int32_t* __restrict__ cell_child,
@@ -132,6 +206,10 @@ __global__ void __launch_bounds__(FORCE_THREADS, 6) force_kernel(const float4* _
         const uint32_t nextkey = __shfl_down_sync(0xffffffffu, mykey, 1);
         const int lvp = (lane + 1 < nb) ? bh_shared_digits(mykey, nextkey) : 99;   // pair (lane, lane+1)
         const unsigned ox = bh_f2ord(me.x), oy = bh_f2ord(me.y), oz = bh_f2ord(me.z);
+        const f32x2 npx = pack2(-me.x, -me.x), npy = pack2(-me.y, -me.y), npz = pack2(-me.z, -me.z);
+        const f32x2 soft2 = pack2(soft, soft);
+        SrcPair* const alist = reinterpret_cast<SrcPair*>(W.alist);   // 32 pairs = ring of 64 sources
+        SrcPair* const tile = reinterpret_cast<SrcPair*>(W.tile);     // 16 pairs
         float ax = 0.f, ay = 0.f, az = 0.f;      // this lane's body, final
         unsigned cuts = 0;                        // bit j: boundary between lanes j and j+1
         unsigned acc_cells_w = 0, dir_bodies_w = 0;   // weighted by sub-group size
@@ -182,8 +260,10 @@ __global__ void __launch_bounds__(FORCE_THREADS, 6) force_kernel(const float4* _
         const float cy = __fmul_rn(__fadd_rn(loy, hiy), 0.5f), hy = __fmul_rn(__fsub_rn(hiy, loy), 0.5f);
         const float cz = __fmul_rn(__fadd_rn(loz, hiz), 0.5f), hz = __fmul_rn(__fsub_rn(hiz, loz), 0.5f);
 
-        float tx = 0.f, ty = 0.f, tz = 0.f;      // this sub-group's pass (kept only by its lanes)
+        Accum t;                                  // this sub-group's pass (kept only by its lanes)
+        t.x = t.y = t.z = pack2(0.f, 0.f);
         int sp = 0, na = 0, nd = 0;
+        int ahead = 0;                            // ring head of the accepted list: 0 or 32
         unsigned acc_cells = 0, dir_bodies = 0;
         if (root >= 0) {
             if (lane == 0) W.stack[0] = root;
@@ -217,13 +297,14 @@ __global__ void __launch_bounds__(FORCE_THREADS, 6) force_kernel(const float4* _
 
             // ---- accepted cells -> interaction list ----
             const unsigned am = __ballot_sync(0xffffffffu, mine && accept);
-            if (mine && accept) W.alist[na + __popc(am & lt_mask)] = cm;
+            if (mine && accept) store_source(alist, (ahead + na + __popc(am & lt_mask)) & 63, cm);
             na += __popc(am);
             acc_cells += __popc(am);
             __syncwarp();
-            if (na >= 32) {
+            if (na >= 32) {   // the 32 oldest entries are the aligned half of the ring at `ahead`
+                eval_tile(alist + (ahead >> 1), npx, npy, npz, soft2, t);
+                ahead ^= 32;
                 na -= 32;
-                eval_tile(W.alist + na, me.x, me.y, me.z, soft, tx, ty, tz);
                 __syncwarp();
             }
 
@@ -266,9 +347,9 @@ __global__ void __launch_bounds__(FORCE_THREADS, 6) force_kernel(const float4* _
             // ---- direct list: full tiles ----
             while (nd >= 32) {
                 nd -= 32;
-                W.tile[lane] = __ldg(posm + W.dlist[nd + lane]);
+                store_source(tile, lane, __ldg(posm + W.dlist[nd + lane]));
                 __syncwarp();
-                eval_tile(W.tile, me.x, me.y, me.z, soft, tx, ty, tz);
+                eval_tile(tile, npx, npy, npz, soft2, t);
                 __syncwarp();
             }
 
@@ -287,9 +368,9 @@ __global__ void __launch_bounds__(FORCE_THREADS, 6) force_kernel(const float4* _
                     __syncwarp();
                     if (nd >= 32) {
                         nd -= 32;
-                        W.tile[lane] = __ldg(posm + W.dlist[nd + lane]);
+                        store_source(tile, lane, __ldg(posm + W.dlist[nd + lane]));
                         __syncwarp();
-                        eval_tile(W.tile, me.x, me.y, me.z, soft, tx, ty, tz);
+                        eval_tile(tile, npx, npy, npz, soft2, t);
                         __syncwarp();
                     }
                 }
@@ -298,19 +379,24 @@ __global__ void __launch_bounds__(FORCE_THREADS, 6) force_kernel(const float4* _
 
         // ---- partial tiles (zero-mass padding contributes exactly 0) ----
         if (na > 0) {
-            if (lane >= na) W.alist[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (lane >= na) store_source(alist, ahead + lane, make_float4(0.f, 0.f, 0.f, 0.f));
             __syncwarp();
-            eval_tile(W.alist, me.x, me.y, me.z, soft, tx, ty, tz);
+            eval_tile(alist + (ahead >> 1), npx, npy, npz, soft2, t);
             __syncwarp();
         }
         if (nd > 0) {
-            W.tile[lane] = lane < nd ? __ldg(posm + W.dlist[lane]) : make_float4(0.f, 0.f, 0.f, 0.f);
+            store_source(tile, lane, lane < nd ? __ldg(posm + W.dlist[lane]) : make_float4(0.f, 0.f, 0.f, 0.f));
             __syncwarp();
-            eval_tile(W.tile, me.x, me.y, me.z, soft, tx, ty, tz);
+            eval_tile(tile, npx, npy, npz, soft2, t);
             __syncwarp();
         }
 
-        if (in_group) { ax = tx; ay = ty; az = tz; }
+        if (in_group) {
+            float lo, hi;
+            unpack2(t.x, lo, hi); ax = lo + hi;
+            unpack2(t.y, lo, hi); ay = lo + hi;
+            unpack2(t.z, lo, hi); az = lo + hi;
+        }
         acc_cells_w += acc_cells * gsize;
         dir_bodies_w += dir_bodies * gsize;
         chunk_entries += acc_cells + dir_bodies;

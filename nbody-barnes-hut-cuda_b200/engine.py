@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "libbh.so")
+_LIB_PATH = os.environ.get("BH_LIB") or os.path.join(_HERE, "libbh.so")  # BH_LIB: tuning variants only
 _lib: Optional[C.CDLL] = None
 
 

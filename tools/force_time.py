@@ -1,0 +1,19 @@
+"""Phase timing of one workload for the library selected by BH_LIB (tuning helper)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import bench  # noqa: E402
+import nbody_barnes_hut_cuda_b200 as bh  # noqa: E402
+
+wl = sys.argv[1] if len(sys.argv) > 1 else "refdisk_1m"
+w = bench.WORKLOADS[wl]
+soa = bench.make_ic(bh, w)
+eng = bh.BHEngine(w["n"], flags=2)
+eng.load_soa(*soa)
+eng.simulation_step(5)
+eng.simulation_step(20)
+ms = eng.phase_ms()
+print(os.environ.get("BH_LIB", "default").split("/")[-1], wl, {k: round(v / 20, 4) for k, v in ms.items()},
+      "int/body", (eng.stat(bh.STAT.INTERACTIONS_CELL) + eng.stat(bh.STAT.INTERACTIONS_BODY)) / w["n"])
+eng.check_device_error()
