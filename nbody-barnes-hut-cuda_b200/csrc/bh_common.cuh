@@ -85,15 +85,18 @@ int bh_bounds_launch(const float4* posm, int64_t n, BhDevScalars* sc, cudaStream
 int bh_reorder_launch(const float4* posm_in, const float4* vel_in, const int32_t* ids_in,
                       const uint32_t* perm, float4* posm_out, float4* vel_out, int32_t* ids_out,
                       int64_t n, cudaStream_t st);
-int bh_tree_launch(const uint32_t* keys, int64_t n, int2* pair_info, int32_t* pair_scan,
+// kid_src: 8 float4 per cell — the SOURCE each child contributes when its parent is opened (a loose
+// body's {x,y,z,m}, a child cell's {com,mass}); kid_lv: 8 bytes per cell — level | bucket<<7 of child cells.
+int bh_tree_launch(const uint32_t* keys, const float4* posm, int64_t n, int2* pair_info, int32_t* pair_scan,
                    int32_t* scan_block_sums, int4* cell_meta, int32_t* cell_child,
-                   int32_t* cell_arrive, BhDevScalars* sc, cudaStream_t st);
+                   int32_t* cell_arrive, float4* kid_src, uint8_t* kid_lv, BhDevScalars* sc, cudaStream_t st);
 int bh_com_launch(const float4* posm, int64_t n, const int4* cell_meta, const int32_t* cell_child,
-                  int32_t* cell_arrive, float4* cell_mom, float4* cell_com,
+                  int32_t* cell_arrive, float4* cell_mom, float4* cell_com, float4* kid_src,
                   BhDevScalars* sc, cudaStream_t st);
 // heavy_list: 2 * max_chunks u32, heavy_flag: 2 * max_chunks bytes (see BhDevScalars::epoch)
 int bh_force_launch(const float4* posm, const uint32_t* keys, int64_t n, int64_t first_body, int64_t body_count,
                     const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
+                    const float4* kid_src, const uint8_t* kid_lv,
                     float4* acc, BhDevScalars* sc, uint32_t* heavy_list, uint8_t* heavy_flag, int64_t max_chunks,
                     float theta, float softening, float G, float split_alpha, int num_sms, cudaStream_t st);
 int bh_force_prepare();

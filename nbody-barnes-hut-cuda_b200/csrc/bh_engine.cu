@@ -42,6 +42,8 @@ struct bh_ctx {
     int4* cell_meta = nullptr;
     int32_t *cell_child = nullptr, *cell_arrive = nullptr;
     float4 *cell_mom = nullptr, *cell_com = nullptr;
+    float4* kid_src = nullptr;   // 8 per cell
+    uint8_t* kid_lv = nullptr;   // 8 per cell
     uint32_t* heavy_list = nullptr;   // 2 * max_chunks
     uint8_t* heavy_flag = nullptr;    // 2 * max_chunks
     int64_t max_chunks = 0;
@@ -69,7 +71,7 @@ void free_all(bh_ctx* c) {
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     void* ptrs[] = {c->posm, c->vel, c->posm_s, c->vel_s, c->acc, c->ids, c->ids_s, c->keys0, c->keys1, c->vals0,
                     c->vals1, c->sort_tmp, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
-                    c->cell_arrive, c->cell_mom, c->cell_com, c->sc, c->stage, c->d_scratch, c->heavy_list, c->heavy_flag};
+                    c->cell_arrive, c->cell_mom, c->cell_com, c->sc, c->stage, c->d_scratch, c->heavy_list, c->heavy_flag, c->kid_src, c->kid_lv};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -102,17 +104,17 @@ int phase_sort(bh_ctx* c, cudaStream_t st) {
 }
 
 int phase_build(bh_ctx* c, cudaStream_t st) {
-    return bh_tree_launch(c->keys0, c->n, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
-                          c->cell_arrive, c->sc, st);
+    return bh_tree_launch(c->keys0, c->posm_s, c->n, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
+                          c->cell_arrive, c->kid_src, c->kid_lv, c->sc, st);
 }
 
 int phase_com(bh_ctx* c, cudaStream_t st) {
-    return bh_com_launch(c->posm_s, c->n, c->cell_meta, c->cell_child, c->cell_arrive, c->cell_mom, c->cell_com, c->sc, st);
+    return bh_com_launch(c->posm_s, c->n, c->cell_meta, c->cell_child, c->cell_arrive, c->cell_mom, c->cell_com, c->kid_src, c->sc, st);
 }
 
 int phase_force(bh_ctx* c, cudaStream_t st) {
     return bh_force_launch(c->posm_s, c->keys0, c->n, c->slice_first, c->slice_count, c->cell_meta, c->cell_child,
-                           c->cell_com, c->acc, c->sc, c->heavy_list, c->heavy_flag, c->max_chunks, c->prm.theta,
+                           c->cell_com, c->kid_src, c->kid_lv, c->acc, c->sc, c->heavy_list, c->heavy_flag, c->max_chunks, c->prm.theta,
                            c->prm.softening, c->prm.G, c->prm.group_split, c->num_sms, st);
 }
 
@@ -206,6 +208,7 @@ int bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device) 
     TRYA(dev_alloc(&c->pair_info, na)); TRYA(dev_alloc(&c->pair_scan, na)); TRYA(dev_alloc(&c->tile_sums, na / 2048 + 16));
     TRYA(dev_alloc(&c->cell_meta, na)); TRYA(dev_alloc(&c->cell_child, na * 8)); TRYA(dev_alloc(&c->cell_arrive, na));
     TRYA(dev_alloc(&c->cell_mom, na)); TRYA(dev_alloc(&c->cell_com, na));
+    TRYA(dev_alloc(&c->kid_src, na * 8)); TRYA(dev_alloc(&c->kid_lv, na * 8));
     TRYA(dev_alloc(&c->sc, 1)); TRYA(dev_alloc(&c->d_scratch, 8));
     c->max_chunks = (int64_t)(na / BH_GROUP + 1);
     TRYA(dev_alloc(&c->heavy_list, 2 * (size_t)c->max_chunks)); TRYA(dev_alloc(&c->heavy_flag, 2 * (size_t)c->max_chunks));

@@ -3,28 +3,29 @@
 // Replaces computeForceKernel  nbody_v5_bench.cu:191-225  (one thread per body, private
 // int stack[64], 76-byte AoS nodes).
 //
-// One warp owns a GROUP of 32 Morton-consecutive bodies (one body per lane).  The warp keeps
-// ONE traversal stack in shared memory and pops up to 32 cells at a time, one per lane:
-//   - every lane tests its cell against the group's bounding box (exact AABB of the 32
-//     positions): accept iff  w_L^2 < theta^2 * (d^2 + SOFTENING), d = distance from the cell's
-//     centre of mass to the box.  This is bench:207-208 (`width / sqrtf(d2 + SOFTENING) < THETA`)
-//     squared and evaluated at the closest point of the group, so the decision is uniform for
-//     the warp and every body of the group would also have accepted under the reference test;
-//   - __ballot_sync/__popc compact accepted cells into a shared interaction list, opened cells
-//     push their child cells back on the stack and their loose bodies on a direct list (warp
-//     prefix sums over __shfl_up_sync); identical-key buckets append their body range;
-//   - whenever a list holds 32 entries the warp evaluates a 32x32 tile: each lane keeps its own
-//     body in registers and reads the 32 sources as shared-memory broadcasts (LDS.128), doing
-//     bench:205-213's arithmetic with rsqrtf.
+// One warp owns a GROUP of up to 32 Morton-consecutive bodies (one body per lane).  The warp keeps ONE
+// stack of cells TO OPEN in shared memory and pops up to 32 of them at a time, one per lane.  Opening a
+// cell reads one 128-byte line, kid_src[cell][0..8): what each child contributes as a source — a loose
+// body's {x,y,z,m} or a child cell's {centre of mass, mass} — plus the child ids and levels.  The lane
+// then classifies its 8 children in registers:
+//   - loose body          -> source
+//   - child cell accepted -> source.  Test: w_L^2 < theta^2 * (d^2 + SOFTENING), d = distance from the
+//     child's centre of mass to the group's bounding box (exact AABB of the positions).  This is
+//     bench:207-208 (`width / sqrtf(d2 + SOFTENING) < THETA`) squared and taken at the group's closest
+//     point, so it is uniform for the warp and every body of the group would have accepted too;
+//   - child cell rejected -> pushed to be opened (identical-key buckets: their body range is appended).
+// One dependent global access per tree level (the child's data lives in the parent's line), warp
+// prefix sums (__shfl_up_sync) place sources and pushes, and whenever 32 sources are pending the warp
+// evaluates a 32x32 tile: each lane keeps its own body in registers and reads the sources as shared
+// memory broadcasts (LDS.128), bench:205-213's arithmetic in packed FP32 with rsqrt.approx.ftz.
+//
 // Group splitting: a 32-slot chunk of the Morton order that straddles a coarse cell boundary would
 // get a huge bounding box (measured on the 1M reference disk: median list 1,088 entries, worst
 // chunk 61,493 — one warp then outlives the whole grid).  The warp therefore cuts its chunk at the
 // coarsest key boundary whenever  ext(A) + ext(B) < alpha * ext(A u B)  (ext = sum of the box
 // edges; redux.sync min/max on order-preserving integer images of the coordinates), recursively,
-// and traverses each sub-group with all 32 lanes testing cells but only the sub-group's lanes
+// and traverses each sub-group with all 32 lanes opening cells but only the sub-group's lanes
 // keeping the result.  oracle/bh_oracle.cpp:orc_make_groups is the CPU restatement of the rule.
-// The tree (32-byte records + 32-byte child tables) and the positions stay L2-resident at
-// 1M bodies; shared memory holds only per-warp traversal state.
 #include "bh_common.cuh"
 
 namespace {
@@ -32,19 +33,16 @@ namespace {
 constexpr int FORCE_WARPS = 4;
 constexpr int FORCE_THREADS = FORCE_WARPS * 32;
 #ifndef FORCE_MIN_CTAS
-#define FORCE_MIN_CTAS 5
+#define FORCE_MIN_CTAS 4
 #endif
-constexpr int STACK_CAP = 1024;
+constexpr int STACK_CAP = 768;
 constexpr int STACK_RESERVE = 384;   // >= 224 (one wide pop/push) + 7 * deepest level, see DESIGN.md
-constexpr int ALIST_CAP = 64;
-constexpr int DLIST_CAP = 352;
+constexpr int SRC_CAP = 320;         // pending sources: < 32 left over + 8 per lane + one bucket slab of 32
 constexpr unsigned LOOP_GUARD = 1u << 24;
 
 struct __align__(16) WarpScratch {
-    float4 alist[ALIST_CAP];   // accepted cells (com.xyz, mass) as a 2x32 ring of source PAIRS
-    float4 tile[32];           // gathered bodies for one direct tile, same pair layout
-    int stack[STACK_CAP];
-    int dlist[DLIST_CAP];      // body slots awaiting direct evaluation
+    float4 src[SRC_CAP];       // pending sources, stored as PAIRS (see SrcPair)
+    int stack[STACK_CAP];      // cells waiting to be opened
 };
 
 // r2 >= SOFTENING > 0, never denormal: the flush-to-zero form is a bare MUFU.RSQ (the default
@@ -142,31 +140,25 @@ __device__ __forceinline__ void eval_tile(const SrcPair* __restrict__ src, f32x2
     }
 }
 
-__global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(const float4* __restrict__ posm,
-                                                             const uint32_t* __restrict__ keys, int64_t first_body,
-                                                             int64_t body_count, const int4* __restrict__ cell_meta,
-                                                             const int32_t* __restrict__ cell_child,
-                                                             const float4* __restrict__ cell_com,
-                                                             float4* __restrict__ acc, BhDevScalars* sc,
-                                                             uint32_t* __restrict__ heavy_list,
-                                                             uint8_t* __restrict__ heavy_flag, int64_t max_chunks,
-                                                             float theta, float soft, float G, float split_alpha) {
+__global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
+    const float4* __restrict__ posm, const uint32_t* __restrict__ keys, int64_t first_body, int64_t body_count,
+    const int4* __restrict__ cell_meta, const int32_t* __restrict__ cell_child, const float4* __restrict__ cell_com,
+    const float4* __restrict__ kid_src, const uint8_t* __restrict__ kid_lv, float4* __restrict__ acc, BhDevScalars* sc,
+    uint32_t* __restrict__ heavy_list, uint8_t* __restrict__ heavy_flag, int64_t max_chunks, float theta, float soft,
+    float G, float split_alpha) {
     __shared__ WarpScratch s_warp[FORCE_WARPS];
-    __shared__ float s_w2[BH_MAX_LEVEL + 1];
-
-    if (threadIdx.x <= BH_MAX_LEVEL) {
-        const float root_w = __fsub_rn(sc->bounds[3], sc->bounds[0]);   // bench:208 maxX - minX of the root
-        const float w = ldexpf(root_w, -(int)threadIdx.x);              // exact halving per level
-        s_w2[threadIdx.x] = __fmul_rn(w, w);
-    }
-    __syncthreads();
 
     const int lane = bh_lane();
-    const unsigned lt_mask = (1u << lane) - 1u;
     WarpScratch& W = s_warp[threadIdx.x >> 5];
+    SrcPair* const slist = reinterpret_cast<SrcPair*>(W.src);
     const float theta2 = __fmul_rn(theta, theta);
     const int root = sc->root;
+    // bench:208 maxX - minX of the root; a level-L cell is root_w * 2^-L wide, so its squared width is
+    // root_w^2 with 2L taken off the exponent (exact: power-of-two scaling commutes with rounding)
+    const float root_w = __fsub_rn(sc->bounds[3], sc->bounds[0]);
+    const int root_w2_bits = __float_as_int(__fmul_rn(root_w, root_w));
     const int4* child4 = reinterpret_cast<const int4*>(cell_child);
+    const uint2* lv2 = reinterpret_cast<const uint2*>(kid_lv);
     const int64_t ngroups = (body_count + BH_GROUP - 1) / BH_GROUP;
     const int64_t end_body = first_body + body_count;
 
@@ -208,8 +200,6 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(co
         const unsigned ox = bh_f2ord(me.x), oy = bh_f2ord(me.y), oz = bh_f2ord(me.z);
         const f32x2 npx = pack2(-me.x, -me.x), npy = pack2(-me.y, -me.y), npz = pack2(-me.z, -me.z);
         const f32x2 soft2 = pack2(soft, soft);
-        SrcPair* const alist = reinterpret_cast<SrcPair*>(W.alist);   // 32 pairs = ring of 64 sources
-        SrcPair* const tile = reinterpret_cast<SrcPair*>(W.tile);     // 16 pairs
         float ax = 0.f, ay = 0.f, az = 0.f;      // this lane's body, final
         unsigned cuts = 0;                        // bit j: boundary between lanes j and j+1
         unsigned acc_cells_w = 0, dir_bodies_w = 0;   // weighted by sub-group size
@@ -260,14 +250,60 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(co
         const float cy = __fmul_rn(__fadd_rn(loy, hiy), 0.5f), hy = __fmul_rn(__fsub_rn(hiy, loy), 0.5f);
         const float cz = __fmul_rn(__fadd_rn(loz, hiz), 0.5f), hz = __fmul_rn(__fsub_rn(hiz, loz), 0.5f);
 
+        // acceptance of a cell {com, level} for this sub-group (warp-uniform inputs except the cell)
+        auto accepts = [&](const float4 cm, int level) -> bool {
+            const float dx = fmaxf(0.0f, __fsub_rn(fabsf(__fsub_rn(cm.x, cx)), hx));
+            const float dy = fmaxf(0.0f, __fsub_rn(fabsf(__fsub_rn(cm.y, cy)), hy));
+            const float dz = fmaxf(0.0f, __fsub_rn(fabsf(__fsub_rn(cm.z, cz)), hz));
+            const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
+            const float w2 = __int_as_float(root_w2_bits - (level << 24));   // root_w^2 * 4^-level
+            return w2 < __fmul_rn(theta2, __fadd_rn(d2, soft));
+        };
+
         Accum t;                                  // this sub-group's pass (kept only by its lanes)
         t.x = t.y = t.z = pack2(0.f, 0.f);
-        int sp = 0, na = 0, nd = 0;
-        int ahead = 0;                            // ring head of the accepted list: 0 or 32
+        int sp = 0, ns = 0;                       // stack entries, pending sources
         unsigned acc_cells = 0, dir_bodies = 0;
+
+        // evaluate every full tile of 32 pending sources, keep the (< 32) remainder at the front
+        auto drain = [&]() {
+            if (ns < 32) return;
+            const int full = ns >> 5;
+            for (int b = 0; b < full; ++b) eval_tile(slist + b * 16, npx, npy, npz, soft2, t);
+            const int rem = ns & 31;
+            __syncwarp();
+            if (lane < ((rem + 1) >> 1)) {        // move whole pairs; `full*16` pairs were consumed
+                const SrcPair p = slist[full * 16 + lane];
+                slist[lane] = p;
+            }
+            ns = rem;
+            __syncwarp();
+        };
+        // append the bodies [bfirst, bfirst+bcount) of a rejected bucket
+        auto append_bucket = [&](int bfirst, int bcount) {
+            dir_bodies += bcount;
+            for (int b = 0; b < bcount; b += 32) {
+                const int m = min(32, bcount - b);
+                if (lane < m) store_source(slist, ns + lane, __ldg(posm + bfirst + b + lane));
+                ns += m;
+                __syncwarp();
+                drain();
+            }
+        };
+
+        // ---- the root is the only cell tested without a parent ----
         if (root >= 0) {
-            if (lane == 0) W.stack[0] = root;
-            sp = 1;
+            const float4 rcm = __ldg(cell_com + root);
+            const int4 rmt = __ldg(cell_meta + root);
+            if (accepts(rcm, rmt.z & 0xFF)) {
+                if (lane == 0) store_source(slist, 0, rcm);
+                ns = 1; acc_cells = 1;
+            } else if ((rmt.z >> 8) & 1) {
+                append_bucket(rmt.x, rmt.y);
+            } else {
+                if (lane == 0) W.stack[0] = root;
+                sp = 1;
+            }
         }
         __syncwarp();
 
@@ -281,113 +317,91 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(co
             sp -= take;
             __syncwarp();
 
-            float4 cm = make_float4(0.f, 0.f, 0.f, 0.f);
-            int4 mt = make_int4(0, 0, 0, 0);
-            bool accept = false, bucket = false;
+            // ---- open: ids, levels and the 128-byte source line of the 8 children ----
+            int e[8] = {BH_CHILD_EMPTY, BH_CHILD_EMPTY, BH_CHILD_EMPTY, BH_CHILD_EMPTY,
+                        BH_CHILD_EMPTY, BH_CHILD_EMPTY, BH_CHILD_EMPTY, BH_CHILD_EMPTY};
+            float4 s[8];
+            unsigned lvlo = 0, lvhi = 0;
+            unsigned src_mask = 0, push_mask = 0, bucket_mask = 0;   // per child slot
             if (mine) {
-                cm = __ldg(cell_com + cell);
-                mt = __ldg(cell_meta + cell);
-                bucket = (mt.z >> 8) & 1;
-                const float dx = fmaxf(0.0f, __fsub_rn(fabsf(__fsub_rn(cm.x, cx)), hx));
-                const float dy = fmaxf(0.0f, __fsub_rn(fabsf(__fsub_rn(cm.y, cy)), hy));
-                const float dz = fmaxf(0.0f, __fsub_rn(fabsf(__fsub_rn(cm.z, cz)), hz));
-                const float d2 = __fmaf_rn(dz, dz, __fmaf_rn(dy, dy, __fmul_rn(dx, dx)));
-                accept = s_w2[mt.z & 0xFF] < __fmul_rn(theta2, __fadd_rn(d2, soft));
-            }
-
-            // ---- accepted cells -> interaction list ----
-            const unsigned am = __ballot_sync(0xffffffffu, mine && accept);
-            if (mine && accept) store_source(alist, (ahead + na + __popc(am & lt_mask)) & 63, cm);
-            na += __popc(am);
-            acc_cells += __popc(am);
-            __syncwarp();
-            if (na >= 32) {   // the 32 oldest entries are the aligned half of the ring at `ahead`
-                eval_tile(alist + (ahead >> 1), npx, npy, npz, soft2, t);
-                ahead ^= 32;
-                na -= 32;
-                __syncwarp();
-            }
-
-            // ---- opened internal cells: child cells -> stack, loose bodies -> direct list ----
-            const bool open = mine && !accept && !bucket;
-            int e[8];
-            int packed = 0;  // child cells in the low half, bodies in the high half
-            if (open) {
-                const int4 lo = __ldg(child4 + 2 * cell), hi = __ldg(child4 + 2 * cell + 1);
+                const int4 lo = __ldg(child4 + 2 * (size_t)cell), hi = __ldg(child4 + 2 * (size_t)cell + 1);
+                const uint2 lv = __ldg(lv2 + cell);
+                lvlo = lv.x; lvhi = lv.y;
                 e[0] = lo.x; e[1] = lo.y; e[2] = lo.z; e[3] = lo.w;
                 e[4] = hi.x; e[5] = hi.y; e[6] = hi.z; e[7] = hi.w;
+                const float4* line = kid_src + (size_t)cell * 8;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (e[q] != BH_CHILD_EMPTY) s[q] = __ldg(line + q);
+            }
+            // software pipelining: the tiles pending from the previous round are evaluated while the
+            // loads above are in flight
+            drain();
+            if (mine) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    if (e[q] < 0) packed += 1 << 16;
-                    else if (e[q] != BH_CHILD_EMPTY) packed += 1;
+                    if (e[q] == BH_CHILD_EMPTY) continue;
+                    if (e[q] < 0) { src_mask |= 1u << q; continue; }                 // loose body
+                    const unsigned info = ((q < 4 ? lvlo : lvhi) >> (8 * (q & 3))) & 0xFFu;
+                    if (accepts(s[q], info & 0x7F)) src_mask |= 1u << (q + 8);       // accepted cell
+                    else if (info & 0x80) bucket_mask |= 1u << q;
+                    else push_mask |= 1u << q;
                 }
             }
+            const int n_body = __popc(src_mask & 0xFFu), n_cell = __popc(src_mask >> 8);
+            const int n_push = __popc(push_mask);
+            // one warp prefix sum for both streams: sources in the high half, pushes in the low half
+            const int packed = ((n_body + n_cell) << 16) | n_push;
             int incl = packed;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += t;
+                const int v = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += v;
             }
             const int total = __shfl_sync(0xffffffffu, incl, 31);
-            if (open) {
+            if (mine) {
                 int so = sp + ((incl - packed) & 0xFFFF);
-                int dof = nd + ((incl - packed) >> 16);
+                int di = ns + ((incl - packed) >> 16);
+                const unsigned any_src = (src_mask | (src_mask >> 8)) & 0xFFu;
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                    if (e[q] < 0) W.dlist[dof++] = e[q] & 0x7FFFFFFF;
-                    else if (e[q] != BH_CHILD_EMPTY) W.stack[so++] = e[q];
+                    if ((any_src >> q) & 1u) store_source(slist, di++, s[q]);
+                    if ((push_mask >> q) & 1u) W.stack[so++] = e[q];
                 }
             }
+            // warp totals of the two kinds of sources (interaction statistics)
+            acc_cells += __reduce_add_sync(0xffffffffu, (unsigned)n_cell);
+            dir_bodies += __reduce_add_sync(0xffffffffu, (unsigned)n_body);
             sp += total & 0xFFFF;
-            nd += total >> 16;
-            dir_bodies += total >> 16;
+            ns += total >> 16;
             max_sp = max(max_sp, (unsigned)sp);
             __syncwarp();
 
-            // ---- direct list: full tiles ----
-            while (nd >= 32) {
-                nd -= 32;
-                store_source(tile, lane, __ldg(posm + W.dlist[nd + lane]));
-                __syncwarp();
-                eval_tile(tile, npx, npy, npz, soft2, t);
-                __syncwarp();
-            }
-
-            // ---- rejected buckets: their bodies are a contiguous range ----
-            unsigned bm = __ballot_sync(0xffffffffu, mine && !accept && bucket);
+            // ---- rejected buckets (identical keys): their bodies are a contiguous range ----
+            unsigned bm = __ballot_sync(0xffffffffu, bucket_mask != 0);
             while (bm) {
-                const int src = __ffs(bm) - 1;
+                const int srcl = __ffs(bm) - 1;
                 bm &= bm - 1;
-                const int bfirst = __shfl_sync(0xffffffffu, mt.x, src);
-                const int bcount = __shfl_sync(0xffffffffu, mt.y, src);
-                dir_bodies += bcount;
-                for (int b = 0; b < bcount; b += 32) {
-                    const int m = min(32, bcount - b);
-                    if (lane < m) W.dlist[nd + lane] = bfirst + b + lane;
-                    nd += m;
-                    __syncwarp();
-                    if (nd >= 32) {
-                        nd -= 32;
-                        store_source(tile, lane, __ldg(posm + W.dlist[nd + lane]));
-                        __syncwarp();
-                        eval_tile(tile, npx, npy, npz, soft2, t);
-                        __syncwarp();
-                    }
+                unsigned qm = __shfl_sync(0xffffffffu, bucket_mask, srcl);
+                while (qm) {
+                    const int q = __ffs(qm) - 1;
+                    qm &= qm - 1;
+                    int id = 0;
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) id = (k == q) ? e[k] : id;
+                    id = __shfl_sync(0xffffffffu, id, srcl);
+                    const int4 bmt = __ldg(cell_meta + id);
+                    append_bucket(bmt.x, bmt.y);
                 }
             }
         }
 
-        // ---- partial tiles (zero-mass padding contributes exactly 0) ----
-        if (na > 0) {
-            if (lane >= na) store_source(alist, ahead + lane, make_float4(0.f, 0.f, 0.f, 0.f));
+        // ---- what is still pending: full tiles, then the last partial one (zero-mass padding adds 0) ----
+        drain();
+        if (ns > 0) {
+            if (lane >= ns) store_source(slist, lane, make_float4(0.f, 0.f, 0.f, 0.f));
             __syncwarp();
-            eval_tile(alist + (ahead >> 1), npx, npy, npz, soft2, t);
-            __syncwarp();
-        }
-        if (nd > 0) {
-            store_source(tile, lane, lane < nd ? __ldg(posm + W.dlist[lane]) : make_float4(0.f, 0.f, 0.f, 0.f));
-            __syncwarp();
-            eval_tile(tile, npx, npy, npz, soft2, t);
+            eval_tile(slist, npx, npy, npz, soft2, t);
             __syncwarp();
         }
 
@@ -467,6 +481,7 @@ int bh_force_prepare() {
 
 int bh_force_launch(const float4* posm, const uint32_t* keys, int64_t n, int64_t first_body, int64_t body_count,
                     const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
+                    const float4* kid_src, const uint8_t* kid_lv,
                     float4* acc, BhDevScalars* sc, uint32_t* heavy_list, uint8_t* heavy_flag, int64_t max_chunks,
                     float theta, float softening, float G, float split_alpha, int num_sms, cudaStream_t st) {
     if (body_count <= 0) return 0;
@@ -481,7 +496,8 @@ int bh_force_launch(const float4* posm, const uint32_t* keys, int64_t n, int64_t
     int64_t want = (ngroups + FORCE_WARPS - 1) / FORCE_WARPS;
     int64_t grid = (int64_t)(num_sms > 0 ? num_sms : BH_NUM_SMS_FALLBACK) * max_ctas;  // persistent: fill the chip once
     if (grid > want) grid = want;
-    force_kernel<<<(int)grid, FORCE_THREADS, 0, st>>>(posm, keys, first_body, body_count, cell_meta, cell_child, cell_com, acc,
-                                                     sc, heavy_list, heavy_flag, max_chunks, theta, softening, G, split_alpha);
+    force_kernel<<<(int)grid, FORCE_THREADS, 0, st>>>(posm, keys, first_body, body_count, cell_meta, cell_child, cell_com,
+                                                     kid_src, kid_lv, acc, sc, heavy_list, heavy_flag, max_chunks, theta,
+                                                     softening, G, split_alpha);
     return (int)cudaGetLastError();
 }

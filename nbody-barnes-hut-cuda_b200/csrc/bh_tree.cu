@@ -194,10 +194,11 @@ __global__ void __launch_bounds__(TB) init_cells_kernel(int4* __restrict__ child
 }
 
 // ---- pass E: every cell and every loose body links itself under its parent -------------------
-__global__ void __launch_bounds__(TB) link_kernel(const uint32_t* __restrict__ K, int n,
+__global__ void __launch_bounds__(TB) link_kernel(const uint32_t* __restrict__ K, const float4* __restrict__ posm, int n,
                                                  const int2* __restrict__ pair_info,
                                                  const int32_t* __restrict__ pair_scan, int4* __restrict__ cell_meta,
-                                                 int32_t* __restrict__ cell_child, BhDevScalars* sc) {
+                                                 int32_t* __restrict__ cell_child, float4* __restrict__ kid_src,
+                                                 uint8_t* __restrict__ kid_lv, BhDevScalars* sc) {
     for (int i = blockIdx.x * TB + threadIdx.x; i < n; i += gridDim.x * TB) {
         const uint32_t ki = __ldg(K + i);
         const int lv_left = lv_pair(K, i - 1, n);   // pair (i-1, i)
@@ -210,6 +211,7 @@ __global__ void __launch_bounds__(TB) link_kernel(const uint32_t* __restrict__ K
             const int parent = pair_scan[pair_info[sp].x];
             const int slot = (ki >> (BH_KEY_BITS - 3 * (Lb + 1))) & 7;
             cell_child[parent * 8 + slot] = (int)(0x80000000u | (uint32_t)i);
+            kid_src[(size_t)parent * 8 + slot] = __ldg(posm + i);   // what the traversal reads when it opens `parent`
         }
 
         // (2) pair i, if it leads a cell
@@ -222,17 +224,18 @@ __global__ void __launch_bounds__(TB) link_kernel(const uint32_t* __restrict__ K
                 const int r = find_right(K, n, i, L);
                 const int a = lv_pair(K, l - 1, n), b = lv_pair(K, r, n);
                 const int Lp = max(a, b);
-                int parent = -1;
+                int parent = -1, slot = 0;
                 if (Lp >= 0) {
                     if (Lp >= L) atomicOr(&sc->err, BH_DERR_TREE);
                     const int sp = (a >= b) ? l - 1 : r;
                     parent = pair_scan[pair_info[sp].x];
-                    const int slot = (ki >> (BH_KEY_BITS - 3 * (Lp + 1))) & 7;
+                    slot = (ki >> (BH_KEY_BITS - 3 * (Lp + 1))) & 7;
                     cell_child[parent * 8 + slot] = c;
+                    kid_lv[(size_t)parent * 8 + slot] = (uint8_t)(L | ((L == BH_MAX_LEVEL) << 7));
                 } else {
                     sc->root = c;
                 }
-                cell_meta[c] = make_int4(l, r - l + 1, L | ((L == BH_MAX_LEVEL) << 8), parent);
+                cell_meta[c] = make_int4(l, r - l + 1, L | ((L == BH_MAX_LEVEL) << 8) | (slot << 12), parent);
             }
         }
     }
@@ -248,16 +251,19 @@ __device__ __forceinline__ void add_body(Moments& s, const float4 p) {
     s.z = __fmaf_rn(p.w, p.z, s.z);
 }
 
-__device__ __forceinline__ void store_cell(float4* __restrict__ mom, float4* __restrict__ com, int c, const Moments& s) {
+__device__ __forceinline__ void store_cell(float4* __restrict__ mom, float4* __restrict__ com,
+                                           float4* __restrict__ kid_src, int c, const int4 mt, const Moments& s) {
     __stcg(mom + c, make_float4(s.x, s.y, s.z, s.m));
     const float inv = (s.m > 1e-6f) ? __fdiv_rn(1.0f, s.m) : 0.0f;   // bench:181-183
-    com[c] = make_float4(__fmul_rn(s.x, inv), __fmul_rn(s.y, inv), __fmul_rn(s.z, inv), s.m);
+    const float4 cm = make_float4(__fmul_rn(s.x, inv), __fmul_rn(s.y, inv), __fmul_rn(s.z, inv), s.m);
+    com[c] = cm;
+    if (mt.w >= 0) kid_src[(size_t)mt.w * 8 + ((mt.z >> 12) & 7)] = cm;   // the parent's view of this child
 }
 
 __global__ void __launch_bounds__(TB) com_kernel(const float4* __restrict__ posm, const int4* __restrict__ cell_meta,
                                                 const int32_t* __restrict__ cell_child, int32_t* __restrict__ arrive,
                                                 float4* __restrict__ mom, float4* __restrict__ com,
-                                                const BhDevScalars* __restrict__ sc) {
+                                                float4* __restrict__ kid_src, const BhDevScalars* __restrict__ sc) {
     const int M = sc->num_cells;
     const int4* child4 = reinterpret_cast<const int4*>(cell_child);
     for (int c0 = blockIdx.x * TB + threadIdx.x; c0 < M; c0 += gridDim.x * TB) {
@@ -277,7 +283,7 @@ __global__ void __launch_bounds__(TB) com_kernel(const float4* __restrict__ posm
             for (int q = 0; q < 8; ++q)
                 if (e[q] < 0) add_body(s, __ldg(posm + (e[q] & 0x7FFFFFFF)));
         }
-        store_cell(mom, com, c, s);
+        store_cell(mom, com, kid_src, c, mt, s);
         // climb while this thread is the last child cell to arrive
         for (;;) {
             const int p = mt.w;
@@ -302,9 +308,9 @@ __global__ void __launch_bounds__(TB) com_kernel(const float4* __restrict__ posm
                     t.y = __fadd_rn(t.y, cm.y); t.z = __fadd_rn(t.z, cm.z);
                 }
             }
-            store_cell(mom, com, p, t);
             c = p;
             mt = __ldg(cell_meta + c);
+            store_cell(mom, com, kid_src, c, mt, t);
         }
     }
 }
@@ -318,9 +324,9 @@ inline int capped_grid(int64_t work_items, int per_block) {
 
 }  // namespace
 
-int bh_tree_launch(const uint32_t* keys, int64_t n64, int2* pair_info, int32_t* pair_scan,
+int bh_tree_launch(const uint32_t* keys, const float4* posm, int64_t n64, int2* pair_info, int32_t* pair_scan,
                    int32_t* scan_block_sums, int4* cell_meta, int32_t* cell_child,
-                   int32_t* cell_arrive, BhDevScalars* sc, cudaStream_t st) {
+                   int32_t* cell_arrive, float4* kid_src, uint8_t* kid_lv, BhDevScalars* sc, cudaStream_t st) {
     const int n = (int)n64;
     if (n < 2) return 0;
     const int ntiles = (n - 1 + SCAN_TILE - 1) / SCAN_TILE;
@@ -328,14 +334,14 @@ int bh_tree_launch(const uint32_t* keys, int64_t n64, int2* pair_info, int32_t* 
     scan_tiles_kernel<<<1, 1024, 0, st>>>(scan_block_sums, ntiles, sc);
     scan_pairs_kernel<<<ntiles, TB, 0, st>>>(pair_info, n, scan_block_sums, pair_scan);
     init_cells_kernel<<<capped_grid(n, TB), TB, 0, st>>>(reinterpret_cast<int4*>(cell_child), cell_arrive, sc);
-    link_kernel<<<capped_grid(n, TB), TB, 0, st>>>(keys, n, pair_info, pair_scan, cell_meta, cell_child, sc);
+    link_kernel<<<capped_grid(n, TB), TB, 0, st>>>(keys, posm, n, pair_info, pair_scan, cell_meta, cell_child, kid_src, kid_lv, sc);
     return (int)cudaGetLastError();
 }
 
 int bh_com_launch(const float4* posm, int64_t n, const int4* cell_meta, const int32_t* cell_child,
-                  int32_t* cell_arrive, float4* cell_mom, float4* cell_com,
+                  int32_t* cell_arrive, float4* cell_mom, float4* cell_com, float4* kid_src,
                   BhDevScalars* sc, cudaStream_t st) {
     if (n < 2) return 0;
-    com_kernel<<<capped_grid(n / 2 + 1, TB), TB, 0, st>>>(posm, cell_meta, cell_child, cell_arrive, cell_mom, cell_com, sc);
+    com_kernel<<<capped_grid(n / 2 + 1, TB), TB, 0, st>>>(posm, cell_meta, cell_child, cell_arrive, cell_mom, cell_com, kid_src, sc);
     return (int)cudaGetLastError();
 }

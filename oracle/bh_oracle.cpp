@@ -399,7 +399,8 @@ inline float w2_of_level(float root_w, int level) {
 
 extern "C" {
 
-// Canonical tree over ascending keys.  meta: int4 per cell {first,count,level|bucket<<8,parent},
+// Canonical tree over ascending keys.  meta: int4 per cell {first,count,level|bucket<<8|slot<<12,parent}
+// (slot = which child of its parent the cell is),
 // child: 8 ints per cell.  Cells are numbered by ascending leader pair (the numbering the
 // parallel builder produces with a prefix sum).  Returns the cell count, or -1 if cap is short.
 int orc_tree_build(const uint32_t* sorted_keys, int64_t n64, int32_t* meta, int32_t* child,
@@ -423,7 +424,7 @@ int orc_tree_build(const uint32_t* sorted_keys, int64_t n64, int32_t* meta, int3
         int id = rank[old];
         meta[4 * id + 0] = c.first;
         meta[4 * id + 1] = c.count;
-        meta[4 * id + 2] = c.level | (c.bucket << 8);
+        meta[4 * id + 2] = c.level | (c.bucket << 8) | ((c.parent < 0 ? 0 : c.slot) << 12);
         meta[4 * id + 3] = c.parent < 0 ? -1 : rank[c.parent];
         for (int q = 0; q < 8; ++q) {
             int e = c.child[q];
