@@ -288,6 +288,9 @@ def run_ours(args, w):
 
 
 def main():
+    # keep stdout for the ONE JSON line: libraries (NCCL's version banner, torchrun notices) get stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=100)
@@ -303,7 +306,8 @@ def main():
     w = WORKLOADS[args.workload]
     line = run_reference_arm(args, w) if args.impl == "reference" else run_ours(args, w)
     if line is not None:
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
 
 
 if __name__ == "__main__":
