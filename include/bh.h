@@ -36,6 +36,7 @@ extern "C" {
 #define BH_E_STATE      (-3)  /* call order violated (e.g. step before import) */
 #define BH_E_UNSUPPORTED (-4) /* parameter combination not implemented         */
 #define BH_E_DEVICE     (-5)  /* a kernel raised its device-side error flag    */
+#define BH_E_IO         (-6)  /* file could not be opened / is not a checkpoint */
 
 /* Simulation parameters — the reference's compile-time constants
  * (nbody_v5_bench.cu:13-18) plus the tree-shape knobs it hard-codes.       */
@@ -192,6 +193,25 @@ int  bh_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in,
 int  bh_direct_sample(bh_ctx* ctx, const int32_t* sample, int k, double* acc_out);
 /* Total kinetic and (softened, pairwise) potential energy in double.       */
 int  bh_energy(bh_ctx* ctx, double* kinetic, double* potential);
+
+/* ---- callers either side of the step --------------------------- */
+/* ≙ updateVisualsKernel (nbody_v5.cu:278-292): interleaved xyz positions and the
+ * speed colour ramp (t = min(|v|/150, 1); rgb = 0.4+0.6t, 0.3+0.4t, 1-0.7t) for
+ * body i at vbo_p[3i..], vbo_c[3i..] — ORIGINAL body order.  DEVICE pointers
+ * (e.g. mapped GL buffers, nbody_v5.cu:332-334); either may be NULL.           */
+int  bh_export_visuals(bh_ctx* ctx, float* vbo_p, float* vbo_c, void* stream);
+/* Totals in double: out[0]=mass, out[1..3]=linear momentum, out[4..6]=angular
+ * momentum about the origin.                                                 */
+int  bh_momentum(bh_ctx* ctx, double out[7]);
+/* Text dump in the format of the older tool's output_bh.txt:1-5
+ * ("# Bodies: N, Theta: t, dt: d" header, then "x y z vx vy vz" per body in
+ * ORIGINAL order, %.6f).                                                      */
+int  bh_dump_text(bh_ctx* ctx, const char* path);
+/* Binary checkpoint of the exact internal state (Morton-ordered posm/vel/ids,
+ * step count, parameters): loading it and stepping reproduces an uninterrupted
+ * run bit for bit.                                                            */
+int  bh_save_checkpoint(bh_ctx* ctx, const char* path);
+int  bh_load_checkpoint(bh_ctx* ctx, const char* path);
 
 /* Initial conditions (host arrays, n floats each).
  * refdisk: main()'s generator, nbody_v5_bench.cu:294-308, glibc rand().    */

@@ -113,3 +113,6 @@ int bh_direct_launch(const float4* posm, int64_t n, const int32_t* sample_slots,
                      float softening, float G, double* acc_out, cudaStream_t st);
 int bh_energy_launch(const float4* posm, const float4* vel, int64_t n, float softening, float G,
                      double* ke_pe /*2 doubles, zeroed by the launcher*/, cudaStream_t st);
+int bh_visuals_launch(const float4* posm, const float4* vel, const int32_t* ids, int64_t n, float* vbo_p, float* vbo_c,
+                      cudaStream_t st);
+int bh_momentum_launch(const float4* posm, const float4* vel, int64_t n, double* out7, cudaStream_t st);

@@ -64,6 +64,43 @@ __global__ void __launch_bounds__(DT) energy_kernel(const float4* __restrict__ p
     }
 }
 
+// ≙ updateVisualsKernel nbody_v5.cu:278-292, reading the Morton-ordered float4 state and scattering to
+// the caller's original-order interleaved buffers.
+__global__ void __launch_bounds__(DT) visuals_kernel(const float4* __restrict__ posm, const float4* __restrict__ vel,
+                                                    const int32_t* __restrict__ ids, int64_t n, float* vbo_p, float* vbo_c) {
+    for (int64_t i = (int64_t)blockIdx.x * DT + threadIdx.x; i < n; i += (int64_t)gridDim.x * DT) {
+        const int64_t o = 3 * (int64_t)ids[i];
+        if (vbo_p) {
+            const float4 p = __ldg(posm + i);
+            vbo_p[o] = p.x; vbo_p[o + 1] = p.y; vbo_p[o + 2] = p.z;
+        }
+        if (vbo_c) {
+            const float4 v = __ldg(vel + i);
+            const float speed = __fsqrt_rn(__fmaf_rn(v.z, v.z, __fmaf_rn(v.x, v.x, __fmul_rn(v.y, v.y))));
+            const float t = fminf(__fdiv_rn(speed, 150.0f), 1.0f);
+            vbo_c[o] = __fmaf_rn(t, 0.6f, 0.4f); vbo_c[o + 1] = __fmaf_rn(t, 0.4f, 0.3f); vbo_c[o + 2] = __fmaf_rn(t, -0.7f, 1.0f);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(DT) momentum_kernel(const float4* __restrict__ posm, const float4* __restrict__ vel,
+                                                     int64_t n, double* __restrict__ out7) {
+    __shared__ double s_buf[DT / 32];
+    double a[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int64_t i = (int64_t)blockIdx.x * DT + threadIdx.x; i < n; i += (int64_t)gridDim.x * DT) {
+        const float4 p = __ldg(posm + i), v = __ldg(vel + i);
+        const double m = p.w, px = m * v.x, py = m * v.y, pz = m * v.z;
+        a[0] += m; a[1] += px; a[2] += py; a[3] += pz;
+        a[4] += (double)p.y * pz - (double)p.z * py;
+        a[5] += (double)p.z * px - (double)p.x * pz;
+        a[6] += (double)p.x * py - (double)p.y * px;
+    }
+    for (int k = 0; k < 7; ++k) {
+        const double t = block_sum(a[k], s_buf);
+        if (threadIdx.x == 0) atomicAdd(out7 + k, t);
+    }
+}
+
 // ---- probes -----------------------------------------------------------------------------
 // 8 independent FMA chains per thread, register resident: measures the FP32 FMA issue rate.
 __global__ void __launch_bounds__(256) fma_probe_kernel(float* out, int iters, float a, float b) {
@@ -125,6 +162,24 @@ int bh_energy_launch(const float4* posm, const float4* vel, int64_t n, float sof
     if (n <= 0) return 0;
     int grid = (int)(n < 148 * 16 ? n : 148 * 16);
     energy_kernel<<<grid, DT, 0, st>>>(posm, vel, n, softening, G, ke_pe);
+    return (int)cudaGetLastError();
+}
+
+int bh_visuals_launch(const float4* posm, const float4* vel, const int32_t* ids, int64_t n, float* vbo_p, float* vbo_c,
+                      cudaStream_t st) {
+    if (n <= 0 || (!vbo_p && !vbo_c)) return 0;
+    int64_t blocks = (n + DT - 1) / DT;
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    visuals_kernel<<<(int)blocks, DT, 0, st>>>(posm, vel, ids, n, vbo_p, vbo_c);
+    return (int)cudaGetLastError();
+}
+
+int bh_momentum_launch(const float4* posm, const float4* vel, int64_t n, double* out7, cudaStream_t st) {
+    BH_CUDA_TRY(cudaMemsetAsync(out7, 0, 7 * sizeof(double), st));
+    if (n <= 0) return 0;
+    int64_t blocks = (n + DT - 1) / DT;
+    if (blocks > 148 * 4) blocks = 148 * 4;
+    momentum_kernel<<<(int)blocks, DT, 0, st>>>(posm, vel, n, out7);
     return (int)cudaGetLastError();
 }
 

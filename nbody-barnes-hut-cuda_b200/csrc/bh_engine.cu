@@ -176,6 +176,7 @@ const char* bh_error_string(int code) {
         case BH_E_STATE: return "call order violated";
         case BH_E_UNSUPPORTED: return "unsupported parameter combination";
         case BH_E_DEVICE: return "device-side error flag raised";
+        case BH_E_IO: return "file i/o failed or not a checkpoint";
         default: return code > 0 ? cudaGetErrorString((cudaError_t)code) : "unknown error";
     }
 }
@@ -515,6 +516,110 @@ int bh_direct_sample(bh_ctx* c, const int32_t* sample, int k, double* acc_out) {
     cudaError_t ce = cudaMemcpy(acc_out, d_out, (size_t)k * 24, cudaMemcpyDeviceToHost);
     cudaFree(d_slots); cudaFree(d_out);
     return e ? e : (int)ce;
+}
+
+int bh_export_visuals(bh_ctx* c, float* vbo_p, float* vbo_c, void* stream) {
+    if (!c) return BH_E_INVAL;
+    if (!c->have_state) return BH_E_STATE;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    return bh_visuals_launch(c->posm, c->vel, c->ids, c->n, vbo_p, vbo_c, (cudaStream_t)stream);
+}
+
+int bh_momentum(bh_ctx* c, double out[7]) {
+    if (!c || !out) return BH_E_INVAL;
+    if (!c->have_state) return BH_E_STATE;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    BH_CUDA_TRY(cudaDeviceSynchronize());
+    int e = bh_momentum_launch(c->posm, c->vel, c->n, c->d_scratch, 0);
+    if (e) return e;
+    return (int)cudaMemcpy(out, c->d_scratch, 7 * sizeof(double), cudaMemcpyDeviceToHost);
+}
+
+// ---- state I/O ----------------------------------------------------------------
+namespace {
+struct CkptHeader {
+    char magic[8];       // "BHB200\0\0"
+    int32_t version;
+    int32_t reserved;
+    int64_t n;
+    int64_t steps;
+    bh_params prm;
+};
+const char kMagic[8] = {'B', 'H', 'B', '2', '0', '0', 0, 0};
+}  // namespace
+
+int bh_dump_text(bh_ctx* c, const char* path) {
+    if (!c || !path) return BH_E_INVAL;
+    if (!c->have_state) return BH_E_STATE;
+    const size_t n = (size_t)c->n;
+    std::vector<float> a[6];
+    for (auto& v : a) v.resize(n);
+    int e = bh_export_soa_host(c, a[0].data(), a[1].data(), a[2].data(), a[3].data(), a[4].data(), a[5].data(), nullptr,
+                               nullptr, nullptr);
+    if (e) return e;
+    FILE* f = fopen(path, "w");
+    if (!f) return BH_E_IO;
+    // header as output_bh.txt:1-4
+    fprintf(f, "# Barnes-Hut N-Body Simulation Results\n");
+    fprintf(f, "# Final positions and velocities after %lld steps\n", (long long)c->steps);
+    fprintf(f, "# Bodies: %lld, Theta: %.2f, dt: %.3f\n", (long long)c->n, c->prm.theta, c->prm.dt);
+    fprintf(f, "# Format: x y z vx vy vz\n");
+    for (size_t i = 0; i < n; ++i)
+        fprintf(f, "%.6f %.6f %.6f %.6f %.6f %.6f\n", a[0][i], a[1][i], a[2][i], a[3][i], a[4][i], a[5][i]);
+    return fclose(f) == 0 ? 0 : BH_E_IO;
+}
+
+int bh_save_checkpoint(bh_ctx* c, const char* path) {
+    if (!c || !path) return BH_E_INVAL;
+    if (!c->have_state) return BH_E_STATE;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    BH_CUDA_TRY(cudaDeviceSynchronize());
+    const size_t n = (size_t)c->n;
+    std::vector<float4> posm(n), vel(n);
+    std::vector<int32_t> ids(n);
+    BH_CUDA_TRY(cudaMemcpy(posm.data(), c->posm, n * 16, cudaMemcpyDeviceToHost));
+    BH_CUDA_TRY(cudaMemcpy(vel.data(), c->vel, n * 16, cudaMemcpyDeviceToHost));
+    BH_CUDA_TRY(cudaMemcpy(ids.data(), c->ids, n * 4, cudaMemcpyDeviceToHost));
+    CkptHeader h{};
+    memcpy(h.magic, kMagic, 8);
+    h.version = 1; h.n = c->n; h.steps = c->steps; h.prm = c->prm;
+    FILE* f = fopen(path, "wb");
+    if (!f) return BH_E_IO;
+    bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && fwrite(posm.data(), 16, n, f) == n && fwrite(vel.data(), 16, n, f) == n &&
+              fwrite(ids.data(), 4, n, f) == n;
+    ok = (fclose(f) == 0) && ok;
+    return ok ? 0 : BH_E_IO;
+}
+
+int bh_load_checkpoint(bh_ctx* c, const char* path) {
+    if (!c || !path) return BH_E_INVAL;
+    FILE* f = fopen(path, "rb");
+    if (!f) return BH_E_IO;
+    CkptHeader h{};
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, kMagic, 8) != 0 || h.version != 1 || h.n <= 0 || h.n > c->n_max) {
+        fclose(f);
+        return BH_E_IO;
+    }
+    const size_t n = (size_t)h.n;
+    std::vector<float4> posm(n), vel(n);
+    std::vector<int32_t> ids(n);
+    bool ok = fread(posm.data(), 16, n, f) == n && fread(vel.data(), 16, n, f) == n && fread(ids.data(), 4, n, f) == n;
+    fclose(f);
+    if (!ok) return BH_E_IO;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    BH_CUDA_TRY(cudaDeviceSynchronize());
+    BH_CUDA_TRY(cudaMemcpy(c->posm, posm.data(), n * 16, cudaMemcpyHostToDevice));
+    BH_CUDA_TRY(cudaMemcpy(c->vel, vel.data(), n * 16, cudaMemcpyHostToDevice));
+    BH_CUDA_TRY(cudaMemcpy(c->ids, ids.data(), n * 4, cudaMemcpyHostToDevice));
+    // simulation parameters travel with the state; flags and tuning knobs stay the context's own
+    c->prm.theta = h.prm.theta; c->prm.G = h.prm.G; c->prm.dt = h.prm.dt;
+    c->prm.softening = h.prm.softening; c->prm.max_speed = h.prm.max_speed;
+    c->n = h.n; c->steps = h.steps; c->have_state = true; c->have_sorted = false;
+    default_slice(c);
+    BH_CUDA_TRY(cudaMemset((char*)c->sc + offsetof(BhDevScalars, epoch), 0, sizeof(BhDevScalars) - offsetof(BhDevScalars, epoch)));
+    BH_CUDA_TRY(cudaMemset(c->heavy_flag, 0, 2 * (size_t)c->max_chunks));
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }   // theta/dt may have changed
+    return 0;
 }
 
 int bh_energy(bh_ctx* c, double* kinetic, double* potential) {

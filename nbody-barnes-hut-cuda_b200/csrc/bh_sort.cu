@@ -40,22 +40,39 @@ __global__ void __launch_bounds__(SORT_THREADS) histogram_kernel(const uint32_t*
     __shared__ uint32_t s_hist[MAX_PASSES][RADIX];
     for (int i = threadIdx.x; i < MAX_PASSES * RADIX; i += SORT_THREADS) (&s_hist[0][0])[i] = 0;
     __syncthreads();
-    // warp-uniform trip count so the match below always sees the full warp
-    for (int64_t base = (int64_t)blockIdx.x * SORT_THREADS + (threadIdx.x & ~31); base < n;
+    // warp-uniform trip count; each lane takes 4 consecutive keys (one 128-bit load).  Morton-coherent
+    // input puts a whole warp in one bin for the upper digits: that case is one vote + one atomic,
+    // everything else falls back to per-lane shared atomics (spread addresses, no serialisation).
+    const int64_t n4 = n >> 2;
+    const uint4* keys4 = reinterpret_cast<const uint4*>(keys);
+    for (int64_t base = (int64_t)blockIdx.x * SORT_THREADS + (threadIdx.x & ~31); base < n4;
          base += (int64_t)gridDim.x * SORT_THREADS) {
         const int64_t i = base + bh_lane();
-        const bool valid = i < n;
-        const uint32_t k = valid ? __ldg(keys + i) : 0u;
+        const bool valid = i < n4;
+        const uint4 k4 = valid ? __ldg(keys4 + i) : make_uint4(0, 0, 0, 0);
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        const int lead = __ffs(vmask) - 1;
 #pragma unroll
         for (int p = 0; p < MAX_PASSES; ++p) {
             if (p < pd.passes) {
-                // invalid lanes get a private pseudo-digit so they match nobody
-                const uint32_t d = valid ? ((k >> pd.shift[p]) & pd.mask[p]) : (0x10000u + bh_lane());
-                // warp-aggregate: Morton-coherent input puts most of a warp in one bin
-                const unsigned peers = __match_any_sync(0xffffffffu, d);
-                if (valid && (int)bh_lane() == __ffs(peers) - 1) atomicAdd(&s_hist[p][d], (uint32_t)__popc(peers));
+                const uint32_t d0 = (k4.x >> pd.shift[p]) & pd.mask[p], d1 = (k4.y >> pd.shift[p]) & pd.mask[p];
+                const uint32_t d2 = (k4.z >> pd.shift[p]) & pd.mask[p], d3 = (k4.w >> pd.shift[p]) & pd.mask[p];
+                const uint32_t ref = __shfl_sync(0xffffffffu, d0, lead);
+                const bool mine_same = (d0 == ref) & (d1 == ref) & (d2 == ref) & (d3 == ref);
+                const unsigned same = __ballot_sync(0xffffffffu, valid && mine_same);
+                if (same == vmask) {
+                    if ((int)bh_lane() == lead) atomicAdd(&s_hist[p][ref], 4u * (uint32_t)__popc(vmask));
+                } else if (valid) {
+                    atomicAdd(&s_hist[p][d0], 1u); atomicAdd(&s_hist[p][d1], 1u);
+                    atomicAdd(&s_hist[p][d2], 1u); atomicAdd(&s_hist[p][d3], 1u);
+                }
             }
         }
+    }
+    // the (< 4) keys past the last full quad
+    if (blockIdx.x == 0 && threadIdx.x < (n & 3)) {
+        const uint32_t k = __ldg(keys + (n4 << 2) + threadIdx.x);
+        for (int p = 0; p < pd.passes; ++p) atomicAdd(&s_hist[p][(k >> pd.shift[p]) & pd.mask[p]], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < pd.passes * RADIX; i += SORT_THREADS) {
@@ -85,7 +102,7 @@ __global__ void __launch_bounds__(RADIX) scan_hist_kernel(uint32_t* hist, int pa
 }
 
 template <bool IOTA>
-__global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const uint32_t* __restrict__ keys_in,
+__global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_t* __restrict__ keys_in,
                                                                const uint32_t* __restrict__ vals_in,
                                                                uint32_t* __restrict__ keys_out,
                                                                uint32_t* __restrict__ vals_out, int64_t n, int shift,
@@ -95,7 +112,7 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const uint32_t* 
     __shared__ uint32_t s_buf[TILE];
     __shared__ uint32_t s_whist[SORT_WARPS][RADIX];
     __shared__ uint32_t s_tile_excl[RADIX];
-    __shared__ int64_t s_global_off[RADIX];
+    __shared__ uint32_t s_global_off[RADIX];   // n < 2^30: 32-bit wrap-around arithmetic is exact
     __shared__ uint32_t s_scan[SORT_WARPS];
     __shared__ unsigned int s_tile;
 
@@ -108,17 +125,11 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const uint32_t* 
     const int64_t warp_base = tile_base + (int64_t)warp * (32 * ITEMS);
     const int tile_valid = (int)((n - tile_base) < TILE ? (n - tile_base) : TILE);
 
-    uint32_t key[ITEMS], val[ITEMS];
+    uint32_t key[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         int64_t i = warp_base + k * 32 + lane;
         key[k] = i < n ? __ldg(keys_in + i) : 0xFFFFFFFFu;
-    }
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        int64_t i = warp_base + k * 32 + lane;
-        if (IOTA) val[k] = (uint32_t)i;
-        else val[k] = i < n ? __ldg(vals_in + i) : 0u;
     }
 
     // ---- stable in-warp ranking with match-any digit groups --------------------------------
@@ -176,7 +187,7 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const uint32_t* 
             }
             *my_status = ST_INCL | (prior + running);
         }
-        s_global_off[d] = (int64_t)bucket_base[d] + (int64_t)prior - (int64_t)excl_in_tile;
+        s_global_off[d] = bucket_base[d] + prior - excl_in_tile;
     }
     __syncthreads();
 
@@ -188,14 +199,22 @@ __global__ void __launch_bounds__(SORT_THREADS) onesweep_kernel(const uint32_t* 
         pos[k] = s_tile_excl[d] + s_whist[warp][d] + rank[k];
         s_buf[pos[k]] = key[k];
     }
+    // the values are fetched only now (they would otherwise sit in 16 registers through the ranking)
+    uint32_t val[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        int64_t i = warp_base + k * 32 + lane;
+        if (IOTA) val[k] = (uint32_t)i;
+        else val[k] = i < n ? __ldg(vals_in + i) : 0u;
+    }
     __syncthreads();
-    int64_t dst[ITEMS];
+    uint32_t dst[ITEMS];
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const int p = threadIdx.x + k * SORT_THREADS;
         const uint32_t kk = s_buf[p];
         const uint32_t d = (kk >> shift) & mask;
-        dst[k] = s_global_off[d] + p;
+        dst[k] = s_global_off[d] + (uint32_t)p;
         if (p < tile_valid) keys_out[dst[k]] = kk;
     }
     __syncthreads();
@@ -253,7 +272,8 @@ int bh_sort_pairs_launch(const uint32_t* keys_src, const uint32_t* vals_src, uin
     uint32_t* lookback = (uint32_t*)((char*)tmp + plan.hist_bytes);
     unsigned int* tickets = (unsigned int*)((char*)tmp + plan.hist_bytes + plan.lookback_bytes);
     BH_CUDA_TRY(cudaMemsetAsync(tmp, 0, plan.total_bytes, st));
-    int hblocks = (int)((n + (int64_t)SORT_THREADS * 8 - 1) / ((int64_t)SORT_THREADS * 8));
+    int hblocks = (int)((n / 4 + (int64_t)SORT_THREADS * 4 - 1) / ((int64_t)SORT_THREADS * 4));
+    if (hblocks < 1) hblocks = 1;
     if (hblocks > BH_NUM_SMS_FALLBACK * 8) hblocks = BH_NUM_SMS_FALLBACK * 8;
     histogram_kernel<<<hblocks, SORT_THREADS, 0, st>>>(keys_src, n, pd, hist);
     scan_hist_kernel<<<1, RADIX, 0, st>>>(hist, pd.passes);

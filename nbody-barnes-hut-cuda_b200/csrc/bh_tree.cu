@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(TB) link_kernel(const uint32_t* __restrict__ K
             const int sp = (lv_left >= lv_here) ? i - 1 : i;
             const int parent = pair_scan[pair_info[sp].x];
             const int slot = (ki >> (BH_KEY_BITS - 3 * (Lb + 1))) & 7;
-            cell_child[parent * 8 + slot] = (int)(0x80000000u | (uint32_t)i);
+            cell_child[(size_t)parent * 8 + slot] = (int)(0x80000000u | (uint32_t)i);
             kid_src[(size_t)parent * 8 + slot] = __ldg(posm + i);   // what the traversal reads when it opens `parent`
         }
 
@@ -230,7 +230,7 @@ __global__ void __launch_bounds__(TB) link_kernel(const uint32_t* __restrict__ K
                     const int sp = (a >= b) ? l - 1 : r;
                     parent = pair_scan[pair_info[sp].x];
                     slot = (ki >> (BH_KEY_BITS - 3 * (Lp + 1))) & 7;
-                    cell_child[parent * 8 + slot] = c;
+                    cell_child[(size_t)parent * 8 + slot] = c;
                     kid_lv[(size_t)parent * 8 + slot] = (uint8_t)(L | ((L == BH_MAX_LEVEL) << 7));
                 } else {
                     sc->root = c;

@@ -120,6 +120,11 @@ def lib() -> C.CDLL:
     L.bh_sort_pairs_u32.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, C.POINTER(C.c_size_t), vp]
     L.bh_direct_sample.argtypes = [vp, vp, i32, vp]
     L.bh_energy.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+    L.bh_export_visuals.argtypes = [vp, vp, vp, vp]
+    L.bh_momentum.argtypes = [vp, vp]
+    L.bh_dump_text.argtypes = [vp, C.c_char_p]
+    L.bh_save_checkpoint.argtypes = [vp, C.c_char_p]
+    L.bh_load_checkpoint.argtypes = [vp, C.c_char_p]
     L.bh_ic_refdisk.argtypes = [i64, C.c_uint] + [vp] * 7
     L.bh_ic_uniform_cube.argtypes = [i64, C.c_uint64, f32] + [vp] * 7
     L.bh_ic_plummer.argtypes = [i64, C.c_uint64, f32, f32, f32, f32] + [vp] * 7
@@ -307,6 +312,24 @@ class BHEngine:
         ke, pe = C.c_double(), C.c_double()
         _check(lib().bh_energy(self._ctx, C.byref(ke), C.byref(pe)), "bh_energy")
         return float(ke.value), float(pe.value)
+
+    def momentum(self):
+        out = np.zeros(7, np.float64)
+        _check(lib().bh_momentum(self._ctx, _vp(out)), "bh_momentum")
+        return out
+
+    def export_visuals(self, vbo_p, vbo_c, stream: int = 0):
+        """≙ updateVisualsKernel (nbody_v5.cu:278-292); DEVICE pointers / torch tensors."""
+        _check(lib().bh_export_visuals(self._ctx, _vp(vbo_p), _vp(vbo_c), C.c_void_p(stream)), "bh_export_visuals")
+
+    def dump_text(self, path: str):
+        _check(lib().bh_dump_text(self._ctx, path.encode()), "bh_dump_text")
+
+    def save_checkpoint(self, path: str):
+        _check(lib().bh_save_checkpoint(self._ctx, path.encode()), "bh_save_checkpoint")
+
+    def load_checkpoint(self, path: str):
+        _check(lib().bh_load_checkpoint(self._ctx, path.encode()), "bh_load_checkpoint")
 
     # -- multi-GPU slices
     def set_slice(self, rank: int, world: int):

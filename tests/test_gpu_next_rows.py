@@ -1,0 +1,105 @@
+"""Callers either side of the step path: visual export, diagnostics, state I/O, bench front-end."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+f = np.float32
+
+
+def test_visual_export_matches_updateVisualsKernel(bh):
+    """nbody_v5.cu:278-292: interleaved xyz + speed colour ramp, original body order."""
+    import torch
+
+    n = 5000
+    soa = bh.ic_refdisk(n, 42)
+    with bh.BHEngine(n) as eng:
+        eng.load_soa(*soa)
+        eng.simulation_step(2)
+        vp = torch.zeros(3 * n, dtype=torch.float32, device="cuda")
+        vc = torch.zeros(3 * n, dtype=torch.float32, device="cuda")
+        eng.export_visuals(vp, vc)
+        torch.cuda.synchronize()
+        px, py, pz, vx, vy, vz = eng.read_soa(want_acc=False)
+    p = vp.cpu().numpy().reshape(n, 3)
+    c = vc.cpu().numpy().reshape(n, 3)
+    assert p[:, 0].tobytes() == px.tobytes() and p[:, 1].tobytes() == py.tobytes() and p[:, 2].tobytes() == pz.tobytes()
+    speed = np.sqrt(vx.astype(np.float64) ** 2 + vy.astype(np.float64) ** 2 + vz.astype(np.float64) ** 2)
+    t = np.minimum(speed / 150.0, 1.0)
+    want = np.stack([0.4 + 0.6 * t, 0.3 + 0.4 * t, 1.0 - 0.7 * t], 1)
+    assert np.abs(c - want).max() < 1e-6
+
+
+def test_momentum_and_its_conservation(bh):
+    n = 20000
+    soa = bh.ic_plummer(n, 3, 200.0, 10.0, 4.5, 0.5)
+    m = soa[6].astype(np.float64)
+    pos = np.stack(soa[:3], 1).astype(np.float64)
+    vel = np.stack(soa[3:6], 1).astype(np.float64)
+    want = np.concatenate([[m.sum()], (m[:, None] * vel).sum(0), np.cross(pos, m[:, None] * vel).sum(0)])
+    with bh.BHEngine(n) as eng:
+        eng.load_soa(*soa)
+        got = eng.momentum()
+        assert np.allclose(got, want, rtol=1e-9, atol=1e-6)
+        eng.simulation_step(20)
+        after = eng.momentum()
+    scale = (m[:, None] * np.abs(vel)).sum()
+    # Barnes-Hut forces are not exactly antisymmetric: momentum drifts only at the multipole-error level
+    assert np.abs(after[1:4] - got[1:4]).max() < 1e-4 * scale
+
+
+def test_text_dump_has_the_old_tools_format(bh, tmp_path):
+    """output_bh.txt:1-5."""
+    n = 300
+    soa = bh.ic_uniform_cube(n, 9, 1000.0)
+    path = str(tmp_path / "out.txt")
+    with bh.BHEngine(n) as eng:
+        eng.load_soa(*soa)
+        eng.simulation_step(4)
+        eng.dump_text(path)
+        ref = eng.read_soa(want_acc=False)
+    lines = open(path).read().splitlines()
+    assert lines[0] == "# Barnes-Hut N-Body Simulation Results"
+    assert lines[1] == "# Final positions and velocities after 4 steps"
+    assert lines[2] == "# Bodies: 300, Theta: 0.50, dt: 0.020" and lines[3] == "# Format: x y z vx vy vz"
+    rows = np.array([[float(x) for x in ln.split()] for ln in lines[4:]])
+    assert rows.shape == (n, 6) and np.abs(rows - np.stack(ref, 1)).max() < 1e-6 * 1000 + 1e-6
+
+
+def test_checkpoint_resume_is_bit_exact(bh, tmp_path):
+    n = 30000
+    soa = bh.ic_refdisk(n, 42)
+    path = str(tmp_path / "ckpt.bin")
+    with bh.BHEngine(n) as eng:
+        eng.load_soa(*soa)
+        eng.simulation_step(3)
+        eng.save_checkpoint(path)
+        eng.simulation_step(4)
+        want = (eng.debug_get(bh.DBG.POSM), eng.debug_get(bh.DBG.VEL), eng.debug_get(bh.DBG.IDS))
+    with bh.BHEngine(n) as eng:
+        eng.load_checkpoint(path)
+        assert eng.stat(bh.STAT.STEPS) == 3 and eng.n == n
+        eng.simulation_step(4)
+        got = (eng.debug_get(bh.DBG.POSM), eng.debug_get(bh.DBG.VEL), eng.debug_get(bh.DBG.IDS))
+    assert got[0].tobytes() == want[0].tobytes() and got[1].tobytes() == want[1].tobytes() and (got[2] == want[2]).all()
+    with bh.BHEngine(100) as small:
+        with pytest.raises(bh.BHError):
+            small.load_checkpoint(path)          # does not fit: refused, not truncated
+
+
+def test_bench_front_end_prints_the_reference_table(bh):
+    """nbody_v5_bench.cu:287,350-351,366."""
+    exe = os.path.join(os.path.dirname(bh.library_path()), "nbody_bench")
+    if not os.path.exists(exe):
+        pytest.skip("front-end not built")
+    r = subprocess.run([exe, "--n", "20000", "--frames", "3", "--phases"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    out = r.stdout.splitlines()
+    assert out[0] == "Pokretanje Benchmarka za N = 20000..."
+    assert any(ln.startswith("Frame      | Trajanje (ms)   | FPS") for ln in out)
+    assert sum(1 for ln in out if ln[:1].isdigit() and "|" in ln) == 3
+    assert any("interactions/s" in ln for ln in out) and any("octree build" in ln for ln in out)
