@@ -177,13 +177,27 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_
 
         uint32_t prior = 0;
         if (tile > 0) {
+            // Decoupled look-back, LB_WIDE predecessors per round trip: the statuses of tiles p, p-1, ...
+            // are fetched together (independent loads) and consumed in order.  The chain of dependent L2
+            // round trips, which bounds the first wave when hundreds of tiles start together, shrinks by
+            // the same factor.
+            constexpr int LB_WIDE = 8;
             int p = (int)tile - 1;
             unsigned spins = 0;
-            while (true) {
-                uint32_t s = lookback[(size_t)p * RADIX + d];
-                if (s & ST_INCL) { prior += s & ST_MASK; break; }
-                if (s & ST_LOCAL) { prior += s & ST_MASK; --p; spins = 0; continue; }
-                if (++spins > SPIN_LIMIT) { atomicOr(err_flag, BH_DERR_SORT_SPIN); break; }
+            bool done = false;
+            while (!done) {
+                uint32_t st[LB_WIDE];
+#pragma unroll
+                for (int j = 0; j < LB_WIDE; ++j) st[j] = (p - j >= 0) ? lookback[(size_t)(p - j) * RADIX + d] : 0x80000000u;
+#pragma unroll
+                for (int j = 0; j < LB_WIDE; ++j) {
+                    if (done) break;
+                    const uint32_t sv = st[j];
+                    if (sv & ST_INCL) { prior += sv & ST_MASK; done = true; }
+                    else if (sv & ST_LOCAL) { prior += sv & ST_MASK; --p; spins = 0; }
+                    else break;   // not published yet: poll again from this tile
+                }
+                if (!done && ++spins > SPIN_LIMIT) { atomicOr(err_flag, BH_DERR_SORT_SPIN); break; }
             }
             *my_status = ST_INCL | (prior + running);
         }
