@@ -1,0 +1,110 @@
+"""Behaviour of the C ABI itself: call order, error codes, re-use of a context, degenerate sizes."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+
+pytestmark = pytest.mark.gpu
+f = np.float32
+
+
+def test_call_order_and_argument_errors(bh):
+    L = bh.lib()
+    eng = bh.BHEngine(1000)
+    assert L.bh_step(eng._ctx, 1, None) == -3              # BH_E_STATE: nothing imported yet
+    assert L.bh_export_soa(eng._ctx, *([None] * 9), None) == -3
+    soa = bh.ic_uniform_cube(2000, 1, 100.0)
+    with pytest.raises(bh.BHError):
+        eng.load_soa(*soa)                                 # n > n_max
+    assert L.bh_run_phase(eng._ctx, 99, None) == -1
+    assert L.bh_debug_get(eng._ctx, 0, None, 24) == -1
+    eng.close()
+    with pytest.raises(bh.BHError):
+        bh.BHEngine(100, softening=0.0)                    # softening must be positive (self term)
+    with pytest.raises(bh.BHError):
+        bh.BHEngine(100, leaf_cap=8)                       # declared but not implemented: refused loudly
+
+
+@pytest.mark.parametrize("n", [1, 2])
+def test_tiny_systems(bh, n):
+    soa = [np.array([1.0, 4.0][:n], f), np.array([2.0, 6.0][:n], f), np.array([3.0, 3.0][:n], f),
+           np.array([0.5, 0.0][:n], f), np.zeros(n, f), np.zeros(n, f), np.array([2.0, 3.0][:n], f)]
+    with bh.BHEngine(8) as eng:
+        eng.load_soa(*soa)
+        eng.simulation_step(1)
+        eng.check_device_error()
+        out = eng.read_soa()
+    if n == 1:   # a lone body feels nothing and drifts: x += v*dt (bench:246)
+        assert out[6][0] == 0 and out[7][0] == 0 and out[0][0] == f(np.float64(f(0.5)) * np.float64(f(0.02)) + 1.0)
+    else:        # two bodies: the hand formula of bench:205-213
+        d = np.array([3.0, 4.0, 0.0])
+        want0 = 0.5 * 3.0 * d / (25.0 + 50.0) ** 1.5
+        assert np.allclose([out[6][0], out[7][0], out[8][0]], want0, rtol=1e-5)
+        assert np.allclose([out[6][1], out[7][1], out[8][1]], -0.5 * 2.0 * d / 75.0 ** 1.5, rtol=1e-5)
+
+
+def test_context_reuse_with_different_sizes_and_zero_steps(bh):
+    with bh.BHEngine(40000) as eng:
+        for n in (40000, 1234, 40000):
+            soa = bh.ic_refdisk(n, 42)
+            posm, vel, ids = O.soa_to_internal(soa)
+            want = O.engine_step(posm, vel, ids, 2)
+            eng.load_soa(*soa)
+            eng.simulation_step(0)
+            eng.simulation_step(2)                         # graph is re-captured when n changes
+            eng.check_device_error()
+            assert eng.n == n and eng.stat(bh.STAT.STEPS) == 2
+            assert (eng.debug_get(bh.DBG.IDS) == want["ids"]).all()
+            assert O.rel_rms(eng.debug_get(bh.DBG.POSM)[:, :3], want["posm"][:, :3]) < 1e-6
+
+
+def test_two_contexts_are_independent(bh):
+    a_soa, b_soa = bh.ic_uniform_cube(5000, 1, 1000.0), bh.ic_refdisk(7000, 42)
+    with bh.BHEngine(5000) as a, bh.BHEngine(7000) as b:
+        a.load_soa(*a_soa)
+        b.load_soa(*b_soa)
+        a.simulation_step(2)
+        b.simulation_step(2)
+        ra, rb = a.read_soa(), b.read_soa()
+    with bh.BHEngine(5000) as a2:
+        a2.load_soa(*a_soa)
+        a2.simulation_step(2)
+        ra2 = a2.read_soa()
+    for x, y in zip(ra, ra2):
+        assert x.tobytes() == y.tobytes()
+    assert len(rb[0]) == 7000
+
+
+def test_device_pointer_import_export(bh):
+    """bh_import_soa / bh_export_soa with caller-owned DEVICE arrays (the reference's own layout, bench:32-35)."""
+    import torch
+
+    n = 8000
+    soa = bh.ic_refdisk(n, 42)
+    dev = [torch.from_numpy(x).cuda() for x in soa]
+    out = [torch.zeros(n, dtype=torch.float32, device="cuda") for _ in range(9)]
+    stream = torch.cuda.current_stream().cuda_stream
+    with bh.BHEngine(n) as eng:
+        eng.load_soa_device(dev, n, stream)
+        eng.simulation_step(3, stream)
+        bh.lib().bh_export_soa(eng._ctx, *[C.c_void_p(t.data_ptr()) for t in out], C.c_void_p(stream))
+        torch.cuda.synchronize()
+        host = eng.read_soa()
+    for t, h in zip(out, host):
+        assert t.cpu().numpy().tobytes() == h.tobytes()
+
+
+def test_theta_zero_is_the_direct_sum(bh):
+    """theta = 0 rejects every cell: the traversal degenerates to all pairs (via buckets and loose bodies)."""
+    n = 700
+    soa = bh.ic_uniform_cube(n, 4, 300.0)
+    posm, _, _ = O.soa_to_internal(soa)
+    want = O.direct_sum(posm, np.arange(n))
+    with bh.BHEngine(n, theta=0.0) as eng:
+        eng.load_soa(*soa)
+        eng.simulation_step(1)
+        out = eng.read_soa()
+        assert eng.stat(bh.STAT.INTERACTIONS_CELL) == 0 and eng.stat(bh.STAT.INTERACTIONS_BODY) == n * n
+    assert O.rel_rms(np.stack(out[6:9], 1), want) < 2e-6
