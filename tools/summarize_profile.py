@@ -48,7 +48,9 @@ if os.path.exists(rep):
             "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "dram__bytes_read.sum", "dram__bytes_write.sum",
             "launch__registers_per_thread", "launch__grid_size", "launch__occupancy_limit_registers",
             "launch__occupancy_limit_shared_mem", "smsp__thread_inst_executed_per_inst_executed.ratio",
-            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed"]
+            "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+            "smsp__warps_eligible.avg.per_cycle_active"]
     keep += [n for n in h if n.startswith("smsp__average_warps_issue_stalled") and n.endswith("per_issue_active.ratio")]
     vals = {n: (v[i], u[i]) for i, n in enumerate(h) if n in keep}
     with open(os.path.join(PROF, f"{tag}_{kernel}_{workload}.md"), "w") as f:
