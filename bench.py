@@ -29,6 +29,8 @@ WORKLOADS = {
     "refdisk_500k": dict(n=500_000, ic="refdisk", desc="reference code default N=500,000 (bench:31)"),
     "plummer_1m": dict(n=1_000_000, ic="plummer", desc="configs[2]: 1,000,000-body Plummer sphere a=200 cut 10a"),
     "plummer_16m": dict(n=16_000_000, ic="plummer", desc="configs[3]: 16,000,000-body Plummer sphere a=200 cut 10a"),
+    "twodisk_16m": dict(n=16_000_000, ic="twodisk", desc="two-galaxy collision, 16,000,000 bodies (small version of configs[4])"),
+    "twodisk_256m": dict(n=256_000_000, ic="twodisk", desc="configs[4]: 256,000,000-body two-galaxy collision (replicated-tree mode; LET not built)"),
 }
 
 
@@ -37,6 +39,8 @@ def make_ic(bh, w):
         return bh.ic_refdisk(w["n"], 42)
     if w["ic"] == "uniform":
         return bh.ic_uniform_cube(w["n"], 42, 1000.0)
+    if w["ic"] == "twodisk":
+        return bh.ic_two_disks(w["n"], 42, 4000.0, 20.0, 8.0)
     return bh.ic_plummer(w["n"], 42, 200.0, 10.0, 4.5, 0.5)
 
 

@@ -120,6 +120,8 @@ enum {
     BH_PHASE_COUNT
 };
 int  bh_phase_ms(bh_ctx* ctx, float out[BH_PHASE_COUNT]);
+/* Change BH_FLAG_* after creation (e.g. switch the phase timer on for a few steps). */
+int  bh_set_flags(bh_ctx* ctx, int flags);
 
 /* Run ONE phase of the step on the context's current state (parity tests). */
 int  bh_run_phase(bh_ctx* ctx, int phase, void* stream);
@@ -221,6 +223,11 @@ int  bh_ic_refdisk(int64_t n, unsigned seed,
 int  bh_ic_uniform_cube(int64_t n, uint64_t seed, float half_edge,
                         float* px, float* py, float* pz,
                         float* vx, float* vy, float* vz, float* mass);
+/* two refdisk-style discs (bench:297-307 per disc) at centres -/+ (sep/2,0,0) approaching with
+ * -/+ (vx,vy,0): BASELINE.json configs[4].  Counter-based RNG, multi-threaded. */
+int  bh_ic_two_disks(int64_t n, uint64_t seed, float sep, float vx, float vy,
+                     float* px, float* py, float* pz,
+                     float* vx_out, float* vy_out, float* vz_out, float* mass);
 int  bh_ic_plummer(int64_t n, uint64_t seed, float scale_a, float rcut_in_a,
                    float body_mass, float G,
                    float* px, float* py, float* pz,

@@ -16,6 +16,7 @@ from .engine import (  # noqa: F401
     build_library,
     ic_plummer,
     ic_refdisk,
+    ic_two_disks,
     ic_uniform_cube,
     lib,
     library_path,

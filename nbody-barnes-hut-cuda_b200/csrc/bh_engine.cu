@@ -344,6 +344,12 @@ int bh_run_phase(bh_ctx* c, int phase, void* stream) {
     return 0;
 }
 
+int bh_set_flags(bh_ctx* c, int flags) {
+    if (!c) return BH_E_INVAL;
+    c->prm.flags = flags;
+    return 0;
+}
+
 int bh_phase_ms(bh_ctx* c, float out[BH_PHASE_COUNT]) {
     if (!c || !out) return BH_E_INVAL;
     memcpy(out, c->phase_ms, sizeof(c->phase_ms));

@@ -13,6 +13,8 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstdint>
+#include <thread>
+#include <vector>
 
 #ifndef M_PI
 #define M_PI 3.14159265358979323846
@@ -113,5 +115,39 @@ extern "C" int bh_ic_plummer(int64_t n, uint64_t seed, float scale_a, float rcut
         vz[i] = (float)(v * cz);
         mass[i] = body_mass;
     }
+    return 0;
+}
+
+// BASELINE.json configs[4] / SURVEY §8d(5): two discs built like main()'s (bench:297-307), centred at
+// -/+ (sep/2, 0, 0) and approaching with -/+ (vx, vy, 0).  Body i draws from its own SplitMix64 stream
+// (seed, i), so the result does not depend on the thread count.
+extern "C" int bh_ic_two_disks(int64_t n, uint64_t seed, float sep, float vx0, float vy0,
+                               float* px, float* py, float* pz, float* vx, float* vy, float* vz, float* mass) {
+    if (n < 0 || !px || !py || !pz || !vx || !vy || !vz || !mass) return BH_E_INVAL;
+    const float G = 0.5f;
+    auto work = [&](int64_t lo, int64_t hi) {
+        for (int64_t i = lo; i < hi; ++i) {
+            SplitMix64 rng(seed * 0x9E3779B97F4A7C15ull + (uint64_t)i * 0xD1B54A32D192ED03ull);
+            const float side = (i & 1) ? 1.0f : -1.0f;
+            float r = 200.0f + rng.uniform() * 1500.0f;
+            float a = (float)((double)(rng.uniform() * 2.0f) * M_PI);
+            float ca = cosf(a), sa = sinf(a);
+            px[i] = r * ca + side * 0.5f * sep;
+            py[i] = r * sa;
+            pz[i] = (rng.uniform() - 0.5f) * (r * 0.05f);
+            mass[i] = 2.0f + rng.uniform() * 5.0f;
+            float vmag = sqrtf(G * (50000.0f + r * 100.0f) / r);
+            vx[i] = -sa * vmag - side * vx0;
+            vy[i] = ca * vmag - side * vy0;
+            vz[i] = (rng.uniform() - 0.5f) * 2.0f;
+        }
+    };
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt < 1) nt = 1;
+    if (nt > 16) nt = 16;
+    if (n < 100000) { work(0, n); return 0; }
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, n * t / nt, n * (t + 1) / nt);
+    for (auto& x : th) x.join();
     return 0;
 }

@@ -127,6 +127,8 @@ def lib() -> C.CDLL:
     L.bh_load_checkpoint.argtypes = [vp, C.c_char_p]
     L.bh_ic_refdisk.argtypes = [i64, C.c_uint] + [vp] * 7
     L.bh_ic_uniform_cube.argtypes = [i64, C.c_uint64, f32] + [vp] * 7
+    L.bh_ic_two_disks.argtypes = [i64, C.c_uint64, f32, f32, f32] + [vp] * 7
+    L.bh_set_flags.argtypes = [vp, i32]
     L.bh_ic_plummer.argtypes = [i64, C.c_uint64, f32, f32, f32, f32] + [vp] * 7
     L.bh_probe_fp32_tflops.argtypes = [i32, C.POINTER(f32)]
     L.bh_probe_hbm_gbs.argtypes = [i32, C.POINTER(f32)]
@@ -163,6 +165,13 @@ def ic_plummer(n: int, seed: int = 42, scale_a: float = 200.0, rcut_in_a: float 
                body_mass: float = 4.5, G: float = 0.5):
     a = _soa(n)
     _check(lib().bh_ic_plummer(n, seed, scale_a, rcut_in_a, body_mass, G, *[_vp(x) for x in a]), "bh_ic_plummer")
+    return a
+
+
+def ic_two_disks(n: int, seed: int = 42, sep: float = 4000.0, vx: float = 20.0, vy: float = 8.0):
+    """BASELINE.json configs[4]: two reference-style discs on a collision course."""
+    a = _soa(n)
+    _check(lib().bh_ic_two_disks(n, seed, sep, vx, vy, *[_vp(x) for x in a]), "bh_ic_two_disks")
     return a
 
 
@@ -276,6 +285,9 @@ class BHEngine:
 
     def run_phase(self, phase: int, stream: int = 0):
         _check(lib().bh_run_phase(self._ctx, phase, C.c_void_p(stream)), f"bh_run_phase({phase})")
+
+    def set_flags(self, flags: int):
+        _check(lib().bh_set_flags(self._ctx, flags), "bh_set_flags")
 
     def phase_ms(self):
         out = (C.c_float * PHASE.COUNT)()
