@@ -135,13 +135,18 @@ def run_reference_arm(args, w):
         assert rc == 0, f"ref_init {rc}"
         ms = C.c_float()
         clocks = ClockSampler()
-        assert L.ref_step(args.warmup, C.byref(ms)) == 0
+        # the reference needs ~50 ms/step at 1M and seconds per step at 16M (one-thread bounding box,
+        # N/1024 insert launches): bound the sample so the arm ends within minutes
+        steps = args.steps if w["n"] <= 1_000_000 else min(args.steps, 5)
+        warm = args.warmup if w["n"] <= 1_000_000 else 3
+        assert L.ref_step(warm, C.byref(ms)) == 0
         clocks.start()
-        assert L.ref_step(args.steps, C.byref(ms)) == 0
+        assert L.ref_step(steps, C.byref(ms)) == 0
         ck = clocks.stop()
         L.ref_free()
-        value = w["n"] * args.steps / (ms.value * 1e-3)
-        line.update({"value": value, "ms_per_step": ms.value / args.steps, "interactions_per_body": 1.0,
+        value = w["n"] * steps / (ms.value * 1e-3)
+        line["steps"], line["warmup"] = steps, warm
+        line.update({"value": value, "ms_per_step": ms.value / steps, "interactions_per_body": 1.0,
                      "interactions_per_s": value, "clocks": ck, "gpu_launches": None,
                      "reference_kind": "UNMODIFIED nbody_v5_bench.cu kernels + simulationStep() compiled -arch=sm_100 "
                                        "(oracle/ref_wrap.cu includes the source in place), run on this B200; "
@@ -288,6 +293,28 @@ def run_ours(args, w):
     }
     if not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(w)
+    if args.workload == "refdisk_1m" and not args.no_scale_ref:
+        # the N>1 runs use the 16M-body Plummer sphere (BASELINE.json configs[3]); measure it on this one GPU
+        # too so the 1/2/4/8-GPU series can be read off the same workload
+        w2 = WORKLOADS["plummer_16m"]
+        soa2 = make_ic(bh, w2)
+        eng2 = bh.BHEngine(w2["n"], device=local)
+        eng2.load_soa(*soa2)
+        eng2.simulation_step(3, stream)
+        barrier()
+        a2, b2 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a2.record()
+        eng2.simulation_step(10, stream)
+        b2.record()
+        barrier()
+        eng2.check_device_error()
+        ms2 = a2.elapsed_time(b2) / 10
+        inter2 = eng2.stat(bh.STAT.INTERACTIONS_CELL) + eng2.stat(bh.STAT.INTERACTIONS_BODY)
+        eng2.close()
+        line["scale_ref_1gpu"] = {"workload": "plummer_16m", "n_bodies": w2["n"], "ms_per_step": ms2,
+                                  "value": w2["n"] / (ms2 * 1e-3), "unit": "body-steps/s",
+                                  "interactions_per_body": inter2 / w2["n"],
+                                  "note": "same workload as the default --gpus 2/4/8 runs (strong scaling)"}
     return line
 
 
@@ -302,6 +329,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-scale-ref", action="store_true", help="skip the 16M-body single-GPU reference point")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
