@@ -237,6 +237,7 @@ def run_ours(args, w):
     psteps = max(3, min(args.steps, 20))
     engt.simulation_step(psteps, stream)
     phases = {k: v / psteps for k, v in engt.phase_ms().items()}
+    inter_t = engt.stat(bh.STAT.INTERACTIONS_CELL) + engt.stat(bh.STAT.INTERACTIONS_BODY)   # of the steps just timed
     engt.close()
     fp32_peak = bh.probe_fp32_tflops(local)
     peaks = {}
@@ -245,7 +246,7 @@ def run_ours(args, w):
     except Exception:
         pass
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
-    force_tflops = FLOP_PER_INTERACTION * inter / (phases["force"] * 1e-3) / 1e12
+    force_tflops = FLOP_PER_INTERACTION * inter_t / (phases["force"] * 1e-3) / 1e12
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "force_traffic.json"))).get(args.workload)

@@ -75,8 +75,9 @@ int  bh_import_soa(bh_ctx* ctx,
                    const float* px, const float* py, const float* pz,
                    const float* vx, const float* vy, const float* vz,
                    const float* mass, int64_t n, void* stream);
-/* Same, HOST pointers (pageable or pinned); copies through the context's
- * pinned staging buffer.                                                  */
+/* Same, HOST pointers (pinned memory gives full PCIe rate, pageable works);
+ * copies into the context's device staging buffer, then imports.  Returns
+ * after the copy has completed.                                           */
 int  bh_import_soa_host(bh_ctx* ctx,
                         const float* px, const float* py, const float* pz,
                         const float* vx, const float* vy, const float* vz,
@@ -139,7 +140,8 @@ enum {
     BH_DBG_VEL,          /* float4[n]  vx,vy,vz,0  current state            */
     BH_DBG_ACC,          /* float4[n]  ax,ay,az,0  sorted order of the last
                             step (slot i pairs with *_SORTED slot i)        */
-    BH_DBG_CELL_META,    /* int4[cells]   first,count,level|bucket<<8,parent */
+    BH_DBG_CELL_META,    /* int4[cells]   first,count,level|bucket<<8|slot<<12,parent
+                            (slot = which child of its parent the cell is)   */
     BH_DBG_CELL_COM,     /* float4[cells] comx,comy,comz,mass               */
     BH_DBG_CELL_CHILD,   /* i32[cells*8]  child table                       */
     BH_DBG_POSM_SORTED,  /* float4[n]  positions the last sort/force used

@@ -11,7 +11,7 @@
 #define BH_KEY_BITS 30
 #define BH_MAX_LEVEL 10
 #define BH_GROUP 32          // bodies per traversal group (one warp)
-#define BH_NUM_SMS_FALLBACK 148
+#define BH_NUM_SMS_FALLBACK 148   // B200: 2 dies x 74 SMs; grids are sized in multiples of it
 
 // device error flag bits (BH_STAT_DEVICE_ERROR)
 #define BH_DERR_SORT_SPIN   1   // onesweep look-back exceeded its spin budget
@@ -55,7 +55,6 @@ __device__ __forceinline__ int bh_shared_digits(uint32_t a, uint32_t b) {
     return x == 0 ? BH_MAX_LEVEL : (__clz((int)x) - (32 - BH_KEY_BITS)) / 3;
 }
 
-__device__ __forceinline__ float4 bh_ldg4(const float4* p) { return __ldg(p); }
 
 #define BH_CUDA_TRY(expr)                                  \
     do {                                                   \
