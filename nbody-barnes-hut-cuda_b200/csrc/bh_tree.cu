@@ -342,6 +342,8 @@ int bh_com_launch(const float4* posm, int64_t n, const int4* cell_meta, const in
                   int32_t* cell_arrive, float4* cell_mom, float4* cell_com, float4* kid_src,
                   BhDevScalars* sc, cudaStream_t st) {
     if (n < 2) return 0;
-    com_kernel<<<capped_grid(n / 2 + 1, TB), TB, 0, st>>>(posm, cell_meta, cell_child, cell_arrive, cell_mom, cell_com, kid_src, sc);
+    // one thread per possible cell, no grid-stride: a thread that climbs towards the root must not delay
+    // the leaf-level cells a strided loop would hand it next
+    com_kernel<<<(int)((n + TB - 1) / TB), TB, 0, st>>>(posm, cell_meta, cell_child, cell_arrive, cell_mom, cell_com, kid_src, sc);
     return (int)cudaGetLastError();
 }

@@ -15,5 +15,12 @@ eng.simulation_step(5)
 eng.simulation_step(20)
 ms = eng.phase_ms()
 print(os.environ.get("BH_LIB", "default").split("/")[-1], wl, {k: round(v / 20, 4) for k, v in ms.items()},
-      "int/body", (eng.stat(bh.STAT.INTERACTIONS_CELL) + eng.stat(bh.STAT.INTERACTIONS_BODY)) / w["n"])
+      "int/body", (eng.stat(bh.STAT.INTERACTIONS_CELL) + eng.stat(bh.STAT.INTERACTIONS_BODY)) / w["n"],
+      "cell/body", eng.stat(bh.STAT.INTERACTIONS_CELL) / w["n"], "direct/body", eng.stat(bh.STAT.INTERACTIONS_BODY) / w["n"],
+      "cells/n", eng.stat(bh.STAT.CELLS) / w["n"])
+import numpy as np
+meta = eng.debug_get(bh.DBG.CELL_META)
+bucket = ((meta[:, 2] >> 8) & 1) == 1
+print("buckets", int(bucket.sum()), "bodies in buckets", int(meta[bucket, 1].sum()), "max bucket", int(meta[bucket, 1].max()) if bucket.any() else 0,
+      "mean bucket", float(meta[bucket, 1].mean()) if bucket.any() else 0)
 eng.check_device_error()
