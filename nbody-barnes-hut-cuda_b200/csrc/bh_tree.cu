@@ -293,10 +293,12 @@ __global__ void __launch_bounds__(TB) com_kernel(const float4* __restrict__ posm
             int ncc = 0;
 #pragma unroll
             for (int q = 0; q < 8; ++q) ncc += (e[q] >= 0 && e[q] != BH_CHILD_EMPTY);
-            __threadfence();
+            __threadfence();   // publish this cell's moments (st.cg) before announcing arrival
             const int old = atomicAdd(arrive + p, 1);
             if (old + 1 < ncc) break;
-            __threadfence();
+            // last arrival: the siblings' moments were fenced before their own atomics and are read with
+            // ld.cg (L2, the coherence point) below, after the atomic's result is known — the pattern of the
+            // CUDA threadFenceReduction sample; no second fence is needed
             Moments t = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
             for (int q = 0; q < 8; ++q) {   // slot order => run-to-run identical sums
