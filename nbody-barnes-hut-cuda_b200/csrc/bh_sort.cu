@@ -132,6 +132,16 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_
         key[k] = i < n ? __ldg(keys_in + i) : 0xFFFFFFFFu;
     }
 
+    // values: requested now so that their latency hides behind the ranking (a 1M-pair sort has fewer
+    // than two tiles per SM: nothing else would cover it)
+    uint32_t val[ITEMS];
+#pragma unroll
+    for (int k = 0; k < ITEMS; ++k) {
+        int64_t i = warp_base + k * 32 + lane;
+        if (IOTA) val[k] = (uint32_t)i;
+        else val[k] = i < n ? __ldg(vals_in + i) : 0u;
+    }
+
     // ---- stable in-warp ranking with match-any digit groups --------------------------------
     uint32_t rank[ITEMS];
     uint32_t* my_hist = s_whist[warp];
@@ -212,14 +222,6 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_
         const uint32_t d = (key[k] >> shift) & mask;
         pos[k] = s_tile_excl[d] + s_whist[warp][d] + rank[k];
         s_buf[pos[k]] = key[k];
-    }
-    // the values are fetched only now (they would otherwise sit in 16 registers through the ranking)
-    uint32_t val[ITEMS];
-#pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        int64_t i = warp_base + k * 32 + lane;
-        if (IOTA) val[k] = (uint32_t)i;
-        else val[k] = i < n ? __ldg(vals_in + i) : 0u;
     }
     __syncthreads();
     uint32_t dst[ITEMS];
