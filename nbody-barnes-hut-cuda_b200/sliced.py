@@ -29,6 +29,12 @@ def slice_bounds(n: int, rank: int, world: int):
     return first, last - first, per
 
 
+def C_void(t):
+    import ctypes as C
+
+    return C.c_void_p(t.data_ptr())
+
+
 class _DevView:
     """Zero-copy torch view of a raw device pointer via the CUDA array interface."""
 
@@ -70,6 +76,32 @@ class SlicedSimulation:
         for _ in range(nsteps):
             self.eng.simulation_step(1, stream)
             allgather_slices(self.dist, self.views, self.rank, self.per)
+
+    def step_host(self, host_in, host_out, nsteps: int = 1):
+        """End-to-end step with HOST state, sharded over the ranks' PCIe links: every rank uploads 1/world of
+        the 7 SoA arrays, an all-gather completes them on every device, bh_import_soa + sliced step(s) +
+        slice all-gather run as usual, and every rank reads back 1/world of the 6 result arrays (original body
+        order) into host_out — the host ends up with the full state, spread over the ranks.
+        host_in: 7 pinned float32 torch tensors [n]; host_out: 6 pinned float32 torch tensors [n]."""
+        torch, dist = self.torch, self.dist
+        n, world, rank = self.n, self.world, self.rank
+        chunk = (n + world - 1) // world
+        lo, hi = min(n, rank * chunk), min(n, (rank + 1) * chunk)
+        if not hasattr(self, "_soa_dev"):
+            self._soa_dev = [torch.empty(chunk * world, dtype=torch.float32, device=self.device) for _ in range(9)]
+        stream = torch.cuda.current_stream().cuda_stream
+        for k in range(7):
+            self._soa_dev[k][lo:hi].copy_(host_in[k][lo:hi], non_blocking=True)
+            dist.all_gather_into_tensor(self._soa_dev[k], self._soa_dev[k][rank * chunk:(rank + 1) * chunk])
+        self.eng.load_soa_device(self._soa_dev[:7], n, stream)
+        self.step(nsteps)
+        ptrs = [C_void(t) for t in self._soa_dev[:6]] + [None] * 3
+        from .engine import _check, lib
+        import ctypes as C
+        _check(lib().bh_export_soa(self.eng._ctx, *ptrs, C.c_void_p(stream)), "bh_export_soa")
+        for k in range(6):
+            host_out[k][lo:hi].copy_(self._soa_dev[k][lo:hi], non_blocking=True)
+        torch.cuda.synchronize()
 
     def close(self):
         self.eng.close()
@@ -128,33 +160,25 @@ def run_sliced_bench(args, w, bh, dist, rank, world, local):
     barrier()
     allgather_ms = ag0.elapsed_time(ag1) / 5
 
-    # e2e: every rank uploads the full host state (its own PCIe link), one sliced step, all-gather,
-    # rank 0 reads the full state back.  Skipped above 64M bodies (host memory: 7 pinned arrays per rank).
+    # e2e: host SoA in and out every step, sharded over the ranks' PCIe links (SlicedSimulation.step_host).
+    # Skipped above 64M bodies (13 pinned host arrays per rank).
     e2e = None
     if n <= 64_000_000:
-        pinned = [torch.from_numpy(x).pin_memory() for x in soa]
-        harr = [t.numpy() for t in pinned]
+        host_in = [torch.from_numpy(x).pin_memory() for x in soa]
+        host_out = [torch.empty(n, dtype=torch.float32).pin_memory() for _ in range(6)]
         esteps = 5
-
-        def e2e_once():
-            sim.eng.load_soa(*harr)
-            sim.eng.simulation_step(1, stream)
-            allgather_slices(dist, sim.views, rank, sim.per)
-            torch.cuda.synchronize()
-            if rank == 0:
-                sim.eng.read_soa(want_acc=False)
-
-        e2e_once()
+        sim.step_host(host_in, host_out, 1)
         barrier()
         t0 = time.perf_counter()
         for _ in range(esteps):
-            e2e_once()
+            sim.step_host(host_in, host_out, 1)
         barrier()
         e2e_s = torch.tensor([(time.perf_counter() - t0) / esteps], device=dev, dtype=torch.float64)
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
-        e2e = {"value": n / float(e2e_s.item()), "unit": "body-steps/s", "h2d_bytes_per_step": 28 * n * world,
+        e2e = {"value": n / float(e2e_s.item()), "unit": "body-steps/s", "h2d_bytes_per_step": 28 * n,
                "d2h_bytes_per_step": 24 * n, "ms_per_step": float(e2e_s.item()) * 1e3,
-               "api": "every rank bh_import_soa_host(full state), 1 sliced step, all-gather, rank 0 bh_export_soa_host"}
+               "api": "SlicedSimulation.step_host: each rank uploads 1/N of the host SoA, all-gather, bh_import_soa, "
+                      "1 sliced step, slice all-gather, bh_export_soa, each rank reads back 1/N"}
     cells = sim.eng.stat(bh.STAT.CELLS)
     sim.close()
     total_ms = float(ms.item())
