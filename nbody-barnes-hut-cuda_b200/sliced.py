@@ -151,6 +151,9 @@ def run_sliced_bench(args, w, bh, dist, rank, world, local):
             acc[k] = acc.get(k, 0.0) + v / psteps
         allgather_slices(dist, sim.views, rank, sim.per)
     sim.eng.set_flags(0)
+    force_all = torch.zeros(world, device=dev, dtype=torch.float32)
+    dist.all_gather_into_tensor(force_all, torch.tensor([acc["force"]], device=dev, dtype=torch.float32))
+    force_per_rank = [round(float(x), 3) for x in force_all.tolist()]
     ag0, ag1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ag0.record()
@@ -192,7 +195,8 @@ def run_sliced_bench(args, w, bh, dist, rank, world, local):
                    "l2": "state far larger than L2 (>= 5 GB context at 16M bodies); no flush between steps"},
         "interactions_per_body": float(inter.item()) / n,
         "interactions_per_s": float(inter.item()) * args.steps / (total_ms * 1e-3),
-        "phase_ms_rank0": {k: round(v, 4) for k, v in acc.items()}, "allgather_ms": allgather_ms,
+        "phase_ms_rank0": {k: round(v, 4) for k, v in acc.items()}, "force_ms_per_rank": force_per_rank,
+        "allgather_ms": allgather_ms,
         "cells": cells, "e2e": e2e,
         "gpu_launches": bench.LAUNCHES_PER_STEP * args.steps * world, "clocks": ck,
     }

@@ -31,11 +31,24 @@ def make_case(bh, kind, n, seed=1):
         pos[: n // 4] += rng.uniform(-40, 40, (n // 4, 3)).astype(f)
         return [pos[:, 0].copy(), pos[:, 1].copy(), pos[:, 2].copy(), z.copy(), z.copy(), z.copy(),
                 rng.uniform(2, 7, n).astype(f)]
+    if kind == "line":         # bodies on a line: a chain-like tree, the cell count approaches n-1 (worst-case pools)
+        x = np.sort(rng.uniform(-900, 900, n)).astype(f)
+        return [x, z.copy(), z.copy(), z.copy(), z.copy(), z.copy(), rng.uniform(2, 7, n).astype(f)]
+    if kind == "bigbucket":    # one very large identical-key bucket next to an ordinary cloud
+        pos = rng.uniform(-500, 500, (n, 3)).astype(f)
+        pos[: n // 2] = np.array([123.0, -45.0, 67.0], f)
+        return [pos[:, 0].copy(), pos[:, 1].copy(), pos[:, 2].copy(), z.copy(), z.copy(), z.copy(),
+                rng.uniform(2, 7, n).astype(f)]
+    if kind == "tracers":      # massless bodies feel forces and exert none
+        soa = bh.ic_uniform_cube(n, seed, 800.0)
+        soa[6][::3] = 0.0
+        return soa
     raise ValueError(kind)
 
 
 CASES = [("uniform", 2), ("uniform", 3), ("uniform", 31), ("uniform", 33), ("uniform", 1000), ("uniform", 16384),
-         ("disk", 50001), ("clustered", 20000), ("coincident", 500), ("lattice", 4096), ("plummer", 30000)]
+         ("disk", 50001), ("clustered", 20000), ("coincident", 500), ("lattice", 4096), ("plummer", 30000),
+         ("line", 20000), ("bigbucket", 12000), ("tracers", 9000)]
 
 
 @pytest.mark.parametrize("kind,n", CASES)
