@@ -61,6 +61,9 @@ typedef struct bh_ctx bh_ctx;
 /* Fill *p with the reference defaults listed above. */
 void bh_default_params(bh_params* p);
 int  bh_abi_version(void);
+/* bodies per traversal chunk (Morton-consecutive bodies handled by one warp); multi-GPU slices are
+ * whole chunks.                                                              */
+int  bh_group_size(void);
 const char* bh_error_string(int code);
 
 /* Replaces the 16 cudaMalloc calls + H2D copies of main()

@@ -10,7 +10,7 @@
 
 #define BH_KEY_BITS 30
 #define BH_MAX_LEVEL 10
-#define BH_GROUP 32          // bodies per traversal group (one warp)
+#define BH_GROUP 32          // bodies per traversal chunk (one warp, one body per lane)
 #define BH_NUM_SMS_FALLBACK 148   // B200: 2 dies x 74 SMs; grids are sized in multiples of it
 
 // device error flag bits (BH_STAT_DEVICE_ERROR)

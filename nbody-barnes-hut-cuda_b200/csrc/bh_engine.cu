@@ -167,6 +167,7 @@ void bh_default_params(bh_params* p) {
 }
 
 int bh_abi_version(void) { return BH_ABI_VERSION; }
+int bh_group_size(void) { return BH_GROUP; }
 
 const char* bh_error_string(int code) {
     switch (code) {

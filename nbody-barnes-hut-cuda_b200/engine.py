@@ -98,6 +98,7 @@ def lib() -> C.CDLL:
     L.bh_default_params.argtypes = [C.POINTER(BHParams)]
     L.bh_default_params.restype = None
     L.bh_abi_version.restype = i32
+    L.bh_group_size.restype = i32
     L.bh_error_string.argtypes = [i32]
     L.bh_error_string.restype = C.c_char_p
     L.bh_create.argtypes = [C.POINTER(vp), i64, C.POINTER(BHParams), i32]

@@ -17,7 +17,9 @@ import time
 
 import numpy as np
 
-GROUP = 32
+from .engine import lib as _lib
+
+GROUP = int(_lib().bh_group_size())   # bodies per traversal chunk (BH_GROUP in csrc/bh_common.cuh)
 
 
 def slice_bounds(n: int, rank: int, world: int):

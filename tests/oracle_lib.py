@@ -102,9 +102,10 @@ def force_group(posm, b, meta, child, com, root, group=32, theta=THETA, soft=SOF
 
 
 SPLIT = 0.5   # bh_params.group_split default
+GROUP = 32    # bodies per traversal chunk = bh_group_size() (tests/test_abi.py checks the two agree)
 
 
-def make_groups(posm, sorted_keys, chunk=32, alpha=SPLIT):
+def make_groups(posm, sorted_keys, chunk=GROUP, alpha=SPLIT):
     """Traversal groups of the engine: chunks of the Morton order, cut at coarse key boundaries."""
     n = len(posm)
     gs = np.zeros(n + 1, np.int32)
@@ -142,7 +143,7 @@ def energy(posm, vel, soft=SOFT, G_=G):
     return ke.value, pe.value
 
 
-def engine_step(posm, vel, ids, nsteps=1, group=32, G_=G, theta=THETA, dt=DT, soft=SOFT, vmax=VMAX, alpha=SPLIT,
+def engine_step(posm, vel, ids, nsteps=1, group=GROUP, G_=G, theta=THETA, dt=DT, soft=SOFT, vmax=VMAX, alpha=SPLIT,
                 slice_first=0, slice_count=-1):
     """Oracle-I: nsteps of the shipped algorithm on copies of the internal-layout state."""
     posm, vel, ids = posm.copy(), vel.copy(), ids.copy()

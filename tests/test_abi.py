@@ -27,6 +27,9 @@ def test_library_exports_every_declared_symbol(bh):
     missing = [n for n in declared_functions() if not hasattr(L, n)]
     assert not missing, missing
     assert L.bh_abi_version() == 1
+    import oracle_lib as O
+
+    assert L.bh_group_size() == O.GROUP
 
 
 def test_default_params_are_the_reference_constants(bh):

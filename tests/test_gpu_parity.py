@@ -91,7 +91,7 @@ def test_every_phase_against_oracle(bh, kind, n):
         # --- force: same decisions (interaction counts equal), accelerations to rounding
         eng.run_phase(P.FORCE)
         assert eng.stat(S.DEVICE_ERROR) == 0
-        groups = O.make_groups(ps, ks, 32, O.SPLIT)        # same cut rule as the warp applies
+        groups = O.make_groups(ps, ks, O.GROUP, O.SPLIT)        # same cut rule as the warp applies
         acc, counts = O.force_groups(ps, b, meta, child, com, root, groups)
         gacc = eng.debug_get(D.ACC)
         assert eng.stat(S.INTERACTIONS_CELL) == counts[0]

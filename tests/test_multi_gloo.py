@@ -41,14 +41,14 @@ def _worker(rank, world, port, n, steps, q):
 
 def test_slice_bounds_cover_everything_in_whole_chunks():
     sys.path.insert(0, ROOT)
-    from nbody_barnes_hut_cuda_b200.sliced import slice_bounds
+    from nbody_barnes_hut_cuda_b200.sliced import GROUP, slice_bounds
 
     for n in (1, 31, 32, 33, 1000, 16384, 1_000_003):
         for world in (1, 2, 3, 4, 8):
             covered = 0
             for r in range(world):
                 first, count, per = slice_bounds(n, r, world)
-                assert (first % 32 == 0 or count == 0) and per % 32 == 0 and first == min(n, r * per)
+                assert (first % GROUP == 0 or count == 0) and per % GROUP == 0 and first == min(n, r * per)
                 covered += count
             assert covered == n and per * world >= n
 
