@@ -92,11 +92,11 @@ int bh_tree_launch(const uint32_t* keys, const float4* posm, int64_t n, int2* pa
 int bh_com_launch(const float4* posm, int64_t n, const int4* cell_meta, const int32_t* cell_child,
                   int32_t* cell_arrive, float4* cell_mom, float4* cell_com, float4* kid_src,
                   BhDevScalars* sc, cudaStream_t st);
-// heavy_list: 2 * max_chunks u32, heavy_flag: 2 * max_chunks bytes (see BhDevScalars::epoch)
+// heavy_list, heavy_flag: 2 * max_chunks u32 each (see BhDevScalars::epoch)
 int bh_force_launch(const float4* posm, const uint32_t* keys, int64_t n, int64_t first_body, int64_t body_count,
                     const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
                     const float4* kid_src, const uint8_t* kid_lv,
-                    float4* acc, BhDevScalars* sc, uint32_t* heavy_list, uint8_t* heavy_flag, int64_t max_chunks,
+                    float4* acc, BhDevScalars* sc, uint32_t* heavy_list, uint32_t* heavy_flag, int64_t max_chunks,
                     float theta, float softening, float G, float split_alpha, int num_sms, cudaStream_t st);
 int bh_force_prepare();
 int bh_integrate_launch(const float4* posm_s, const float4* vel_s, const int32_t* ids_s, const float4* acc,

@@ -45,7 +45,7 @@ struct bh_ctx {
     float4* kid_src = nullptr;   // 8 per cell
     uint8_t* kid_lv = nullptr;   // 8 per cell
     uint32_t* heavy_list = nullptr;   // 2 * max_chunks
-    uint8_t* heavy_flag = nullptr;    // 2 * max_chunks
+    uint32_t* heavy_flag = nullptr;   // 2 * max_chunks epoch tags
     int64_t max_chunks = 0;
     BhDevScalars* sc = nullptr;
     float* stage = nullptr;  // 10 * n_alloc floats, lazily allocated for the host-pointer entry points
@@ -219,7 +219,7 @@ int bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device) 
 #undef TRYA
     if (e == cudaSuccess) e = cudaMemset(c->sc, 0, sizeof(BhDevScalars));
     if (e == cudaSuccess) e = cudaMemset(c->acc, 0, na * sizeof(float4));
-    if (e == cudaSuccess) e = cudaMemset(c->heavy_flag, 0, 2 * (size_t)c->max_chunks);
+    if (e == cudaSuccess) e = cudaMemset(c->heavy_flag, 0, 8 * (size_t)c->max_chunks);
     if (e != cudaSuccess) { free_all(c); delete c; return (int)e; }
     *out = c;
     return 0;
@@ -242,7 +242,7 @@ int bh_import_soa(bh_ctx* c, const float* px, const float* py, const float* pz, 
     // scheduling history of the previous body set is meaningless now
     BH_CUDA_TRY(cudaMemsetAsync((char*)c->sc + offsetof(BhDevScalars, epoch), 0,
                                 sizeof(BhDevScalars) - offsetof(BhDevScalars, epoch), (cudaStream_t)stream));
-    BH_CUDA_TRY(cudaMemsetAsync(c->heavy_flag, 0, 2 * (size_t)c->max_chunks, (cudaStream_t)stream));
+    BH_CUDA_TRY(cudaMemsetAsync(c->heavy_flag, 0, 8 * (size_t)c->max_chunks, (cudaStream_t)stream));
     int e = bh_import_launch(px, py, pz, vx, vy, vz, mass, n, c->posm, c->vel, c->ids, (cudaStream_t)stream);
     if (e) return e;
     c->have_state = true;
@@ -281,7 +281,7 @@ int bh_set_slice(bh_ctx* c, int rank, int world) {
         BH_CUDA_TRY(cudaDeviceSynchronize());
         // chunk indices are relative to the slice: drop the heavy-chunk history
         BH_CUDA_TRY(cudaMemset((char*)c->sc + offsetof(BhDevScalars, epoch), 0, sizeof(BhDevScalars) - offsetof(BhDevScalars, epoch)));
-        BH_CUDA_TRY(cudaMemset(c->heavy_flag, 0, 2 * (size_t)c->max_chunks));
+        BH_CUDA_TRY(cudaMemset(c->heavy_flag, 0, 8 * (size_t)c->max_chunks));
     }
     return 0;
 }
@@ -624,7 +624,7 @@ int bh_load_checkpoint(bh_ctx* c, const char* path) {
     c->n = h.n; c->steps = h.steps; c->have_state = true; c->have_sorted = false;
     default_slice(c);
     BH_CUDA_TRY(cudaMemset((char*)c->sc + offsetof(BhDevScalars, epoch), 0, sizeof(BhDevScalars) - offsetof(BhDevScalars, epoch)));
-    BH_CUDA_TRY(cudaMemset(c->heavy_flag, 0, 2 * (size_t)c->max_chunks));
+    BH_CUDA_TRY(cudaMemset(c->heavy_flag, 0, 8 * (size_t)c->max_chunks));
     if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }   // theta/dt may have changed
     return 0;
 }

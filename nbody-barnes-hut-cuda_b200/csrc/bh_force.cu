@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
     const float4* __restrict__ posm, const uint32_t* __restrict__ keys, int64_t first_body, int64_t body_count,
     const int4* __restrict__ cell_meta, const int32_t* __restrict__ cell_child, const float4* __restrict__ cell_com,
     const float4* __restrict__ kid_src, const uint8_t* __restrict__ kid_lv, float4* __restrict__ acc, BhDevScalars* sc,
-    uint32_t* __restrict__ heavy_list, uint8_t* __restrict__ heavy_flag, int64_t max_chunks, float theta, float soft,
+    uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_flag, int64_t max_chunks, float theta, float soft,
     float G, float split_alpha) {
     __shared__ WarpScratch s_warp[FORCE_WARPS];
 
@@ -167,13 +167,16 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
 
     // heavy-first scheduling: tickets [0, heavy_n) replay last step's heavy chunks, the rest walk the
     // chunks in Morton order and skip the ones already handed out
-    const unsigned cur = sc->epoch & 1u, nxt = cur ^ 1u;
+    // heavy_flag holds launch-epoch tags instead of booleans, so nothing has to be cleared between launches:
+    // a chunk is on the list being replayed iff its tag equals this launch's epoch
+    const unsigned epoch = sc->epoch;
+    const unsigned cur = epoch & 1u, nxt = cur ^ 1u;
     const unsigned heavy_n = min(sc->heavy_n[cur], (unsigned)min(ngroups, max_chunks));
     const unsigned heavy_thresh = sc->heavy_thresh;
     const uint32_t* list_cur = heavy_list + (size_t)cur * max_chunks;
-    const uint8_t* flag_cur = heavy_flag + (size_t)cur * max_chunks;
+    const uint32_t* flag_cur = heavy_flag + (size_t)cur * max_chunks;
     uint32_t* list_nxt = heavy_list + (size_t)nxt * max_chunks;
-    uint8_t* flag_nxt = heavy_flag + (size_t)nxt * max_chunks;
+    uint32_t* flag_nxt = heavy_flag + (size_t)nxt * max_chunks;
 
     for (;;) {
         unsigned g = 0;
@@ -182,7 +185,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
                 const unsigned t = atomicAdd(&sc->group_ticket, 1u);
                 if (t < heavy_n) { g = list_cur[t]; break; }
                 g = t - heavy_n;
-                if ((int64_t)g >= ngroups || !flag_cur[g]) break;   // flagged chunks were served from the list
+                if ((int64_t)g >= ngroups || flag_cur[g] != epoch) break;   // tagged chunks were served from the list
             }
         }
         g = __shfl_sync(0xffffffffu, g, 0);
@@ -419,7 +422,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
         tot_entries += chunk_entries;
         if (lane == 0 && chunk_entries > heavy_thresh && (int64_t)g < max_chunks) {
             const unsigned slot = atomicAdd(&sc->heavy_n[nxt], 1u);
-            if ((int64_t)slot < max_chunks) { list_nxt[slot] = g; flag_nxt[g] = 1; }
+            if ((int64_t)slot < max_chunks) { list_nxt[slot] = g; flag_nxt[g] = epoch + 1u; }
         }
 
         if (valid) acc[my] = make_float4(G * ax, G * ay, G * az, 0.f);
@@ -435,15 +438,11 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
     }
 }
 
-__global__ void __launch_bounds__(256) reset_force_scalars(BhDevScalars* sc, uint8_t* heavy_flag, int64_t max_chunks,
-                                                          int64_t ngroups) {
-    // one CTA: advance the epoch, derive the heavy threshold from the previous launch, clear the list
-    // and flags that this launch will fill
-    __shared__ unsigned s_nxt;
+__global__ void reset_force_scalars(BhDevScalars* sc, int64_t ngroups) {
+    // advance the epoch, derive the heavy threshold from the previous launch, empty the list this launch fills
     if (threadIdx.x == 0) {
         sc->epoch += 1u;
         const unsigned nxt = (sc->epoch & 1u) ^ 1u;
-        s_nxt = nxt;
         const unsigned long long prev = sc->entries_total;
         // 2.5x the mean list length of the previous launch; nothing is heavy on the first one
         sc->heavy_thresh = prev ? (unsigned)min((unsigned long long)0x7FFFFFFF, prev * 5ull / (2ull * (unsigned long long)ngroups) + 1ull)
@@ -455,10 +454,6 @@ __global__ void __launch_bounds__(256) reset_force_scalars(BhDevScalars* sc, uin
         sc->inter_body = 0;
         sc->max_stack = 0;
     }
-    __syncthreads();
-    uint8_t* f = heavy_flag + (size_t)s_nxt * max_chunks;
-    const int64_t lim = ngroups < max_chunks ? ngroups : max_chunks;
-    for (int64_t i = threadIdx.x; i < lim; i += blockDim.x) f[i] = 0;
 }
 
 __global__ void __launch_bounds__(256) zero_acc_kernel(float4* acc, int64_t first, int64_t count) {
@@ -482,10 +477,10 @@ int bh_force_prepare() {
 int bh_force_launch(const float4* posm, const uint32_t* keys, int64_t n, int64_t first_body, int64_t body_count,
                     const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
                     const float4* kid_src, const uint8_t* kid_lv,
-                    float4* acc, BhDevScalars* sc, uint32_t* heavy_list, uint8_t* heavy_flag, int64_t max_chunks,
+                    float4* acc, BhDevScalars* sc, uint32_t* heavy_list, uint32_t* heavy_flag, int64_t max_chunks,
                     float theta, float softening, float G, float split_alpha, int num_sms, cudaStream_t st) {
     if (body_count <= 0) return 0;
-    reset_force_scalars<<<1, 256, 0, st>>>(sc, heavy_flag, max_chunks, (body_count + BH_GROUP - 1) / BH_GROUP);
+    reset_force_scalars<<<1, 32, 0, st>>>(sc, (body_count + BH_GROUP - 1) / BH_GROUP);
     if (n < 2) {  // a single body feels nothing (its self term is exactly zero, bench:205-213)
         zero_acc_kernel<<<1, 256, 0, st>>>(acc, first_body, body_count);
         return (int)cudaGetLastError();
