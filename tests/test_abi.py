@@ -60,6 +60,7 @@ def test_bad_arguments_rejected_before_touching_cuda(bh):
     L = bh.lib()
     ctx = C.c_void_p()
     assert L.bh_create(C.byref(ctx), 0, None, 0) == -1
+    assert L.bh_create(C.byref(ctx), 1 << 30, None, 0) == -1      # body slots are 31-bit tagged ints: n < 2^30
     assert L.bh_create(None, 10, None, 0) == -1
     assert L.bh_step(None, 1, None) == -1
     need = C.c_size_t(0)

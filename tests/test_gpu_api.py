@@ -18,6 +18,8 @@ def test_call_order_and_argument_errors(bh):
     soa = bh.ic_uniform_cube(2000, 1, 100.0)
     with pytest.raises(bh.BHError):
         eng.load_soa(*soa)                                 # n > n_max
+    empty = [np.zeros(0, f) for _ in range(7)]
+    assert L.bh_import_soa_host(eng._ctx, *[x.ctypes.data_as(C.c_void_p) for x in empty], 0) == -1   # empty input
     assert L.bh_run_phase(eng._ctx, 99, None) == -1
     assert L.bh_debug_get(eng._ctx, 0, None, 24) == -1
     eng.close()
