@@ -180,6 +180,10 @@ int64_t bh_stat(bh_ctx* ctx, int which);
  * groups [first_body, first_body+count) of the freshly sorted order, then
  * the ranks all-gather their updated slices (posm, vel, ids) in place.     */
 int  bh_set_slice(bh_ctx* ctx, int rank, int world);
+/* One step in two halves so the all-gather can overlap compute: half 0 = bounds, keys, radix sort
+ * (reads positions only); half 1 = reorder, tree, centre of mass, traversal, update (needs velocities
+ * and ids as well).  bh_step_half(0) + bh_step_half(1) == bh_step(ctx, 1).                          */
+int  bh_step_half(bh_ctx* ctx, int half, void* stream);
 /* Device pointers to the CURRENT Morton-ordered state (float4 posm, float4
  * vel, int32 ids) and this rank's slice [first, first+count).              */
 int  bh_state_ptrs(bh_ctx* ctx, void** posm, void** vel, void** ids,

@@ -53,6 +53,8 @@ struct bh_ctx {
 
     cudaGraphExec_t graph_exec = nullptr;
     int64_t graph_n = -1, graph_first = -1, graph_count = -1;
+    cudaGraphExec_t half_exec[2] = {nullptr, nullptr};   // head / tail of the step (bh_step_half)
+    int64_t graph_half_n = -1, graph_half_first = -1, graph_half_count = -1;
     cudaStream_t own_stream = nullptr;
     cudaEvent_t ev[BH_PHASE_COUNT + 1] = {};
     float phase_ms[BH_PHASE_COUNT] = {};
@@ -67,6 +69,7 @@ cudaError_t dev_alloc(T** p, size_t count) {
 
 void free_all(bh_ctx* c) {
     if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    for (auto& g : c->half_exec) if (g) cudaGraphExecDestroy(g);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     void* ptrs[] = {c->posm, c->vel, c->posm_s, c->vel_s, c->acc, c->ids, c->ids_s, c->keys0, c->keys1, c->vals0,
@@ -93,14 +96,24 @@ int phase_keys(bh_ctx* c, cudaStream_t st) {
     return bh_keys_launch(c->posm, c->n, c->sc, c->keys0, st);
 }
 
-int phase_sort(bh_ctx* c, cudaStream_t st) {
+int sort_keys_only(bh_ctx* c, cudaStream_t st) {
     int in_q = 0;
     // pass 0 reads keys0 (+ implicit iota values) -> keys1/vals1 -> keys0/vals0 -> ...; 4 passes end in keys0/vals0
     int e = bh_sort_pairs_launch(c->keys0, nullptr, c->keys1, c->vals1, c->keys0, c->vals0, c->n, 0, BH_KEY_BITS,
                                  c->sort_tmp, true, (unsigned int*)((char*)c->sc + offsetof(BhDevScalars, err)), &in_q, st);
     if (e) return e;
     if (!in_q) return BH_E_UNSUPPORTED;  // 30 bits = 4 passes: always even
+    return 0;
+}
+
+int reorder_only(bh_ctx* c, cudaStream_t st) {
     return bh_reorder_launch(c->posm, c->vel, c->ids, c->vals0, c->posm_s, c->vel_s, c->ids_s, c->n, st);
+}
+
+int phase_sort(bh_ctx* c, cudaStream_t st) {
+    int e = sort_keys_only(c, st);
+    if (e) return e;
+    return reorder_only(c, st);
 }
 
 int phase_build(bh_ctx* c, cudaStream_t st) {
@@ -131,6 +144,39 @@ int launch_all_phases(bh_ctx* c, cudaStream_t st) {
         int e = kPhases[p](c, st);
         if (e) return e;
     }
+    return 0;
+}
+
+// The step in two halves for multi-GPU overlap: the HEAD (bounds, keys, radix sort) reads positions only, so
+// it can run while the all-gather of velocities and ids is still in flight; the TAIL is everything else.
+int launch_half(bh_ctx* c, int half, cudaStream_t st) {
+    if (half == 0) {
+        int e = phase_keys(c, st);
+        if (e) return e;
+        return sort_keys_only(c, st);
+    }
+    int e = reorder_only(c, st);
+    for (int p = BH_PHASE_BUILD; !e && p < BH_PHASE_TOTAL; ++p) e = kPhases[p](c, st);
+    return e;
+}
+
+int ensure_half_graphs(bh_ctx* c) {
+    if (c->half_exec[0] && c->half_exec[1] && c->graph_half_n == c->n && c->graph_half_first == c->slice_first &&
+        c->graph_half_count == c->slice_count)
+        return 0;
+    for (int h = 0; h < 2; ++h) {
+        if (c->half_exec[h]) { cudaGraphExecDestroy(c->half_exec[h]); c->half_exec[h] = nullptr; }
+        cudaGraph_t graph = nullptr;
+        BH_CUDA_TRY(cudaStreamBeginCapture(c->own_stream, cudaStreamCaptureModeThreadLocal));
+        int e = launch_half(c, h, c->own_stream);
+        cudaError_t ce = cudaStreamEndCapture(c->own_stream, &graph);
+        if (e) { if (graph) cudaGraphDestroy(graph); return e; }
+        if (ce != cudaSuccess) return (int)ce;
+        ce = cudaGraphInstantiate(&c->half_exec[h], graph, 0);
+        cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) return (int)ce;
+    }
+    c->graph_half_n = c->n; c->graph_half_first = c->slice_first; c->graph_half_count = c->slice_count;
     return 0;
 }
 
@@ -332,6 +378,22 @@ int bh_step(bh_ctx* c, int nsteps, void* stream) {
         }
     }
     if (nsteps > 0) { c->steps += nsteps; c->have_sorted = true; }
+    return 0;
+}
+
+int bh_step_half(bh_ctx* c, int half, void* stream) {
+    if (!c || half < 0 || half > 1) return BH_E_INVAL;
+    if (!c->have_state) return BH_E_STATE;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    if (c->prm.flags & (BH_FLAG_NO_GRAPH | BH_FLAG_PHASE_TIMER)) {
+        int e = launch_half(c, half, (cudaStream_t)stream);
+        if (e) return e;
+    } else {
+        int e = ensure_half_graphs(c);
+        if (e) return e;
+        BH_CUDA_TRY(cudaGraphLaunch(c->half_exec[half], (cudaStream_t)stream));
+    }
+    if (half == 1) { c->steps += 1; c->have_sorted = true; }
     return 0;
 }
 
@@ -626,6 +688,7 @@ int bh_load_checkpoint(bh_ctx* c, const char* path) {
     BH_CUDA_TRY(cudaMemset((char*)c->sc + offsetof(BhDevScalars, epoch), 0, sizeof(BhDevScalars) - offsetof(BhDevScalars, epoch)));
     BH_CUDA_TRY(cudaMemset(c->heavy_flag, 0, 8 * (size_t)c->max_chunks));
     if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }   // theta/dt may have changed
+    for (auto& g : c->half_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     return 0;
 }
 

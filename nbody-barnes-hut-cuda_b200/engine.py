@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
     L.bh_import_soa.argtypes = [vp] + [vp] * 7 + [i64, vp]
     L.bh_import_soa_host.argtypes = [vp] + [vp] * 7 + [i64]
     L.bh_step.argtypes = [vp, i32, vp]
+    L.bh_step_half.argtypes = [vp, i32, vp]
     L.bh_export_soa.argtypes = [vp] + [vp] * 9 + [vp]
     L.bh_export_soa_host.argtypes = [vp] + [vp] * 9
     L.bh_step_host.argtypes = [vp] + [vp] * 7 + [i64, i32]
@@ -257,6 +258,10 @@ class BHEngine:
     def simulation_step(self, nsteps: int = 1, stream: int = 0):
         """≙ simulationStep() x nsteps (bench:255-283); asynchronous."""
         _check(lib().bh_step(self._ctx, nsteps, C.c_void_p(stream)), "bh_step")
+
+    def step_half(self, half: int, stream: int = 0):
+        """Head (0: bounds, keys, sort — positions only) or tail (1: the rest) of one step."""
+        _check(lib().bh_step_half(self._ctx, half, C.c_void_p(stream)), "bh_step_half")
 
     def read_soa(self, want_acc: bool = True):
         """Device state -> host SoA in ORIGINAL body order: (px,py,pz,vx,vy,vz[,ax,ay,az])."""

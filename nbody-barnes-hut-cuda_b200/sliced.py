@@ -73,11 +73,35 @@ class SlicedSimulation:
         assert (st["first"], st["count"]) == (self.first, self.count), "slice arithmetic differs from the C side"
         self.views = device_views(torch, st, self.per, world, self.device)
 
-    def step(self, nsteps: int = 1):
+    def step(self, nsteps: int = 1, overlap: bool = True):
+        """nsteps sliced steps.  With overlap the three all-gathers are issued asynchronously in the order
+        posm, vel, ids; the next step's head (bounds, keys, radix sort — positions only) starts as soon as
+        the positions have landed, while velocities and ids are still crossing NVLink."""
         stream = self.torch.cuda.current_stream().cuda_stream
+        if not overlap:
+            for _ in range(nsteps):
+                self.eng.simulation_step(1, stream)
+                allgather_slices(self.dist, self.views, self.rank, self.per)
+            return
+        lo, hi = self.rank * self.per, (self.rank + 1) * self.per
         for _ in range(nsteps):
-            self.eng.simulation_step(1, stream)
-            allgather_slices(self.dist, self.views, self.rank, self.per)
+            pending = getattr(self, "_pending", None)
+            if pending:
+                pending[0].wait()               # positions of the previous step are complete
+            self.eng.step_half(0, stream)
+            if pending:
+                pending[1].wait()
+                pending[2].wait()
+            self.eng.step_half(1, stream)
+            self._pending = [self.dist.all_gather_into_tensor(full, full[lo:hi], async_op=True) for full in self.views]
+
+    def finish(self):
+        """Complete the all-gathers a previous step(overlap=True) left in flight."""
+        pending = getattr(self, "_pending", None)
+        if pending:
+            for h in pending:
+                h.wait()
+            self._pending = None
 
     def step_host(self, host_in, host_out, nsteps: int = 1):
         """End-to-end step with HOST state, sharded over the ranks' PCIe links: every rank uploads 1/world of
@@ -95,8 +119,10 @@ class SlicedSimulation:
         for k in range(7):
             self._soa_dev[k][lo:hi].copy_(host_in[k][lo:hi], non_blocking=True)
             dist.all_gather_into_tensor(self._soa_dev[k], self._soa_dev[k][rank * chunk:(rank + 1) * chunk])
+        self.finish()
         self.eng.load_soa_device(self._soa_dev[:7], n, stream)
         self.step(nsteps)
+        self.finish()
         ptrs = [C_void(t) for t in self._soa_dev[:6]] + [None] * 3
         from .engine import _check, lib
         import ctypes as C
@@ -106,6 +132,8 @@ class SlicedSimulation:
         torch.cuda.synchronize()
 
     def close(self):
+        self.finish()
+        self.torch.cuda.synchronize()
         self.eng.close()
 
 
@@ -124,6 +152,7 @@ def run_sliced_bench(args, w, bh, dist, rank, world, local):
         torch.cuda.synchronize()
 
     sim.step(args.warmup)
+    sim.finish()
     barrier()
     sim.eng.check_device_error()
     clocks = bench.ClockSampler(local)
@@ -132,6 +161,7 @@ def run_sliced_bench(args, w, bh, dist, rank, world, local):
     barrier()
     a.record()
     sim.step(args.steps)
+    sim.finish()
     b.record()
     barrier()
     ms = torch.tensor([a.elapsed_time(b)], device=dev)

@@ -110,3 +110,24 @@ def test_theta_zero_is_the_direct_sum(bh):
         out = eng.read_soa()
         assert eng.stat(bh.STAT.INTERACTIONS_CELL) == 0 and eng.stat(bh.STAT.INTERACTIONS_BODY) == n * n
     assert O.rel_rms(np.stack(out[6:9], 1), want) < 2e-6
+
+
+def test_step_halves_equal_a_full_step(bh):
+    """bh_step_half(0) + bh_step_half(1) == bh_step(1), with and without graphs."""
+    n = 30000
+    soa = bh.ic_refdisk(n, 42)
+    with bh.BHEngine(n) as ref:
+        ref.load_soa(*soa)
+        ref.simulation_step(3)
+        want = (ref.debug_get(bh.DBG.POSM), ref.debug_get(bh.DBG.VEL), ref.debug_get(bh.DBG.IDS))
+    for flags in (0, 1):
+        with bh.BHEngine(n, flags=flags) as eng:
+            eng.load_soa(*soa)
+            for _ in range(3):
+                eng.step_half(0)
+                eng.step_half(1)
+            eng.check_device_error()
+            assert eng.stat(bh.STAT.STEPS) == 3
+            got = (eng.debug_get(bh.DBG.POSM), eng.debug_get(bh.DBG.VEL), eng.debug_get(bh.DBG.IDS))
+            assert got[0].tobytes() == want[0].tobytes() and got[1].tobytes() == want[1].tobytes()
+            assert (got[2] == want[2]).all()

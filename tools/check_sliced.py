@@ -16,7 +16,8 @@ dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
 n, steps = 300_001, 3
 soa = bh.ic_refdisk(n, 42)
 sim = SlicedSimulation(bh, soa, rank, world, local, dist)
-sim.step(steps)
+sim.step(steps)            # overlapped all-gathers (default)
+sim.finish()
 torch.cuda.synchronize()
 got = sim.eng.read_soa(want_acc=False)
 # sharded host path: same physics starting from the same host state
@@ -33,6 +34,14 @@ with bh.BHEngine(n, device=local) as ref:
 for k in range(6):
     ok &= got[k].tobytes() == want[k].tobytes()
     ok &= host_out[k].numpy()[lo:hi].tobytes() == want[k][lo:hi].tobytes()
+# and the plain (non-overlapped) loop gives the same bits
+sim2 = SlicedSimulation(bh, soa, rank, world, local, dist)
+sim2.step(steps, overlap=False)
+torch.cuda.synchronize()
+got2 = sim2.eng.read_soa(want_acc=False)
+for k in range(6):
+    ok &= got2[k].tobytes() == want[k].tobytes()
+sim2.close()
 flag = torch.tensor([1 if ok else 0], device=f"cuda:{local}")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
