@@ -97,6 +97,40 @@ void orc_morton_keys(const float* px, const float* py, const float* pz, int64_t 
     }
 }
 
+// bh_params.key_bits = 60: `hi` is the reference key above, `lo` interleaves ten more bits per axis taken
+// from the fractional part of the same float t = (p-min)/size*1023.0f (t - trunc(t) is exact in float), so
+// (hi << 30 | lo) refines the reference order without ever contradicting it.
+void orc_morton_keys60(const float* px, const float* py, const float* pz, int64_t n,
+                       const float b[6], uint32_t* hi, uint32_t* lo) {
+    const float size = fmaxf(b[3] - b[0], 1.0f);
+    auto split = [&](float p, float mn, uint32_t& q, uint32_t& fr) {
+        float t = (p - mn) / size * 1023.0f;
+        q = quantise(p, mn, size);
+        float frac = t - (float)q;
+        float g = frac * 1024.0f;
+        fr = !(g > 0.0f) ? 0u : (g >= 1023.0f ? 1023u : (uint32_t)g);
+    };
+#pragma omp parallel for schedule(static)
+    for (int64_t i = 0; i < n; ++i) {
+        uint32_t qx, qy, qz, fx, fy, fz;
+        split(px[i], b[0], qx, fx); split(py[i], b[1], qy, fy); split(pz[i], b[2], qz, fz);
+        hi[i] = (spread10(qx) << 2) | (spread10(qy) << 1) | spread10(qz);
+        lo[i] = (spread10(fx) << 2) | (spread10(fy) << 1) | spread10(fz);
+    }
+}
+
+// stable ascending sort of 64-bit keys; idx follows
+void orc_stable_sort64(uint64_t* keys, int32_t* idx, int64_t n) {
+    std::vector<int64_t> order(n);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) { return keys[a] < keys[b]; });
+    std::vector<uint64_t> k2(n);
+    std::vector<int32_t> i2(n);
+    for (int64_t i = 0; i < n; ++i) { k2[i] = keys[order[i]]; i2[i] = idx[order[i]]; }
+    std::memcpy(keys, k2.data(), n * sizeof(uint64_t));
+    std::memcpy(idx, i2.data(), n * sizeof(int32_t));
+}
+
 // bench:262-264 — thrust::sort_by_key is a stable ascending radix sort.
 void orc_stable_sort(uint32_t* keys, int32_t* idx, int64_t n) {
     std::vector<int64_t> order(n);
@@ -336,19 +370,21 @@ int orc_reference_step(float* px, float* py, float* pz, float* vx, float* vy, fl
 // =========================================================================================
 namespace {
 
-constexpr int KEY_BITS = 30;
-constexpr int MAX_LEVEL = 10;
+// Keys are handled as 64-bit values with `levels` 3-bit digits: 10 digits = the reference's 30-bit key
+// (bench:57-61), 20 digits = the same key extended by 10 fractional bits per axis (bh_params.key_bits = 60,
+// the top 30 bits stay the reference key bit for bit).
+constexpr int MAX_LEVELS_ANY = 20;
 constexpr int CHILD_EMPTY = 0x7F7F7F7F;
 
 // number of leading 3-bit digits two keys share (0..10)
-inline int shared_digits(uint32_t a, uint32_t b) {
-    uint32_t x = a ^ b;
-    if (x == 0) return MAX_LEVEL;
-    int lead = __builtin_clz(x) - (32 - KEY_BITS);
+inline int shared_digits(uint64_t a, uint64_t b, int levels) {
+    uint64_t x = a ^ b;
+    if (x == 0) return levels;
+    int lead = __builtin_clzll(x) - (64 - 3 * levels);
     return lead / 3;
 }
-inline int digit_at(uint32_t key, int level /*1-based digit index*/) {
-    return (key >> (KEY_BITS - 3 * level)) & 7;
+inline int digit_at(uint64_t key, int level /*1-based digit index*/, int levels) {
+    return (int)((key >> (3 * (levels - level))) & 7);
 }
 
 struct Cell {
@@ -358,29 +394,30 @@ struct Cell {
 };
 
 struct TreeBuilder {
-    const uint32_t* k;
+    const uint64_t* k;
+    int levels;
     std::vector<Cell> cells;
 
     // returns a child-table entry for the range [first, first+count)
     int build(int first, int count, int parent, int slot) {
         if (count == 1) return (int)(0x80000000u | (uint32_t)first);
-        int L = shared_digits(k[first], k[first + count - 1]);
+        int L = shared_digits(k[first], k[first + count - 1], levels);
         Cell c;
         c.first = first; c.count = count; c.level = L; c.parent = parent; c.slot = slot;
-        c.bucket = (L == MAX_LEVEL);
+        c.bucket = (L == levels);
         for (int q = 0; q < 8; ++q) c.child[q] = CHILD_EMPTY;
         int me = (int)cells.size();
         cells.push_back(c);
-        if (L == MAX_LEVEL) {
+        if (L == levels) {
             cells[me].leader = first;  // first equal pair of the run
             return me;
         }
         int pos = first, end = first + count;
         bool first_child = true;
         while (pos < end) {
-            int d = digit_at(k[pos], L + 1);
+            int d = digit_at(k[pos], L + 1, levels);
             int e = pos + 1;
-            while (e < end && digit_at(k[e], L + 1) == d) ++e;
+            while (e < end && digit_at(k[e], L + 1, levels) == d) ++e;
             if (first_child) { cells[me].leader = e - 1; first_child = false; }
             int entry = build(pos, e - pos, me, d);
             cells[me].child[d] = entry;
@@ -403,13 +440,25 @@ extern "C" {
 // (slot = which child of its parent the cell is),
 // child: 8 ints per cell.  Cells are numbered by ascending leader pair (the numbering the
 // parallel builder produces with a prefix sum).  Returns the cell count, or -1 if cap is short.
+int orc_tree_build64(const uint64_t* sorted_keys, int64_t n64, int levels, int32_t* meta, int32_t* child,
+                     int64_t cap, int32_t* root_out);
+
 int orc_tree_build(const uint32_t* sorted_keys, int64_t n64, int32_t* meta, int32_t* child,
                    int64_t cap, int32_t* root_out) {
+    std::vector<uint64_t> k64((size_t)std::max<int64_t>(n64, 1));
+    for (int64_t i = 0; i < n64; ++i) k64[i] = sorted_keys[i];
+    return orc_tree_build64(k64.data(), n64, 10, meta, child, cap, root_out);
+}
+
+// Same for keys of `levels` digits held in 64 bits (levels = 10 or 20).
+int orc_tree_build64(const uint64_t* sorted_keys, int64_t n64, int levels, int32_t* meta, int32_t* child,
+                     int64_t cap, int32_t* root_out) {
     const int n = (int)n64;
     if (root_out) *root_out = -1;
     if (n < 2) return 0;
     TreeBuilder tb;
     tb.k = sorted_keys;
+    tb.levels = levels;
     tb.cells.reserve(n);
     tb.build(0, n, -1, 0);
     const int M = (int)tb.cells.size();
@@ -524,8 +573,8 @@ void orc_force_groups(const float* posm, int64_t n64, const float* bounds,
     const int n = (int)n64; (void)n;
     const float root_w = bounds[3] - bounds[0];
     const float theta2 = theta * theta;
-    float w2[MAX_LEVEL + 1];
-    for (int L = 0; L <= MAX_LEVEL; ++L) w2[L] = w2_of_level(root_w, L);
+    float w2[MAX_LEVELS_ANY + 1];
+    for (int L = 0; L <= MAX_LEVELS_ANY; ++L) w2[L] = w2_of_level(root_w, L);
     int64_t ncell = 0, nbody = 0;
 #pragma omp parallel for schedule(dynamic, 16) reduction(+ : ncell, nbody)
     for (int g = 0; g < ngroups; ++g) {
@@ -613,8 +662,18 @@ static float range_ext(const float* posm, int a, int b) {
     return ((hi[0] - lo[0]) + (hi[1] - lo[1])) + (hi[2] - lo[2]);
 }
 
+int orc_make_groups64(const float* posm, const uint64_t* keys, int64_t n64, int levels, int chunk, float alpha,
+                      int32_t* gstart);
+
 int orc_make_groups(const float* posm, const uint32_t* keys, int64_t n64, int chunk, float alpha,
                     int32_t* gstart) {
+    std::vector<uint64_t> k64((size_t)std::max<int64_t>(n64, 1));
+    for (int64_t i = 0; i < n64; ++i) k64[i] = keys[i];
+    return orc_make_groups64(posm, k64.data(), n64, 10, chunk, alpha, gstart);
+}
+
+int orc_make_groups64(const float* posm, const uint64_t* keys, int64_t n64, int levels, int chunk, float alpha,
+                      int32_t* gstart) {
     const int n = (int)n64;
     int ng = 0;
     for (int c0 = 0; c0 < n; c0 += chunk) {
@@ -628,11 +687,11 @@ int orc_make_groups(const float* posm, const uint32_t* keys, int64_t n64, int ch
             if (b - a >= 2) {
                 int best = a, bestlv = 99;
                 for (int j = a; j < b - 1; ++j) {
-                    int lv = shared_digits(keys[j], keys[j + 1]);
+                    int lv = shared_digits(keys[j], keys[j + 1], levels);
                     if (lv < bestlv) { bestlv = lv; best = j; }
                 }
                 const int k = best + 1;
-                if (bestlv < MAX_LEVEL) {
+                if (bestlv < levels) {
                     float eA = range_ext(posm, a, k), eB = range_ext(posm, k, b), eAB = range_ext(posm, a, b);
                     if (eA + eB < alpha * eAB) {
                         split = true;
@@ -746,7 +805,8 @@ void orc_energy(const float* posm, const float* vel, int64_t n, float soft, floa
 int orc_engine_step(float* posm, float* vel, int32_t* ids, int64_t n64, int nsteps,
                     float G, float theta, float dt, float soft, float max_speed, int group, float split_alpha,
                     float* acc_out, uint32_t* keys_out, int32_t* perm_out, float* bounds_out,
-                    int64_t* counts_out, double* phase_ms, int64_t slice_first, int64_t slice_count) {
+                    int64_t* counts_out, double* phase_ms, int64_t slice_first, int64_t slice_count,
+                    int key_bits, uint32_t* keys_lo_out) {
     // slice_count < 0: the whole range.  Otherwise only sorted slots [slice_first, slice_first+slice_count)
     // are traversed and integrated (multi-GPU Morton slices, engine: bh_set_slice); the other slots of
     // posm/vel/ids are left holding this step's sorted pre-drift state, to be overwritten by the
@@ -754,7 +814,10 @@ int orc_engine_step(float* posm, float* vel, int32_t* ids, int64_t n64, int nste
     if (n64 <= 0 || n64 > (1 << 30)) return -1;
     const int n = (int)n64;
     std::vector<float> sx(n), sy(n), sz(n), p2(4 * (size_t)n), v2(4 * (size_t)n), acc(4 * (size_t)n);
-    std::vector<uint32_t> keys(n);
+    if (key_bits != 30 && key_bits != 60) return -2;
+    const int levels = key_bits / 3;
+    std::vector<uint32_t> keys(n), keys_lo(n, 0u);
+    std::vector<uint64_t> k64(n);
     std::vector<int32_t> perm(n), id2(n), meta, child;
     std::vector<float> mom, com;
     double ph[6] = {0, 0, 0, 0, 0, 0};
@@ -763,9 +826,19 @@ int orc_engine_step(float* posm, float* vel, int32_t* ids, int64_t n64, int nste
         for (int i = 0; i < n; ++i) { sx[i] = posm[4 * (size_t)i]; sy[i] = posm[4 * (size_t)i + 1]; sz[i] = posm[4 * (size_t)i + 2]; }
         float b[6];
         orc_bounds(sx.data(), sy.data(), sz.data(), n, b);
-        orc_morton_keys(sx.data(), sy.data(), sz.data(), n, b, keys.data(), perm.data());
+        if (key_bits == 30) {
+            orc_morton_keys(sx.data(), sy.data(), sz.data(), n, b, keys.data(), perm.data());
+            for (int i = 0; i < n; ++i) k64[i] = keys[i];
+        } else {
+            orc_morton_keys60(sx.data(), sy.data(), sz.data(), n, b, keys.data(), keys_lo.data());
+            for (int i = 0; i < n; ++i) { k64[i] = ((uint64_t)keys[i] << 30) | keys_lo[i]; perm[i] = i; }
+        }
         double t1 = now_ms();
-        orc_stable_sort(keys.data(), perm.data(), n);
+        orc_stable_sort64(k64.data(), perm.data(), n);
+        for (int i = 0; i < n; ++i) {
+            keys[i] = key_bits == 30 ? (uint32_t)k64[i] : (uint32_t)(k64[i] >> 30);
+            keys_lo[i] = key_bits == 30 ? 0u : (uint32_t)(k64[i] & 0x3FFFFFFFu);
+        }
         for (int i = 0; i < n; ++i) {
             std::memcpy(&p2[4 * (size_t)i], &posm[4 * (size_t)perm[i]], 16);
             std::memcpy(&v2[4 * (size_t)i], &vel[4 * (size_t)perm[i]], 16);
@@ -777,7 +850,7 @@ int orc_engine_step(float* posm, float* vel, int32_t* ids, int64_t n64, int nste
         double t2 = now_ms();
         meta.assign(4 * (size_t)n, 0); child.assign(8 * (size_t)n, 0);
         int32_t root = -1;
-        int M = orc_tree_build(keys.data(), n, meta.data(), child.data(), n, &root);
+        int M = orc_tree_build64(k64.data(), n, levels, meta.data(), child.data(), n, &root);
         double t3 = now_ms();
         mom.assign(4 * (size_t)std::max(M, 1), 0.f); com.assign(4 * (size_t)std::max(M, 1), 0.f);
         orc_tree_com(posm, n, meta.data(), child.data(), M, root, mom.data(), com.data());
@@ -785,7 +858,7 @@ int orc_engine_step(float* posm, float* vel, int32_t* ids, int64_t n64, int nste
         int64_t counts[2] = {0, 0};
         std::fill(acc.begin(), acc.end(), 0.f);
         std::vector<int32_t> gstart((size_t)n + 1);
-        int ng = orc_make_groups(posm, keys.data(), n, group, split_alpha, gstart.data());
+        int ng = orc_make_groups64(posm, k64.data(), n, levels, group, split_alpha, gstart.data());
         const int s0 = slice_count < 0 ? 0 : (int)slice_first;
         const int s1 = slice_count < 0 ? n : (int)(slice_first + slice_count);
         int g0 = 0, g1 = ng;
@@ -797,6 +870,7 @@ int orc_engine_step(float* posm, float* vel, int32_t* ids, int64_t n64, int nste
         if (s == nsteps - 1) {
             if (acc_out) std::memcpy(acc_out, acc.data(), 16 * (size_t)n);
             if (keys_out) std::memcpy(keys_out, keys.data(), 4 * (size_t)n);
+            if (keys_lo_out) std::memcpy(keys_lo_out, keys_lo.data(), 4 * (size_t)n);
             if (perm_out) std::memcpy(perm_out, perm.data(), 4 * (size_t)n);
             if (bounds_out) std::memcpy(bounds_out, b, sizeof(b));
             if (counts_out) { counts_out[0] = counts[0]; counts_out[1] = counts[1]; counts_out[2] = M; }

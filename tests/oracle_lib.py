@@ -48,6 +48,39 @@ def morton_keys(px, py, pz, b):
     return keys, idx
 
 
+def morton_keys60(px, py, pz, b):
+    """hi = the reference 30-bit key, lo = 10 more bits per axis (bh_params.key_bits = 60)."""
+    n = len(px)
+    hi, lo = np.zeros(n, np.uint32), np.zeros(n, np.uint32)
+    lib().orc_morton_keys60(_p(px), _p(py), _p(pz), C.c_int64(n), _p(b), _p(hi), _p(lo))
+    return hi, lo
+
+
+def stable_sort64(keys64, idx):
+    k, i = np.ascontiguousarray(keys64, np.uint64).copy(), idx.copy()
+    lib().orc_stable_sort64(_p(k), _p(i), C.c_int64(len(k)))
+    return k, i
+
+
+def tree_build64(sorted_keys64, levels):
+    n = len(sorted_keys64)
+    cap = max(n, 1)
+    meta, child = np.zeros((cap, 4), np.int32), np.zeros((cap, 8), np.int32)
+    root = C.c_int32(-1)
+    k = np.ascontiguousarray(sorted_keys64, np.uint64)
+    M = lib().orc_tree_build64(_p(k), C.c_int64(n), levels, _p(meta), _p(child), C.c_int64(cap), C.byref(root))
+    assert M >= 0
+    return meta[:M].copy(), child[:M].copy(), int(root.value)
+
+
+def make_groups64(posm, sorted_keys64, levels, chunk=None, alpha=None):
+    n = len(posm)
+    gs = np.zeros(n + 1, np.int32)
+    k = np.ascontiguousarray(sorted_keys64, np.uint64)
+    ng = lib().orc_make_groups64(_p(posm), _p(k), C.c_int64(n), levels, chunk or GROUP, f32(SPLIT if alpha is None else alpha), _p(gs))
+    return gs[: ng + 1].copy()
+
+
 def stable_sort(keys, idx):
     k, i = keys.copy(), idx.copy()
     lib().orc_stable_sort(_p(k), _p(i), C.c_int64(len(k)))
@@ -144,17 +177,18 @@ def energy(posm, vel, soft=SOFT, G_=G):
 
 
 def engine_step(posm, vel, ids, nsteps=1, group=GROUP, G_=G, theta=THETA, dt=DT, soft=SOFT, vmax=VMAX, alpha=SPLIT,
-                slice_first=0, slice_count=-1):
+                slice_first=0, slice_count=-1, key_bits=30):
     """Oracle-I: nsteps of the shipped algorithm on copies of the internal-layout state."""
     posm, vel, ids = posm.copy(), vel.copy(), ids.copy()
     n = len(posm)
     acc, keys, perm = np.zeros((n, 4), np.float32), np.zeros(n, np.uint32), np.zeros(n, np.int32)
     b, counts, ph = np.zeros(6, np.float32), np.zeros(3, np.int64), np.zeros(6)
+    keys_lo = np.zeros(n, np.uint32)
     rc = lib().orc_engine_step(_p(posm), _p(vel), _p(ids), C.c_int64(n), nsteps, f32(G_), f32(theta), f32(dt), f32(soft),
                                f32(vmax), group, f32(alpha), _p(acc), _p(keys), _p(perm), _p(b), _p(counts), _p(ph),
-                               C.c_int64(slice_first), C.c_int64(slice_count))
+                               C.c_int64(slice_first), C.c_int64(slice_count), key_bits, _p(keys_lo))
     assert rc == 0
-    return dict(posm=posm, vel=vel, ids=ids, acc=acc, keys=keys, perm=perm, bounds=b, inter_cell=int(counts[0]),
+    return dict(posm=posm, vel=vel, ids=ids, acc=acc, keys=keys, keys_lo=keys_lo, perm=perm, bounds=b, inter_cell=int(counts[0]),
                 inter_body=int(counts[1]), cells=int(counts[2]), phase_ms=ph)
 
 

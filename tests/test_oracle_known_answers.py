@@ -292,3 +292,26 @@ def test_group_splitting_rule():
     a0, c0 = O.force_groups(ps3, b3, meta, child, com, root, O.make_groups(ps3, ks3, 32, 0.0))
     a1, c1 = O.force_groups(ps3, b3, meta, child, com, root, O.make_groups(ps3, ks3, 32, 0.5))
     assert O.rel_rms(a1[:, :3], a0[:, :3]) < 5e-3
+
+
+def test_sixty_bit_keys_refine_the_reference_order():
+    """SURVEY H2 groundwork (oracle only so far): key60 = reference key << 30 | ten fractional bits per axis."""
+    soa = _random_soa(20000, 21, clustered=True)
+    b = O.bounds(*soa[:3])
+    keys, idx = O.morton_keys(*soa[:3], b)
+    hi, lo = O.morton_keys60(*soa[:3], b)
+    assert (hi == keys).all() and lo.max() < (1 << 30)       # the top 30 bits ARE the reference key
+    k64 = (hi.astype(np.uint64) << np.uint64(30)) | lo.astype(np.uint64)
+    ks64, perm64 = O.stable_sort64(k64, idx)
+    ks30, perm30 = O.stable_sort(keys, idx)
+    assert ((ks64 >> np.uint64(30)).astype(np.uint32) == ks30).all()      # same coarse sequence
+    # a deeper tree over the same bodies: every 30-bit cell range is still a cell range (or splits further)
+    m30, c30, r30 = O.tree_build(ks30)
+    m60, c60, r60 = O.tree_build64(ks64, 20)
+    assert len(m60) >= len(m30) and m60[r60, 1] == len(keys)
+    posm, vel, ids = O.soa_to_internal(soa)
+    e30 = O.engine_step(posm, vel, ids, 1, key_bits=30)
+    e60 = O.engine_step(posm, vel, ids, 1, key_bits=60)
+    a30 = np.zeros((20000, 3)); a30[e30["ids"]] = e30["acc"][:, :3]
+    a60 = np.zeros((20000, 3)); a60[e60["ids"]] = e60["acc"][:, :3]
+    assert O.rel_rms(a60, a30) < 5e-3                         # both are theta=0.5 approximations of the same field
