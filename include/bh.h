@@ -189,6 +189,31 @@ int  bh_step_half(bh_ctx* ctx, int half, void* stream);
 int  bh_state_ptrs(bh_ctx* ctx, void** posm, void** vel, void** ids,
                    int64_t* n, int64_t* slice_first, int64_t* slice_count);
 
+/* ---- multi-GPU: locally-essential-tree exchange (north_star) -----
+ * For body counts that are not replicated on every GPU.  A rank owns a subset of the bodies; per step it
+ *   1. agrees on the global bounding cube with its peers and fixes it (bh_set_fixed_bounds) so that every
+ *      rank's Morton keys live on the same grid,
+ *   2. builds the tree of its OWN bodies (bh_run_phase KEYS..COM),
+ *   3. walks that tree once per peer against the peer's domain box (bh_let_export): the coarsest point
+ *      masses — accepted cells' {centre of mass, mass}, loose bodies, bodies of rejected buckets — that may
+ *      stand in for this rank's bodies anywhere inside that box,
+ *   4. exchanges those lists, merges what it received (ids = -1) with its own bodies (bh_import_state) and
+ *      runs an ordinary bh_step on the union; imported points are dropped afterwards.
+ * nbody-barnes-hut-cuda_b200/let.py is the torch.distributed driver.                                    */
+/* Use this cube instead of computing one from the state (NULL switches back).  b = d_bounds layout
+ * (min xyz, min+size xyz; nbody_v5_bench.cu:149-154).                                                  */
+int  bh_set_fixed_bounds(bh_ctx* ctx, const float b[6]);
+/* min xyz / max xyz of the current state (host floats; synchronises).                                   */
+int  bh_local_bounds(bh_ctx* ctx, float lohi[6]);
+/* Load the internal layout directly: DEVICE float4 posm {x,y,z,m}, float4 vel, int32 ids (any ids; the
+ * step carries them along unchanged).                                                                   */
+int  bh_import_state(bh_ctx* ctx, const void* posm, const void* vel, const int32_t* ids, int64_t n, void* stream);
+/* boxes_lohi: HOST npeers x 6 (lo xyz, hi xyz; lo.x > hi.x = skip that peer); out: DEVICE float4
+ * [npeers * cap_per_peer]; counts: HOST npeers.  Needs the tree of the current state (phases KEYS..COM).
+ * Synchronises.  Returns BH_E_DEVICE if an output list overflowed.                                      */
+int  bh_let_export(bh_ctx* ctx, const float* boxes_lohi, int npeers, void* out, int64_t cap_per_peer,
+                   int32_t* counts, void* stream);
+
 /* ---- standalone pieces -------------------------------------------------- */
 /* Stable LSD radix sort of (u32 key, u32 value) pairs over bits
  * [begin_bit,end_bit) — replaces thrust::sort_by_key (bench:262-264).

@@ -4,7 +4,9 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
+#include <string.h>
 
 #include "../../include/bh.h"
 
@@ -18,6 +20,7 @@
 #define BH_DERR_STACK       2   // traversal stack guard tripped
 #define BH_DERR_LOOP        4   // traversal iteration guard tripped
 #define BH_DERR_TREE        8   // builder found an inconsistent range
+#define BH_DERR_LET_OVERFLOW 16  // locally-essential-tree export ran out of output / queue space
 
 struct BhDevScalars {        // one small device struct, zeroed/filled by kernels
     float bounds[6];         // as d_bounds (nbody_v5_bench.cu:149-154)
@@ -115,3 +118,7 @@ int bh_energy_launch(const float4* posm, const float4* vel, int64_t n, float sof
 int bh_visuals_launch(const float4* posm, const float4* vel, const int32_t* ids, int64_t n, float* vbo_p, float* vbo_c,
                       cudaStream_t st);
 int bh_momentum_launch(const float4* posm, const float4* vel, int64_t n, double* out7, cudaStream_t st);
+int bh_let_export_launch(const int4* cell_meta, const int32_t* cell_child, const float4* cell_com, const float4* kid_src,
+                         const uint8_t* kid_lv, const float4* posm, BhDevScalars* sc, const float* boxes_dev, int npeers,
+                         float4* out, unsigned int* out_count, long long cap, int2* queue, unsigned int* qcounts,
+                         long long qcap, float theta, float softening, float root_w, cudaStream_t st);

@@ -51,6 +51,14 @@ struct bh_ctx {
     float* stage = nullptr;  // 10 * n_alloc floats, lazily allocated for the host-pointer entry points
     double* d_scratch = nullptr;
 
+    // locally-essential-tree mode
+    bool fixed_bounds_set = false;
+    float fixed_bounds[6] = {0, 0, 0, 0, 0, 0};
+    float* let_boxes = nullptr;          // 64 peers x 6
+    unsigned int* let_counts = nullptr;  // 64 + 2 queue counters
+    int2* let_queue = nullptr;           // 2 x let_qcap
+    long long let_qcap = 0;
+
     cudaGraphExec_t graph_exec = nullptr;
     int64_t graph_n = -1, graph_first = -1, graph_count = -1;
     cudaGraphExec_t half_exec[2] = {nullptr, nullptr};   // head / tail of the step (bh_step_half)
@@ -74,7 +82,7 @@ void free_all(bh_ctx* c) {
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     void* ptrs[] = {c->posm, c->vel, c->posm_s, c->vel_s, c->acc, c->ids, c->ids_s, c->keys0, c->keys1, c->vals0,
                     c->vals1, c->sort_tmp, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
-                    c->cell_arrive, c->cell_mom, c->cell_com, c->sc, c->stage, c->d_scratch, c->heavy_list, c->heavy_flag, c->kid_src, c->kid_lv};
+                    c->cell_arrive, c->cell_mom, c->cell_com, c->sc, c->stage, c->d_scratch, c->heavy_list, c->heavy_flag, c->kid_src, c->kid_lv, c->let_boxes, c->let_counts, c->let_queue};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -91,7 +99,13 @@ void default_slice(bh_ctx* c) {
 
 // ---- the phases ---------------------------------------------------------------------------
 int phase_keys(bh_ctx* c, cudaStream_t st) {
-    int e = bh_bounds_launch(c->posm, c->n, c->sc, st);
+    int e = 0;
+    if (c->fixed_bounds_set) {   // LET mode: the cube was agreed with the other ranks
+        BH_CUDA_TRY(cudaMemcpyAsync((char*)c->sc + offsetof(BhDevScalars, bounds), c->fixed_bounds, sizeof(c->fixed_bounds),
+                                    cudaMemcpyHostToDevice, st));
+    } else {
+        e = bh_bounds_launch(c->posm, c->n, c->sc, st);
+    }
     if (e) return e;
     return bh_keys_launch(c->posm, c->n, c->sc, c->keys0, st);
 }
@@ -316,6 +330,101 @@ static int import_host_impl(bh_ctx* c, const float* px, const float* py, const f
 int bh_import_soa_host(bh_ctx* c, const float* px, const float* py, const float* pz, const float* vx, const float* vy,
                        const float* vz, const float* mass, int64_t n) {
     return import_host_impl(c, px, py, pz, vx, vy, vz, mass, n, true);
+}
+
+int bh_set_fixed_bounds(bh_ctx* c, const float b[6]) {
+    if (!c) return BH_E_INVAL;
+    const bool was = c->fixed_bounds_set;
+    c->fixed_bounds_set = b != nullptr;
+    if (b) memcpy(c->fixed_bounds, b, sizeof(c->fixed_bounds));
+    if (was != c->fixed_bounds_set) {   // the captured graphs contain the other variant of the keys phase
+        BH_CUDA_TRY(cudaSetDevice(c->device));
+        BH_CUDA_TRY(cudaDeviceSynchronize());
+        if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+        for (auto& g : c->half_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    }
+    return 0;
+}
+
+int bh_local_bounds(bh_ctx* c, float lohi[6]) {
+    if (!c || !lohi) return BH_E_INVAL;
+    if (!c->have_state) return BH_E_STATE;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    BH_CUDA_TRY(cudaDeviceSynchronize());
+    int e = bh_bounds_launch(c->posm, c->n, c->sc, 0);
+    if (e) return e;
+    BhDevScalars h;
+    BH_CUDA_TRY(cudaMemcpy(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < 6; ++k) {   // undo the order-preserving integer image (bh_f2ord)
+        const unsigned int u = h.bbox_enc[k];
+        const unsigned int bits = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+        memcpy(&lohi[k], &bits, 4);
+    }
+    return 0;
+}
+
+int bh_import_state(bh_ctx* c, const void* posm, const void* vel, const int32_t* ids, int64_t n, void* stream) {
+    if (!c || !posm || !vel || !ids || n <= 0 || n > c->n_max) return BH_E_INVAL;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    c->n = n; c->steps = 0; c->have_sorted = false;
+    default_slice(c);
+    BH_CUDA_TRY(cudaMemsetAsync((char*)c->sc + offsetof(BhDevScalars, epoch), 0,
+                                sizeof(BhDevScalars) - offsetof(BhDevScalars, epoch), st));
+    BH_CUDA_TRY(cudaMemsetAsync(c->heavy_flag, 0, 8 * (size_t)c->max_chunks, st));
+    BH_CUDA_TRY(cudaMemcpyAsync(c->posm, posm, (size_t)n * 16, cudaMemcpyDeviceToDevice, st));
+    BH_CUDA_TRY(cudaMemcpyAsync(c->vel, vel, (size_t)n * 16, cudaMemcpyDeviceToDevice, st));
+    BH_CUDA_TRY(cudaMemcpyAsync(c->ids, ids, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    c->have_state = true;
+    return 0;
+}
+
+int bh_let_export(bh_ctx* c, const float* boxes_lohi, int npeers, void* out, int64_t cap_per_peer, int32_t* counts,
+                  void* stream) {
+    if (!c || !boxes_lohi || !out || !counts || npeers < 1 || npeers > 64 || cap_per_peer < 1) return BH_E_INVAL;
+    if (!c->have_state || !c->have_sorted) return BH_E_STATE;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!c->let_boxes) {
+        c->let_qcap = c->n_alloc / 4 > (1 << 20) ? c->n_alloc / 4 : (1 << 20);
+        BH_CUDA_TRY(dev_alloc(&c->let_boxes, 64 * 6));
+        BH_CUDA_TRY(dev_alloc(&c->let_counts, 64 + 2));
+        BH_CUDA_TRY(dev_alloc(&c->let_queue, 2 * (size_t)c->let_qcap));
+    }
+    float boxes[64 * 6];
+    for (int r = 0; r < npeers; ++r) {   // centre / half extent exactly as the force kernel forms them
+        const float* b = boxes_lohi + 6 * r;
+        for (int a = 0; a < 3; ++a) {
+            boxes[6 * r + a] = (b[a] + b[3 + a]) * 0.5f;
+            boxes[6 * r + 3 + a] = (b[3 + a] - b[a]) * 0.5f;
+        }
+        if (b[0] > b[3]) boxes[6 * r + 3] = -1.0f;
+    }
+    BH_CUDA_TRY(cudaStreamSynchronize(st));
+    BhDevScalars h;
+    BH_CUDA_TRY(cudaMemcpy(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost));
+    BH_CUDA_TRY(cudaMemcpy(c->let_boxes, boxes, sizeof(float) * 6 * npeers, cudaMemcpyHostToDevice));
+    if (c->n >= 2) {
+        int e = bh_let_export_launch(c->cell_meta, c->cell_child, c->cell_com, c->kid_src, c->kid_lv, c->posm_s, c->sc,
+                                     c->let_boxes, npeers, (float4*)out, c->let_counts, cap_per_peer, c->let_queue,
+                                     c->let_counts + 64, c->let_qcap, c->prm.theta, c->prm.softening,
+                                     h.bounds[3] - h.bounds[0], st);
+        if (e) return e;
+        unsigned int hc[64];
+        BH_CUDA_TRY(cudaMemcpyAsync(hc, c->let_counts, sizeof(unsigned int) * npeers, cudaMemcpyDeviceToHost, st));
+        BH_CUDA_TRY(cudaStreamSynchronize(st));
+        for (int r = 0; r < npeers; ++r) counts[r] = (int32_t)(hc[r] < (unsigned long long)cap_per_peer ? hc[r] : cap_per_peer);
+    } else {   // a single body has no tree: it is its own essential set
+        for (int r = 0; r < npeers; ++r) {
+            counts[r] = 0;
+            if (boxes[6 * r + 3] < 0.0f) continue;
+            BH_CUDA_TRY(cudaMemcpyAsync((float4*)out + (size_t)r * cap_per_peer, c->posm_s, 16, cudaMemcpyDeviceToDevice, st));
+            counts[r] = 1;
+        }
+        BH_CUDA_TRY(cudaStreamSynchronize(st));
+    }
+    BH_CUDA_TRY(cudaMemcpy(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost));
+    return (h.err & BH_DERR_LET_OVERFLOW) ? BH_E_DEVICE : 0;
 }
 
 int bh_set_slice(bh_ctx* c, int rank, int world) {

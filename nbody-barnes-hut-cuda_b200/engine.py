@@ -118,6 +118,10 @@ def lib() -> C.CDLL:
     L.bh_stat.argtypes = [vp, i32]
     L.bh_stat.restype = i64
     L.bh_set_slice.argtypes = [vp, i32, i32]
+    L.bh_set_fixed_bounds.argtypes = [vp, vp]
+    L.bh_local_bounds.argtypes = [vp, vp]
+    L.bh_import_state.argtypes = [vp, vp, vp, vp, i64, vp]
+    L.bh_let_export.argtypes = [vp, vp, i32, vp, i64, vp, vp]
     L.bh_state_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     L.bh_sort_pairs_u32.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, C.POINTER(C.c_size_t), vp]
     L.bh_direct_sample.argtypes = [vp, vp, i32, vp]
@@ -348,6 +352,27 @@ class BHEngine:
 
     def load_checkpoint(self, path: str):
         _check(lib().bh_load_checkpoint(self._ctx, path.encode()), "bh_load_checkpoint")
+
+    # -- locally-essential-tree mode (include/bh.h "multi-GPU: locally-essential-tree exchange")
+    def set_fixed_bounds(self, b):
+        arr = None if b is None else np.ascontiguousarray(b, np.float32)
+        self._fixed_bounds = arr
+        _check(lib().bh_set_fixed_bounds(self._ctx, _vp(arr)), "bh_set_fixed_bounds")
+
+    def local_bounds(self) -> np.ndarray:
+        out = np.zeros(6, np.float32)
+        _check(lib().bh_local_bounds(self._ctx, _vp(out)), "bh_local_bounds")
+        return out
+
+    def import_state(self, posm, vel, ids, n: int, stream: int = 0):
+        _check(lib().bh_import_state(self._ctx, _vp(posm), _vp(vel), _vp(ids), n, C.c_void_p(stream)), "bh_import_state")
+
+    def let_export(self, boxes_lohi, out, cap_per_peer: int, stream: int = 0) -> np.ndarray:
+        boxes = np.ascontiguousarray(boxes_lohi, np.float32).reshape(-1, 6)
+        counts = np.zeros(len(boxes), np.int32)
+        _check(lib().bh_let_export(self._ctx, _vp(boxes), len(boxes), _vp(out), cap_per_peer, _vp(counts),
+                                   C.c_void_p(stream)), "bh_let_export")
+        return counts
 
     # -- multi-GPU slices
     def set_slice(self, rank: int, world: int):
