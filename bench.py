@@ -179,6 +179,11 @@ def run_ours(args, w):
 
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local}"))
     if world > 1:
+        mode = args.mode or ("let" if w["n"] > 100_000_000 else "sliced")   # north_star: replicate up to ~100M bodies
+        if mode == "let":
+            from nbody_barnes_hut_cuda_b200.let import run_let_bench      # locally-essential-tree exchange
+
+            return run_let_bench(args, w, bh, dist, rank, world, local)
         from nbody_barnes_hut_cuda_b200.sliced import run_sliced_bench  # multi-GPU Morton slices
 
         return run_sliced_bench(args, w, bh, dist, rank, world, local)
@@ -329,6 +334,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
+    ap.add_argument("--mode", default=None, choices=["sliced", "let"],
+                    help="multi-GPU scheme: replicated tree + Morton slices, or locally-essential-tree exchange")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scale-ref", action="store_true", help="skip the 16M-body single-GPU reference point")
     args = ap.parse_args()

@@ -168,3 +168,93 @@ class LetSimulation:
 
     def close(self):
         self.rank.close()
+
+
+def _morton30_numpy(px, py, pz, cube):
+    """Host-side copy of the reference key (bench:57-61) for the start-up partition only."""
+    size = max(f32(cube[3] - cube[0]), f32(1.0))
+
+    def q(p, lo):
+        t = ((p - f32(lo)) / size * f32(1023.0)).astype(f32)
+        return np.clip(t, 0, 1023).astype(np.uint32)
+
+    def spread(v):
+        v = (v * np.uint32(0x00010001)) & np.uint32(0xFF0000FF)
+        v = (v * np.uint32(0x00000101)) & np.uint32(0x0F00F00F)
+        v = (v * np.uint32(0x00000011)) & np.uint32(0xC30C30C3)
+        v = (v * np.uint32(0x00000005)) & np.uint32(0x49249249)
+        return v
+
+    return (spread(q(px, cube[0])) << np.uint32(2)) | (spread(q(py, cube[1])) << np.uint32(1)) | spread(q(pz, cube[2]))
+
+
+def run_let_bench(args, w, bh, dist, rank, world, local):
+    """bench.py leg for body counts that are not replicated (default above 100M bodies)."""
+    import time
+
+    import torch
+
+    import bench
+
+    n = w["n"]
+    soa = bench.make_ic(bh, w)                     # every rank generates the same bodies, keeps its key range
+    lo = np.array([soa[a].min() for a in range(3)], f32)
+    hi = np.array([soa[a].max() for a in range(3)], f32)
+    cube = global_cube(np.concatenate([lo, hi])[None, :])
+    keys = _morton30_numpy(soa[0], soa[1], soa[2], cube)
+    mask = split_by_keys(keys, world)[rank]
+    sel = np.nonzero(mask)[0]
+    del keys, mask
+    local_soa = [a[sel] for a in soa]
+    del soa
+    nl = len(sel)
+    cap_peer = max(1 << 20, int(0.15 * n / world))
+    sim = LetSimulation(bh, local_soa, sel.astype(np.int32), rank, world, local, dist,
+                        capacity=int(1.5 * n / world) + (world - 1) * cap_peer // 2 + 4096, cap_per_peer=cap_peer)
+    dev = sim.device
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    sim.step(args.warmup)
+    barrier()
+    sim.rank.eng.check_device_error()
+    clocks = bench.ClockSampler(local)
+    clocks.start()
+    barrier()
+    t0 = time.perf_counter()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    sim.step(args.steps)
+    b.record()
+    barrier()
+    wall = time.perf_counter() - t0
+    ms = torch.tensor([a.elapsed_time(b)], device=dev)
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ck = clocks.stop()
+    eng = sim.rank.eng
+    inter = torch.tensor([float(eng.stat(bh.STAT.INTERACTIONS_CELL) + eng.stat(bh.STAT.INTERACTIONS_BODY))], device=dev,
+                         dtype=torch.float64)
+    dist.all_reduce(inter)
+    st = torch.tensor([float(sim.stats["exported"]), float(sim.stats["imported"]), float(sim.stats["n_local"])], device=dev,
+                      dtype=torch.float64)
+    stats_all = torch.empty((world, 3), dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(stats_all, st)
+    sim.close()
+    total_ms = float(ms.item())
+    line = {
+        "metric": "body-steps/s", "value": n * args.steps / (total_ms * 1e-3), "unit": "body-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "desc": w["desc"], "n_bodies": n, "theta": 0.5, "G": 0.5, "dt": 0.02,
+                   "softening": 50.0, "max_speed": 500.0, "group": 32,
+                   "parallelism": f"locally-essential-tree x{world}: sampled key-range ownership, per-peer export walk, "
+                                  "NCCL all-to-all of point masses, ordinary step on own + imported bodies",
+                   "l2": "state far larger than L2; no flush between steps"},
+        "interactions_per_body": float(inter.item()) / n, "interactions_per_s": float(inter.item()) * args.steps / (total_ms * 1e-3),
+        "let_points_exported_imported_local_per_rank": [[int(x) for x in row] for row in stats_all.tolist()],
+        "wall_s_timed_loop": wall, "e2e": None, "gpu_launches": None, "clocks": ck,
+    }
+    dist.destroy_process_group()
+    return line if rank == 0 else None
