@@ -336,6 +336,7 @@ def main():
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
     ap.add_argument("--mode", default=None, choices=["sliced", "let"],
                     help="multi-GPU scheme: replicated tree + Morton slices, or locally-essential-tree exchange")
+    ap.add_argument("--let-no-rebalance", action="store_true", help="LET mode: equal-count key ranges instead of equal work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scale-ref", action="store_true", help="skip the 16M-body single-GPU reference point")
     args = ap.parse_args()

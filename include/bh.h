@@ -141,8 +141,9 @@ enum {
     BH_DBG_IDS,          /* i32[n]     internal slot -> original body id    */
     BH_DBG_POSM,         /* float4[n]  x,y,z,mass  current state            */
     BH_DBG_VEL,          /* float4[n]  vx,vy,vz,0  current state            */
-    BH_DBG_ACC,          /* float4[n]  ax,ay,az,0  sorted order of the last
-                            step (slot i pairs with *_SORTED slot i)        */
+    BH_DBG_ACC,          /* float4[n]  ax,ay,az,work  sorted order of the last
+                            step (slot i pairs with *_SORTED slot i); work =
+                            interaction-list entries of the body's 32-chunk  */
     BH_DBG_CELL_META,    /* int4[cells]   first,count,level|bucket<<8|slot<<12,parent
                             (slot = which child of its parent the cell is)   */
     BH_DBG_CELL_COM,     /* float4[cells] comx,comy,comz,mass               */
@@ -205,13 +206,30 @@ int  bh_state_ptrs(bh_ctx* ctx, void** posm, void** vel, void** ids,
 int  bh_set_fixed_bounds(bh_ctx* ctx, const float b[6]);
 /* min xyz / max xyz of the current state (host floats; synchronises).                                   */
 int  bh_local_bounds(bh_ctx* ctx, float lohi[6]);
-/* Load the internal layout directly: DEVICE float4 posm {x,y,z,m}, float4 vel, int32 ids (any ids; the
- * step carries them along unchanged).                                                                   */
+/* Load the internal layout directly: DEVICE float4 posm {x,y,z,m}, float4 vel, int32 ids (the step carries
+ * them along unchanged).  A body with id < 0 is a GHOST: it attracts like any other body but its own
+ * acceleration is not wanted — the traversal leaves it out of the group boxes and skips groups made of
+ * ghosts only (imported far-field points would otherwise form huge, expensive groups).  vel.w is carried
+ * along untouched by the step (let.py keeps the per-body work estimate there).                          */
 int  bh_import_state(bh_ctx* ctx, const void* posm, const void* vel, const int32_t* ids, int64_t n, void* stream);
-/* boxes_lohi: HOST npeers x 6 (lo xyz, hi xyz; lo.x > hi.x = skip that peer); out: DEVICE float4
- * [npeers * cap_per_peer]; counts: HOST npeers.  Needs the tree of the current state (phases KEYS..COM).
- * Synchronises.  Returns BH_E_DEVICE if an output list overflowed.                                      */
-int  bh_let_export(bh_ctx* ctx, const float* boxes_lohi, int npeers, void* out, int64_t cap_per_peer,
+/* A domain (a Morton-key range) is not convex, so it is described by K boxes: the tight AABB (lo xyz, hi
+ * xyz; lo > hi when empty) of the bodies whose key lies in [cuts[k], cuts[k+1]) for k < K.  Cutting at
+ * octree-cell boundaries of the key space makes every whole-cell interval convex and disjoint from the other
+ * ranks' ranges.  cuts: HOST K+1 ascending keys (the last may be 2^30); lohi: HOST K x 6; body_counts: HOST
+ * K or NULL.  Needs phases KEYS+SORT of the current state; synchronises.                                  */
+#define BH_LET_MAX_PEERS 64
+#define BH_LET_MAX_BOXES 256
+int  bh_let_domain_boxes(bh_ctx* ctx, const uint32_t* cuts, int K, float* lohi, int32_t* body_counts);
+/* Device pointers to THIS step's Morton-sorted arrays (u32 keys ascending, float4 posm, float4 vel, int32
+ * ids) after phases KEYS+SORT — a key-range owner migrates bodies to their new owners straight from these
+ * (runs of the sorted order) — and to the accelerations of the last force phase (float4 ax,ay,az,work;
+ * same order).  Any pointer may be NULL.  Valid until the next import/step.                               */
+int  bh_sorted_ptrs(bh_ctx* ctx, void** keys, void** posm, void** vel, void** ids, void** acc, int64_t* n);
+/* boxes_lohi: HOST npeers x K x 6 (lo xyz, hi xyz; lo.x > hi.x = unused box; a peer with no used box is
+ * skipped); out: DEVICE float4 [npeers * cap_per_peer]; counts: HOST npeers.  A cell is emitted as one
+ * point iff it passes the acceptance test at the NEAREST of the peer's boxes.  Needs the tree of the
+ * current state (phases KEYS..COM).  Synchronises.  Returns BH_E_DEVICE if an output list overflowed.  */
+int  bh_let_export(bh_ctx* ctx, const float* boxes_lohi, int npeers, int K, void* out, int64_t cap_per_peer,
                    int32_t* counts, void* stream);
 
 /* ---- standalone pieces -------------------------------------------------- */

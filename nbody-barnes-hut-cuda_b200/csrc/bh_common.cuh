@@ -96,8 +96,9 @@ int bh_com_launch(const float4* posm, int64_t n, const int4* cell_meta, const in
                   int32_t* cell_arrive, float4* cell_mom, float4* cell_com, float4* kid_src,
                   BhDevScalars* sc, cudaStream_t st);
 // heavy_list, heavy_flag: 2 * max_chunks u32 each (see BhDevScalars::epoch)
-int bh_force_launch(const float4* posm, const uint32_t* keys, int64_t n, int64_t first_body, int64_t body_count,
-                    const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
+// ids: nullptr, or per-body ids where id < 0 marks a ghost (a source whose own acceleration is not wanted)
+int bh_force_launch(const float4* posm, const uint32_t* keys, const int32_t* ids, int64_t n, int64_t first_body,
+                    int64_t body_count, const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
                     const float4* kid_src, const uint8_t* kid_lv,
                     float4* acc, BhDevScalars* sc, uint32_t* heavy_list, uint32_t* heavy_flag, int64_t max_chunks,
                     float theta, float softening, float G, float split_alpha, int num_sms, cudaStream_t st);
@@ -119,6 +120,8 @@ int bh_visuals_launch(const float4* posm, const float4* vel, const int32_t* ids,
                       cudaStream_t st);
 int bh_momentum_launch(const float4* posm, const float4* vel, int64_t n, double* out7, cudaStream_t st);
 int bh_let_export_launch(const int4* cell_meta, const int32_t* cell_child, const float4* cell_com, const float4* kid_src,
-                         const uint8_t* kid_lv, const float4* posm, BhDevScalars* sc, const float* boxes_dev, int npeers,
-                         float4* out, unsigned int* out_count, long long cap, int2* queue, unsigned int* qcounts,
+                         const uint8_t* kid_lv, const float4* posm, BhDevScalars* sc, const float* boxes_dev,
+                         const float* hull_dev, int npeers, int K, float4* out, unsigned int* out_count, long long cap, int2* queue, unsigned int* qcounts,
                          long long qcap, float theta, float softening, float root_w, cudaStream_t st);
+int bh_domain_boxes_launch(const uint32_t* keys, const float4* posm, long long n, const uint32_t* cuts_dev, int K,
+                           float* out_dev, int* counts_dev, cudaStream_t st);

@@ -54,8 +54,8 @@ struct bh_ctx {
     // locally-essential-tree mode
     bool fixed_bounds_set = false;
     float fixed_bounds[6] = {0, 0, 0, 0, 0, 0};
-    float* let_boxes = nullptr;          // 64 peers x 6
-    unsigned int* let_counts = nullptr;  // 64 + 2 queue counters
+    float* let_boxes = nullptr;          // BH_LET_MAX_PEERS x (BH_LET_MAX_BOXES + 1) x 6: boxes, then one hull per peer
+    unsigned int* let_counts = nullptr;  // BH_LET_MAX_PEERS + 2 queue counters
     int2* let_queue = nullptr;           // 2 x let_qcap
     long long let_qcap = 0;
 
@@ -140,7 +140,7 @@ int phase_com(bh_ctx* c, cudaStream_t st) {
 }
 
 int phase_force(bh_ctx* c, cudaStream_t st) {
-    return bh_force_launch(c->posm_s, c->keys0, c->n, c->slice_first, c->slice_count, c->cell_meta, c->cell_child,
+    return bh_force_launch(c->posm_s, c->keys0, c->ids_s, c->n, c->slice_first, c->slice_count, c->cell_meta, c->cell_child,
                            c->cell_com, c->kid_src, c->kid_lv, c->acc, c->sc, c->heavy_list, c->heavy_flag, c->max_chunks, c->prm.theta,
                            c->prm.softening, c->prm.G, c->prm.group_split, c->num_sms, st);
 }
@@ -379,45 +379,102 @@ int bh_import_state(bh_ctx* c, const void* posm, const void* vel, const int32_t*
     return 0;
 }
 
-int bh_let_export(bh_ctx* c, const float* boxes_lohi, int npeers, void* out, int64_t cap_per_peer, int32_t* counts,
+static int let_scratch(bh_ctx* c) {
+    if (c->let_boxes) return 0;
+    c->let_qcap = c->n_alloc / 4 > (1 << 20) ? c->n_alloc / 4 : (1 << 20);
+    BH_CUDA_TRY(dev_alloc(&c->let_boxes, (size_t)BH_LET_MAX_PEERS * (BH_LET_MAX_BOXES + 1) * 6));
+    BH_CUDA_TRY(dev_alloc(&c->let_counts, BH_LET_MAX_PEERS + 2));
+    BH_CUDA_TRY(dev_alloc(&c->let_queue, 2 * (size_t)c->let_qcap));
+    return 0;
+}
+
+int bh_let_domain_boxes(bh_ctx* c, const uint32_t* cuts, int K, float* lohi, int32_t* body_counts) {
+    if (!c || !cuts || !lohi || K < 1 || K > BH_LET_MAX_BOXES) return BH_E_INVAL;
+    for (int k = 0; k < K; ++k)
+        if (cuts[k] > cuts[k + 1]) return BH_E_INVAL;
+    if (!c->have_state || !c->have_sorted) return BH_E_STATE;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    int e = let_scratch(c);
+    if (e) return e;
+    BH_CUDA_TRY(cudaDeviceSynchronize());
+    // scratch: boxes at the front of let_boxes, cuts and counts behind them (the export call rewrites all of it)
+    uint32_t* d_cuts = (uint32_t*)(c->let_boxes + (size_t)6 * BH_LET_MAX_BOXES);
+    int* d_counts = (int*)(d_cuts + BH_LET_MAX_BOXES + 1);
+    BH_CUDA_TRY(cudaMemcpy(d_cuts, cuts, sizeof(uint32_t) * (K + 1), cudaMemcpyHostToDevice));
+    e = bh_domain_boxes_launch(c->keys0, c->posm_s, c->n, d_cuts, K, c->let_boxes, d_counts, 0);
+    if (e) return e;
+    BH_CUDA_TRY(cudaMemcpy(lohi, c->let_boxes, sizeof(float) * 6 * K, cudaMemcpyDeviceToHost));
+    if (body_counts) BH_CUDA_TRY(cudaMemcpy(body_counts, d_counts, sizeof(int) * K, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int bh_sorted_ptrs(bh_ctx* c, void** keys, void** posm, void** vel, void** ids, void** acc, int64_t* n) {
+    if (!c) return BH_E_INVAL;
+    if (!c->have_state || !c->have_sorted) return BH_E_STATE;
+    if (keys) *keys = c->keys0;
+    if (posm) *posm = c->posm_s;
+    if (vel) *vel = c->vel_s;
+    if (ids) *ids = c->ids_s;
+    if (acc) *acc = c->acc;
+    if (n) *n = c->n;
+    return 0;
+}
+
+int bh_let_export(bh_ctx* c, const float* boxes_lohi, int npeers, int K, void* out, int64_t cap_per_peer, int32_t* counts,
                   void* stream) {
-    if (!c || !boxes_lohi || !out || !counts || npeers < 1 || npeers > 64 || cap_per_peer < 1) return BH_E_INVAL;
+    if (!c || !boxes_lohi || !out || !counts || npeers < 1 || npeers > BH_LET_MAX_PEERS || K < 1 || K > BH_LET_MAX_BOXES ||
+        cap_per_peer < 1)
+        return BH_E_INVAL;
     if (!c->have_state || !c->have_sorted) return BH_E_STATE;
     BH_CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
-    if (!c->let_boxes) {
-        c->let_qcap = c->n_alloc / 4 > (1 << 20) ? c->n_alloc / 4 : (1 << 20);
-        BH_CUDA_TRY(dev_alloc(&c->let_boxes, 64 * 6));
-        BH_CUDA_TRY(dev_alloc(&c->let_counts, 64 + 2));
-        BH_CUDA_TRY(dev_alloc(&c->let_queue, 2 * (size_t)c->let_qcap));
-    }
-    float boxes[64 * 6];
-    for (int r = 0; r < npeers; ++r) {   // centre / half extent exactly as the force kernel forms them
-        const float* b = boxes_lohi + 6 * r;
+    { int e0 = let_scratch(c); if (e0) return e0; }
+    // layout: npeers*K boxes, then npeers hulls (the AABB of each peer's used boxes)
+    std::vector<float> boxes(((size_t)npeers * K + npeers) * 6);
+    std::vector<char> active((size_t)npeers, 0);
+    std::vector<float> hull((size_t)npeers * 6);
+    for (int p = 0; p < npeers; ++p)
+        for (int a = 0; a < 3; ++a) { hull[6 * p + a] = 3.0e38f; hull[6 * p + 3 + a] = -3.0e38f; }
+    auto centre_half = [](const float* b, float* o) {   // centre / half extent exactly as the force kernel forms them
         for (int a = 0; a < 3; ++a) {
-            boxes[6 * r + a] = (b[a] + b[3 + a]) * 0.5f;
-            boxes[6 * r + 3 + a] = (b[3 + a] - b[a]) * 0.5f;
+            o[a] = (b[a] + b[3 + a]) * 0.5f;
+            o[3 + a] = (b[3 + a] - b[a]) * 0.5f;
         }
-        if (b[0] > b[3]) boxes[6 * r + 3] = -1.0f;
+    };
+    for (int r = 0; r < npeers * K; ++r) {
+        const float* b = boxes_lohi + 6 * r;
+        centre_half(b, &boxes[6 * r]);
+        if (b[0] > b[3]) { boxes[6 * r + 3] = -1.0f; continue; }
+        active[r / K] = 1;
+        float* h = &hull[6 * (r / K)];
+        for (int a = 0; a < 3; ++a) {
+            h[a] = b[a] < h[a] ? b[a] : h[a];
+            h[3 + a] = b[3 + a] > h[3 + a] ? b[3 + a] : h[3 + a];
+        }
+    }
+    for (int p = 0; p < npeers; ++p) {
+        float* o = &boxes[((size_t)npeers * K + p) * 6];
+        if (active[p]) centre_half(&hull[6 * p], o);
+        else { for (int a = 0; a < 6; ++a) o[a] = 0.0f; }
     }
     BH_CUDA_TRY(cudaStreamSynchronize(st));
     BhDevScalars h;
     BH_CUDA_TRY(cudaMemcpy(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost));
-    BH_CUDA_TRY(cudaMemcpy(c->let_boxes, boxes, sizeof(float) * 6 * npeers, cudaMemcpyHostToDevice));
+    BH_CUDA_TRY(cudaMemcpy(c->let_boxes, boxes.data(), sizeof(float) * boxes.size(), cudaMemcpyHostToDevice));
     if (c->n >= 2) {
         int e = bh_let_export_launch(c->cell_meta, c->cell_child, c->cell_com, c->kid_src, c->kid_lv, c->posm_s, c->sc,
-                                     c->let_boxes, npeers, (float4*)out, c->let_counts, cap_per_peer, c->let_queue,
-                                     c->let_counts + 64, c->let_qcap, c->prm.theta, c->prm.softening,
+                                     c->let_boxes, c->let_boxes + (size_t)npeers * K * 6, npeers, K, (float4*)out, c->let_counts, cap_per_peer, c->let_queue,
+                                     c->let_counts + BH_LET_MAX_PEERS, c->let_qcap, c->prm.theta, c->prm.softening,
                                      h.bounds[3] - h.bounds[0], st);
         if (e) return e;
-        unsigned int hc[64];
+        unsigned int hc[BH_LET_MAX_PEERS];
         BH_CUDA_TRY(cudaMemcpyAsync(hc, c->let_counts, sizeof(unsigned int) * npeers, cudaMemcpyDeviceToHost, st));
         BH_CUDA_TRY(cudaStreamSynchronize(st));
         for (int r = 0; r < npeers; ++r) counts[r] = (int32_t)(hc[r] < (unsigned long long)cap_per_peer ? hc[r] : cap_per_peer);
     } else {   // a single body has no tree: it is its own essential set
         for (int r = 0; r < npeers; ++r) {
             counts[r] = 0;
-            if (boxes[6 * r + 3] < 0.0f) continue;
+            if (!active[r]) continue;
             BH_CUDA_TRY(cudaMemcpyAsync((float4*)out + (size_t)r * cap_per_peer, c->posm_s, 16, cudaMemcpyDeviceToDevice, st));
             counts[r] = 1;
         }

@@ -26,6 +26,16 @@
 // edges; redux.sync min/max on order-preserving integer images of the coordinates), recursively,
 // and traverses each sub-group with all 32 lanes opening cells but only the sub-group's lanes
 // keeping the result.  oracle/bh_oracle.cpp:orc_make_groups is the CPU restatement of the rule.
+//
+// Ghosts (locally-essential-tree mode): bodies with id < 0 are point masses imported from other ranks.
+// They are sources like any other body (they sit in the tree) but nobody needs THEIR acceleration, and
+// being coarse far-away cells they are spatially sparse — a sub-group box around 32 of them would span
+// half the system and open most of the tree.  They are therefore left out of the sub-group boxes, a
+// sub-group without real bodies is skipped, and a cut that separates ghosts from real bodies is always
+// taken.  Without ghosts (ids == nullptr or all ids >= 0) nothing changes.
+//
+// acc[i].w carries the work of body i's chunk (its interaction-list entries, all sub-groups) so that a
+// driver can balance key ranges by measured work (let.py).
 #include "bh_common.cuh"
 
 namespace {
@@ -141,8 +151,8 @@ __device__ __forceinline__ void eval_tile(const SrcPair* __restrict__ src, f32x2
 }
 
 __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
-    const float4* __restrict__ posm, const uint32_t* __restrict__ keys, int64_t first_body, int64_t body_count,
-    const int4* __restrict__ cell_meta, const int32_t* __restrict__ cell_child, const float4* __restrict__ cell_com,
+    const float4* __restrict__ posm, const uint32_t* __restrict__ keys, const int32_t* __restrict__ ids,
+    int64_t first_body, int64_t body_count, const int4* __restrict__ cell_meta, const int32_t* __restrict__ cell_child, const float4* __restrict__ cell_com,
     const float4* __restrict__ kid_src, const uint8_t* __restrict__ kid_lv, float4* __restrict__ acc, BhDevScalars* sc,
     uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_flag, int64_t max_chunks, float theta, float soft,
     float G, float split_alpha) {
@@ -195,6 +205,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
         const bool valid = my < end_body;
         const int nb = (int)min((int64_t)BH_GROUP, end_body - (first_body + (int64_t)g * BH_GROUP));
         const float4 me = __ldg(posm + (valid ? my : end_body - 1));
+        const bool sink = valid && (ids == nullptr || __ldg(ids + my) >= 0);   // someone wants this body's acceleration
 
         // ---- split the chunk into spatially compact sub-groups (see the file header) ----
         const uint32_t mykey = __ldg(keys + (valid ? my : end_body - 1));
@@ -211,9 +222,11 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
         while (ga < nb) {
         const unsigned pending = cuts >> ga;
         int gb = pending ? ga + __ffs(pending) : nb;
+        unsigned sinks = __ballot_sync(0xffffffffu, lane >= ga && lane < gb && sink);
+        if (!sinks) { ga = gb; continue; }        // ghosts only: nothing to compute
         float lox, loy, loz, hix, hiy, hiz;
         {
-            const bool in = lane >= ga && lane < gb;
+            const bool in = lane >= ga && lane < gb && sink;
             lox = bh_ord2f(__reduce_min_sync(0xffffffffu, in ? ox : 0xFFFFFFFFu));
             loy = bh_ord2f(__reduce_min_sync(0xffffffffu, in ? oy : 0xFFFFFFFFu));
             loz = bh_ord2f(__reduce_min_sync(0xffffffffu, in ? oz : 0xFFFFFFFFu));
@@ -226,7 +239,10 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
             const int best = __reduce_min_sync(0xffffffffu, cand);   // fewest shared digits, first such pair
             if ((best >> 5) >= BH_MAX_LEVEL) break;
             const int gk = (best & 31) + 1;
-            const bool inA = lane >= ga && lane < gk, inB = lane >= gk && lane < gb;
+            const bool inA = lane >= ga && lane < gk && sink, inB = lane >= gk && lane < gb && sink;
+            const unsigned sA = __ballot_sync(0xffffffffu, inA), sB = __ballot_sync(0xffffffffu, inB);
+            if (!sA) { cuts |= 1u << (gk - 1); ga = gk; continue; }   // ghosts in front: drop them, same box
+            if (!sB) { cuts |= 1u << (gk - 1); gb = gk; continue; }   // ghosts behind: leave them to the next round
             const float alx = bh_ord2f(__reduce_min_sync(0xffffffffu, inA ? ox : 0xFFFFFFFFu));
             const float aly = bh_ord2f(__reduce_min_sync(0xffffffffu, inA ? oy : 0xFFFFFFFFu));
             const float alz = bh_ord2f(__reduce_min_sync(0xffffffffu, inA ? oz : 0xFFFFFFFFu));
@@ -245,10 +261,11 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
             if (!(__fadd_rn(eA, eB) < __fmul_rn(split_alpha, eAB))) break;
             cuts |= 1u << (gk - 1);
             gb = gk;
+            sinks = sA;
             lox = alx; loy = aly; loz = alz; hix = ahx; hiy = ahy; hiz = ahz;
         }
         const bool in_group = lane >= ga && lane < gb;
-        const int gsize = gb - ga;
+        const int gsize = __popc(sinks);
         const float cx = __fmul_rn(__fadd_rn(lox, hix), 0.5f), hx = __fmul_rn(__fsub_rn(hix, lox), 0.5f);
         const float cy = __fmul_rn(__fadd_rn(loy, hiy), 0.5f), hy = __fmul_rn(__fsub_rn(hiy, loy), 0.5f);
         const float cz = __fmul_rn(__fadd_rn(loz, hiz), 0.5f), hz = __fmul_rn(__fsub_rn(hiz, loz), 0.5f);
@@ -425,7 +442,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
             if ((int64_t)slot < max_chunks) { list_nxt[slot] = g; flag_nxt[g] = epoch + 1u; }
         }
 
-        if (valid) acc[my] = make_float4(G * ax, G * ay, G * az, 0.f);
+        if (valid) acc[my] = make_float4(G * ax, G * ay, G * az, (float)chunk_entries);
         tot_cell += acc_cells_w;
         tot_body += dir_bodies_w;
     }
@@ -474,8 +491,8 @@ int bh_force_prepare() {
     return 0;
 }
 
-int bh_force_launch(const float4* posm, const uint32_t* keys, int64_t n, int64_t first_body, int64_t body_count,
-                    const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
+int bh_force_launch(const float4* posm, const uint32_t* keys, const int32_t* ids, int64_t n, int64_t first_body,
+                    int64_t body_count, const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
                     const float4* kid_src, const uint8_t* kid_lv,
                     float4* acc, BhDevScalars* sc, uint32_t* heavy_list, uint32_t* heavy_flag, int64_t max_chunks,
                     float theta, float softening, float G, float split_alpha, int num_sms, cudaStream_t st) {
@@ -491,7 +508,7 @@ int bh_force_launch(const float4* posm, const uint32_t* keys, int64_t n, int64_t
     int64_t want = (ngroups + FORCE_WARPS - 1) / FORCE_WARPS;
     int64_t grid = (int64_t)(num_sms > 0 ? num_sms : BH_NUM_SMS_FALLBACK) * max_ctas;  // persistent: fill the chip once
     if (grid > want) grid = want;
-    force_kernel<<<(int)grid, FORCE_THREADS, 0, st>>>(posm, keys, first_body, body_count, cell_meta, cell_child, cell_com,
+    force_kernel<<<(int)grid, FORCE_THREADS, 0, st>>>(posm, keys, ids, first_body, body_count, cell_meta, cell_child, cell_com,
                                                      kid_src, kid_lv, acc, sc, heavy_list, heavy_flag, max_chunks, theta,
                                                      softening, G, split_alpha);
     return (int)cudaGetLastError();

@@ -121,7 +121,9 @@ def lib() -> C.CDLL:
     L.bh_set_fixed_bounds.argtypes = [vp, vp]
     L.bh_local_bounds.argtypes = [vp, vp]
     L.bh_import_state.argtypes = [vp, vp, vp, vp, i64, vp]
-    L.bh_let_export.argtypes = [vp, vp, i32, vp, i64, vp, vp]
+    L.bh_let_export.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp]
+    L.bh_let_domain_boxes.argtypes = [vp, vp, i32, vp, vp]
+    L.bh_sorted_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
     L.bh_state_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
     L.bh_sort_pairs_u32.argtypes = [vp, vp, vp, vp, i64, i32, i32, vp, C.POINTER(C.c_size_t), vp]
     L.bh_direct_sample.argtypes = [vp, vp, i32, vp]
@@ -367,10 +369,27 @@ class BHEngine:
     def import_state(self, posm, vel, ids, n: int, stream: int = 0):
         _check(lib().bh_import_state(self._ctx, _vp(posm), _vp(vel), _vp(ids), n, C.c_void_p(stream)), "bh_import_state")
 
+    def let_domain_boxes(self, cuts):
+        """cuts: K+1 ascending u32 keys -> (boxes [K,6] lo/hi, body counts [K])."""
+        cuts = np.ascontiguousarray(cuts, np.uint32)
+        k = len(cuts) - 1
+        out, counts = np.zeros((k, 6), np.float32), np.zeros(k, np.int32)
+        _check(lib().bh_let_domain_boxes(self._ctx, _vp(cuts), k, _vp(out), _vp(counts)), "bh_let_domain_boxes")
+        return out, counts
+
+    def sorted_ptrs(self):
+        vp, i64 = C.c_void_p, C.c_int64
+        keys, posm, vel, ids, acc, n = vp(), vp(), vp(), vp(), vp(), i64()
+        _check(lib().bh_sorted_ptrs(self._ctx, C.byref(keys), C.byref(posm), C.byref(vel), C.byref(ids), C.byref(acc),
+                                    C.byref(n)), "bh_sorted_ptrs")
+        return dict(keys=keys.value, posm=posm.value, vel=vel.value, ids=ids.value, acc=acc.value, n=n.value)
+
     def let_export(self, boxes_lohi, out, cap_per_peer: int, stream: int = 0) -> np.ndarray:
-        boxes = np.ascontiguousarray(boxes_lohi, np.float32).reshape(-1, 6)
-        counts = np.zeros(len(boxes), np.int32)
-        _check(lib().bh_let_export(self._ctx, _vp(boxes), len(boxes), _vp(out), cap_per_peer, _vp(counts),
+        """boxes_lohi: [npeers, K, 6] host array (lo xyz, hi xyz per box)."""
+        boxes = np.ascontiguousarray(boxes_lohi, np.float32)
+        npeers, k = boxes.shape[0], boxes.shape[1]
+        counts = np.zeros(npeers, np.int32)
+        _check(lib().bh_let_export(self._ctx, _vp(boxes), npeers, k, _vp(out), cap_per_peer, _vp(counts),
                                    C.c_void_p(stream)), "bh_let_export")
         return counts
 

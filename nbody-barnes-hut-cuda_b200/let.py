@@ -1,19 +1,29 @@
 """Locally-essential-tree mode (BASELINE.json north_star "beyond ~100M bodies"; SURVEY §8e, second bullet).
 
-Each rank owns a subset of the bodies (a Morton-key range at start-up) and never sees the others' bodies.
-Per step (include/bh.h "locally-essential-tree exchange"):
-  boxes      every rank's body AABB is all-gathered; their union gives the global cube (reference formula,
+Each rank owns the bodies of one Morton-key range and never sees the others' bodies.  Per step
+(include/bh.h "locally-essential-tree exchange"):
+  cube       every rank's body AABB is all-gathered; their union gives the global cube (reference formula,
              nbody_v5_bench.cu:148-154) that all ranks fix, so Morton keys share one grid;
+  splitters  keys + sort of the own bodies; every body carries the work its traversal chunk cost in the
+             previous step (interaction-list entries, acc.w -> vel.w); every rank contributes SAMPLE keys
+             taken at equal increments of its cumulative work; the weighted quantiles of the pooled sample
+             are the new key ranges (SURVEY §8e "sampled key splitters") — equal WORK, not equal count;
+  migrate    the bodies that left the rank's range are runs of its sorted order: one all-to-all;
   local tree keys, sort, tree, centre of mass over the rank's own bodies;
-  export     one walk of that tree per peer against the peer's box (csrc/bh_let.cu) -> point masses;
+  domain     the key range is cut at octree-cell boundaries (domain_cuts) and described by the tight body
+             AABB of every interval (bh_let_domain_boxes) — a key range is not convex, whole cells are;
+  export     one walk of the local tree per peer against the peer's boxes (csrc/bh_let.cu) -> point masses;
   exchange   all-to-all of the point lists (variable sizes);
   union step own bodies + received points (ids = -1) go through the ordinary step; received points are
-             dropped afterwards, own bodies stay in Morton order for the next step.
+             dropped afterwards.
 `LetRank` is the per-rank logic; `let_step_emulated` drives several ranks on ONE device (tests — the
 guide forbids emulating ranks with kernels that wait on each other, this path has no such kernels);
 `LetSimulation` is the torch.distributed driver (NCCL all-gather + all-to-all).
 """
 from __future__ import annotations
+
+import os
+import time
 
 import numpy as np
 
@@ -21,6 +31,11 @@ from .engine import DBG, FLAG_NO_GRAPH, PHASE, BHEngine
 from .sliced import _DevView
 
 f32 = np.float32
+KEY_END = 1 << 30      # one past the largest 30-bit key
+SAMPLE = 4096          # keys every rank contributes to the splitter election
+WORK_FLOOR = 16.0      # added to every body's measured work (the non-traversal phases; keeps the sum positive)
+MAX_BOXES = 200        # boxes that describe one rank's domain (<= BH_LET_MAX_BOXES)
+EMPTY_BOX = np.array([1, 1, 1, -1, -1, -1], f32)   # lo > hi
 
 
 def global_cube(boxes_lohi: np.ndarray) -> np.ndarray:
@@ -35,12 +50,75 @@ def global_cube(boxes_lohi: np.ndarray) -> np.ndarray:
 
 
 def split_by_keys(keys: np.ndarray, world: int, sample: int = 1 << 20, seed: int = 0):
-    """Sampled key splitters: returns `world` boolean masks, one per rank."""
+    """Start-up partition by sampled key splitters: returns `world` boolean masks."""
     rng = np.random.default_rng(seed)
     samp = np.sort(keys if len(keys) <= sample else rng.choice(keys, sample, replace=False))
     cuts = [samp[(len(samp) * r) // world] for r in range(1, world)]
     edges = [0] + [int(c) for c in cuts] + [1 << 32]
     return [(keys >= edges[r]) & (keys < edges[r + 1]) for r in range(world)]
+
+
+def elect_splitters(samples: np.ndarray, work: np.ndarray) -> np.ndarray:
+    """Key-range edges [world+1] from every rank's key sample.
+
+    samples [world, SAMPLE]: keys of rank r at equal increments of its cumulative work, so that every sample
+    stands for work[r]/SAMPLE (rows of ranks with work 0 are ignored).  Edge r is the key at r/world of the
+    pooled work.  Identical on all ranks (pure function of all-gathered data)."""
+    world = len(work)
+    work = np.asarray(work, np.float64)
+    if not (work > 0).any():
+        return np.array([0] + [KEY_END] * world, np.int64)
+    wgt = np.repeat(np.where(work > 0, work / samples.shape[1], 0.0), samples.shape[1])
+    keys = np.asarray(samples, np.int64).reshape(-1)
+    order = np.argsort(keys, kind="stable")
+    keys, cum = keys[order], np.cumsum(wgt[order])
+    edges = [0]
+    for r in range(1, world):
+        k = int(keys[min(int(np.searchsorted(cum, cum[-1] * r / world)), len(keys) - 1)])
+        edges.append(max(k, edges[-1]))
+    edges.append(KEY_END)
+    return np.array(edges, np.int64)
+
+
+def domain_cuts(k_lo: int, k_hi: int) -> np.ndarray:
+    """MAX_BOXES+1 ascending keys that cut [k_lo, k_hi) at octree-cell boundaries.
+
+    Interior: the 8..64 cells of size S = 8^j (largest with span/S >= 8) that lie inside the range — whole
+    cells, convex, owned by this rank alone.  The two ragged ends (parts of one S-cell each) are cut again
+    at S/64 so that their boxes reach at most one small cell into the neighbour's range.  Padded with k_hi
+    (empty intervals) to a fixed length so the boxes can be all-gathered."""
+    cuts = {int(k_lo), int(k_hi)}
+    span = int(k_hi) - int(k_lo)
+    if span > 0:
+        S = 1
+        while S * 64 <= span:
+            S *= 8
+        first = -(-int(k_lo) // S) * S
+        last = int(k_hi) // S * S
+        if first <= last:
+            cuts.update(range(first, last + 1, S))
+            fine = max(S // 64, 1)
+            for a, b in ((int(k_lo), first), (last, int(k_hi))):
+                if b - a > fine:
+                    cuts.update(range(-(-a // fine) * fine, b, fine))
+        else:                                  # the whole range lies inside one S-cell
+            fine = max(S // 64, 1)
+            cuts.update(range(-(-int(k_lo) // fine) * fine, int(k_hi), fine))
+    out = sorted(c for c in cuts if k_lo <= c <= k_hi)
+    assert len(out) <= MAX_BOXES + 1, len(out)
+    out += [int(k_hi)] * (MAX_BOXES + 1 - len(out))
+    return np.array(out, np.uint32)
+
+
+def compact_boxes(boxes: np.ndarray) -> np.ndarray:
+    """[world, MAX_BOXES, 6] -> [world, K, 6]: used boxes first, K = the largest used count (>= 1)."""
+    used = boxes[:, :, 0] <= boxes[:, :, 3]
+    k = max(1, int(used.sum(1).max()))
+    out = np.tile(EMPTY_BOX, (boxes.shape[0], k, 1))
+    for r in range(boxes.shape[0]):
+        b = boxes[r][used[r]]
+        out[r, : len(b)] = b
+    return out
 
 
 class LetRank:
@@ -52,6 +130,7 @@ class LetRank:
         self.eng = BHEngine(capacity, device=dev_index, flags=FLAG_NO_GRAPH, **params)
         self.out = torch.empty((npeers, cap_per_peer, 4), dtype=torch.float32, device=device)
         self.last = {}
+        self._ev = None
 
     @property
     def n(self) -> int:
@@ -62,21 +141,76 @@ class LetRank:
 
     def local_box(self) -> np.ndarray:
         if self.n == 0:
-            return np.array([1, 1, 1, -1, -1, -1], f32)     # lo > hi: "no bodies here"
+            return EMPTY_BOX.copy()
         self.eng.import_state(self.posm, self.vel, self.ids, self.n, self._stream())
         return self.eng.local_bounds()
 
-    def build_local_tree(self, cube: np.ndarray):
+    # ---- ownership: splitter election and migration ------------------------------------------
+    def sort_own(self, cube: np.ndarray, by_work: bool = True):
+        """Fix the global cube, key + sort the own bodies.  Returns (SAMPLE sorted keys taken at equal increments
+        of the cumulative work the bodies carry in vel.w, total work); bodies without a measurement yet (first
+        step) or by_work=False count 1 each."""
         self.eng.set_fixed_bounds(cube)
+        if self.n == 0:
+            return np.zeros(SAMPLE, np.int64), 0.0
+        torch, st = self.torch, self._stream()
+        self.eng.run_phase(PHASE.KEYS, st)                      # state imported by local_box()
+        self.eng.run_phase(PHASE.SORT, st)
+        keys, _, vel, _ = self._sorted()
+        work = vel[:, 3].double() + WORK_FLOOR if by_work else None
+        if work is None or float(vel[:, 3].max().item()) <= 0.0:
+            pick = torch.linspace(0, self.n - 1, SAMPLE, device=self.device).long()
+            return keys[pick].cpu().numpy().astype(np.int64), float(self.n)
+        cum = torch.cumsum(work, 0)
+        total = float(cum[-1].item())
+        targets = (torch.arange(SAMPLE, device=self.device, dtype=torch.float64) + 0.5) * (total / SAMPLE)
+        pick = torch.searchsorted(cum, targets).clamp_(max=self.n - 1)
+        return keys[pick].cpu().numpy().astype(np.int64), total
+
+    def _sorted(self):
+        """Views of this step's Morton-sorted keys / posm / vel / ids (valid until the next import)."""
+        torch, p = self.torch, self.eng.sorted_ptrs()
+        n = p["n"]
+        return (torch.as_tensor(_DevView(p["keys"], (n,), "<i4"), device=self.device),
+                torch.as_tensor(_DevView(p["posm"], (n, 4), "<f4"), device=self.device),
+                torch.as_tensor(_DevView(p["vel"], (n, 4), "<f4"), device=self.device),
+                torch.as_tensor(_DevView(p["ids"], (n,), "<i4"), device=self.device))
+
+    def migration_plan(self, edges: np.ndarray):
+        """Rows of the sorted order that go to every rank: (send_counts [world] int64, posm, vel, ids views)."""
+        world = len(edges) - 1
+        if self.n == 0:
+            return np.zeros(world, np.int64), None
+        keys, posm, vel, ids = self._sorted()
+        inner = self.torch.tensor(edges[1:-1].astype(np.int32), dtype=self.torch.int32, device=self.device)
+        pos = self.torch.searchsorted(keys, inner).cpu().numpy().astype(np.int64)
+        bounds = np.concatenate([[0], pos, [self.n]])
+        return np.diff(bounds), (posm, vel, ids)
+
+    def adopt(self, posm, vel, ids):
+        self.posm, self.vel, self.ids = posm, vel, ids
+
+    # ---- local tree, domain description, export ----------------------------------------------
+    def build_local_tree(self):
         if self.n == 0:
             return
         st = self._stream()
+        self.eng.import_state(self.posm, self.vel, self.ids, self.n, st)
         for ph in (PHASE.KEYS, PHASE.SORT, PHASE.BUILD, PHASE.COM):
             self.eng.run_phase(ph, st)
 
+    def domain_boxes(self, k_lo: int, k_hi: int) -> np.ndarray:
+        """[MAX_BOXES, 6] tight body AABBs of the octree-aligned key intervals of [k_lo, k_hi)."""
+        if self.n == 0:
+            return np.tile(EMPTY_BOX, (MAX_BOXES, 1))
+        boxes, counts = self.eng.let_domain_boxes(domain_cuts(k_lo, k_hi))
+        assert int(counts.sum()) == self.n, "own bodies outside the own key range"
+        return boxes
+
     def export(self, boxes_lohi: np.ndarray, me: int) -> np.ndarray:
-        boxes = np.asarray(boxes_lohi, f32).reshape(-1, 6).copy()
-        boxes[me] = [1, 1, 1, -1, -1, -1]                    # nothing is exported to oneself
+        """boxes_lohi: [world, K, 6].  Returns the number of points emitted for every peer."""
+        boxes = np.asarray(boxes_lohi, f32).copy()
+        boxes[me] = EMPTY_BOX                                   # nothing is exported to oneself
         if self.n == 0:
             return np.zeros(len(boxes), np.int32)
         return self.eng.let_export(boxes, self.out, self.cap, self._stream())
@@ -96,15 +230,28 @@ class LetRank:
         vel_u = torch.cat([self.vel, torch.zeros((n_imp, 4), dtype=torch.float32, device=self.device)]) if n_imp else self.vel
         ids_u = torch.cat([self.ids, torch.full((n_imp,), -1, dtype=torch.int32, device=self.device)]) if n_imp else self.ids
         st = self._stream()
+        ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+        ev[0].record()
         self.eng.import_state(posm_u.contiguous(), vel_u.contiguous(), ids_u.contiguous(), nu, st)
         self.eng.simulation_step(1, st)
+        ev[1].record()
+        self._ev = (ev[0], ev[1], nl)
         ptr = self.eng.state_ptrs()
         pu = torch.as_tensor(_DevView(ptr["posm"], (nu, 4), "<f4"), device=self.device)
         vu = torch.as_tensor(_DevView(ptr["vel"], (nu, 4), "<f4"), device=self.device)
         iu = torch.as_tensor(_DevView(ptr["ids"], (nu,), "<i4"), device=self.device)
+        au = torch.as_tensor(_DevView(self.eng.sorted_ptrs()["acc"], (nu, 4), "<f4"), device=self.device)
         keep = iu >= 0
         self.posm, self.vel, self.ids = pu[keep].clone(), vu[keep].clone(), iu[keep].clone()
+        self.vel[:, 3] = au[keep, 3]                            # the work each body's chunk cost, for the next election
         self.last = {"n_union": nu, "n_import": n_imp}
+
+    def last_union_ms(self) -> float:
+        """Device time of the last union step (import + ordinary step); synchronises on its end event."""
+        if self._ev is None:
+            return 0.0
+        self._ev[1].synchronize()
+        return float(self._ev[0].elapsed_time(self._ev[1]))
 
     def last_accelerations(self):
         """(ids, acc[k,3]) of the own bodies for the step just taken (host arrays; test/diagnostic path)."""
@@ -117,28 +264,52 @@ class LetRank:
         self.eng.close()
 
 
-def let_step_emulated(ranks):
-    """One LET step of several LetRank objects living on one device; the all-to-all is a list shuffle."""
-    boxes = np.stack([r.local_box() for r in ranks])
-    cube = global_cube(boxes)
-    for r in ranks:
-        r.build_local_tree(cube)
+def let_step_emulated(ranks, rebalance: bool = True):
+    """One LET step of several LetRank objects living on one device; the all-to-alls are list shuffles.
+    Returns (export counts per rank, key-range edges)."""
+    torch = ranks[0].torch
+    world = len(ranks)
+    cube = global_cube(np.stack([r.local_box() for r in ranks]))
+    sw = [r.sort_own(cube, rebalance) for r in ranks]
+    edges = elect_splitters(np.stack([x[0] for x in sw]), np.array([x[1] for x in sw]))
+    plans = [r.migration_plan(edges) for r in ranks]
+    for dst, r in enumerate(ranks):
+        parts = [[], [], []]
+        for src in range(world):
+            sc, views = plans[src]
+            if views is None or sc[dst] == 0:
+                continue
+            a = int(sc[:dst].sum())
+            for k in range(3):
+                parts[k].append(views[k][a:a + int(sc[dst])].clone())
+        if parts[0]:
+            new = [torch.cat(p) for p in parts]
+        else:
+            new = [torch.empty((0, 4), dtype=torch.float32, device=r.device), torch.empty((0, 4), dtype=torch.float32, device=r.device),
+                   torch.empty((0,), dtype=torch.int32, device=r.device)]
+        r._new = new
+    for r in ranks:                                            # adopt only after every rank's runs were copied out
+        r.adopt(*r._new)
+        del r._new
+        r.build_local_tree()
+    boxes = compact_boxes(np.stack([r.domain_boxes(int(edges[i]), int(edges[i + 1])) for i, r in enumerate(ranks)]))
     counts = [r.export(boxes, i) for i, r in enumerate(ranks)]
-    sent = [[r.out[p, : int(counts[i][p])].clone() for p in range(len(ranks))] for i, r in enumerate(ranks)]
+    sent = [[r.out[p, : int(counts[i][p])].clone() for p in range(world)] for i, r in enumerate(ranks)]
     for i, r in enumerate(ranks):
-        r.union_step([sent[s][i] for s in range(len(ranks)) if s != i])
-    return counts
+        r.union_step([sent[s][i] for s in range(world) if s != i])
+    return counts, edges
 
 
 class LetSimulation:
     """torch.distributed driver: one process per GPU, NCCL all-gather of boxes and all-to-all of point lists."""
 
     def __init__(self, bh, local_soa, local_ids, rank: int, world: int, local: int, dist, capacity: int,
-                 cap_per_peer: int, **params):
+                 cap_per_peer: int, rebalance: bool = True, **params):
         import torch
 
         self.torch, self.dist, self.rankno, self.world = torch, dist, rank, world
         self.device = torch.device(f"cuda:{local}")
+        self.rebalance = rebalance
         px, py, pz, vx, vy, vz, m = local_soa
         n = len(px)
         posm = torch.from_numpy(np.stack([px, py, pz, m], 1).astype(f32)).to(self.device)
@@ -146,25 +317,76 @@ class LetSimulation:
         ids = torch.from_numpy(np.asarray(local_ids, np.int32)).to(self.device)
         self.rank = LetRank(bh, torch, self.device, posm, vel, ids, capacity, cap_per_peer, world, **params)
         self.stats = {}
+        self.trace = {} if os.environ.get("BH_LET_TRACE") else None   # phase -> wall ms of the last step (syncs!)
+
+    def _mark(self, name, t0):
+        if self.trace is None:
+            return t0
+        self.torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        self.trace[name] = self.trace.get(name, 0.0) + 1e3 * (t1 - t0)
+        return t1
+
+    def _all_to_all_rows(self, send, sc, rc, shape_tail, dtype):
+        recv = self.torch.empty((int(sum(rc)),) + shape_tail, dtype=dtype, device=self.device)
+        if send is None:
+            send = self.torch.empty((0,) + shape_tail, dtype=dtype, device=self.device)
+        self.dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=rc, input_split_sizes=sc)
+        return recv
 
     def step(self, nsteps: int = 1):
-        torch, dist, w = self.torch, self.dist, self.world
+        torch, dist, w, me = self.torch, self.dist, self.world, self.rankno
         for _ in range(nsteps):
+            if self.trace is not None:
+                self.trace.clear()
+                torch.cuda.synchronize()
+            t = time.perf_counter()
+            # global cube
             box = torch.from_numpy(self.rank.local_box()).to(self.device)
             boxes = torch.empty((w, 6), dtype=torch.float32, device=self.device)
             dist.all_gather_into_tensor(boxes, box)
-            boxes_h = boxes.cpu().numpy()
-            self.rank.build_local_tree(global_cube(boxes_h))
-            counts = self.rank.export(boxes_h, self.rankno)
+            cube = global_cube(boxes.cpu().numpy())
+            t = self._mark("cube", t)
+            # splitter election: every rank's work-spaced key sample + its total work
+            sample, work = self.rank.sort_own(cube, self.rebalance)
+            mine = torch.from_numpy(np.concatenate([sample.astype(np.float64), [work]])).to(self.device)
+            pooled = torch.empty((w, SAMPLE + 1), dtype=torch.float64, device=self.device)
+            dist.all_gather_into_tensor(pooled, mine)
+            pooled = pooled.cpu().numpy()
+            edges = elect_splitters(pooled[:, :SAMPLE].astype(np.int64), pooled[:, SAMPLE])
+            t = self._mark("sort+elect", t)
+            # migration: runs of the sorted order
+            sc_np, views = self.rank.migration_plan(edges)
+            send_counts = torch.from_numpy(sc_np).to(self.device)
+            recv_counts = torch.empty_like(send_counts)
+            dist.all_to_all_single(recv_counts, send_counts)
+            sc, rc = sc_np.tolist(), recv_counts.cpu().numpy().tolist()
+            migrated = int(sum(sc)) - int(sc[me])
+            v = views if views is not None else (None, None, None)
+            new_posm = self._all_to_all_rows(v[0], sc, rc, (4,), torch.float32)
+            new_vel = self._all_to_all_rows(v[1], sc, rc, (4,), torch.float32)
+            new_ids = self._all_to_all_rows(v[2], sc, rc, (), torch.int32)
+            self.rank.adopt(new_posm, new_vel, new_ids)
+            t = self._mark("migrate", t)
+            # local tree, domain boxes, export
+            self.rank.build_local_tree()
+            t = self._mark("local tree", t)
+            dom = torch.from_numpy(self.rank.domain_boxes(int(edges[me]), int(edges[me + 1]))).to(self.device)
+            doms = torch.empty((w, MAX_BOXES, 6), dtype=torch.float32, device=self.device)
+            dist.all_gather_into_tensor(doms, dom)
+            t = self._mark("domain boxes", t)
+            counts = self.rank.export(compact_boxes(doms.cpu().numpy()), me)
+            t = self._mark("export walk", t)
             send_counts = torch.from_numpy(counts.astype(np.int64)).to(self.device)
             recv_counts = torch.empty_like(send_counts)
             dist.all_to_all_single(recv_counts, send_counts)
             sc, rc = counts.astype(np.int64).tolist(), recv_counts.cpu().numpy().tolist()
-            send = torch.cat([self.rank.out[p, : sc[p]] for p in range(w)]) if sum(sc) else torch.empty((0, 4), dtype=torch.float32, device=self.device)
-            recv = torch.empty((int(sum(rc)), 4), dtype=torch.float32, device=self.device)
-            dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=rc, input_split_sizes=sc)
+            send = torch.cat([self.rank.out[p, : sc[p]] for p in range(w)]) if sum(sc) else None
+            recv = self._all_to_all_rows(send, sc, rc, (4,), torch.float32)
+            t = self._mark("exchange", t)
             self.rank.union_step([recv])
-            self.stats = {"exported": int(sum(sc)), "imported": int(sum(rc)), "n_local": self.rank.n}
+            t = self._mark("union step", t)
+            self.stats = {"exported": int(sum(sc)), "imported": int(sum(rc)), "n_local": self.rank.n, "migrated_out": migrated}
 
     def close(self):
         self.rank.close()
@@ -209,8 +431,10 @@ def run_let_bench(args, w, bh, dist, rank, world, local):
     del soa
     nl = len(sel)
     cap_peer = max(1 << 20, int(0.15 * n / world))
+    # work-balanced key ranges may hold up to ~2x the mean body count; imports come on top
     sim = LetSimulation(bh, local_soa, sel.astype(np.int32), rank, world, local, dist,
-                        capacity=int(1.5 * n / world) + (world - 1) * cap_peer // 2 + 4096, cap_per_peer=cap_peer)
+                        capacity=int(2.2 * n / world) + (world - 1) * cap_peer // 2 + 4096, cap_per_peer=cap_peer,
+                        rebalance=not getattr(args, "let_no_rebalance", False))
     dev = sim.device
 
     def barrier():
@@ -237,9 +461,9 @@ def run_let_bench(args, w, bh, dist, rank, world, local):
     inter = torch.tensor([float(eng.stat(bh.STAT.INTERACTIONS_CELL) + eng.stat(bh.STAT.INTERACTIONS_BODY))], device=dev,
                          dtype=torch.float64)
     dist.all_reduce(inter)
-    st = torch.tensor([float(sim.stats["exported"]), float(sim.stats["imported"]), float(sim.stats["n_local"])], device=dev,
-                      dtype=torch.float64)
-    stats_all = torch.empty((world, 3), dtype=torch.float64, device=dev)
+    st = torch.tensor([float(sim.stats["exported"]), float(sim.stats["imported"]), float(sim.stats["n_local"]),
+                       float(sim.stats["migrated_out"]), sim.rank.last_union_ms()], device=dev, dtype=torch.float64)
+    stats_all = torch.empty((world, 5), dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(stats_all, st)
     sim.close()
     total_ms = float(ms.item())
@@ -249,11 +473,14 @@ def run_let_bench(args, w, bh, dist, rank, world, local):
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["desc"], "n_bodies": n, "theta": 0.5, "G": 0.5, "dt": 0.02,
                    "softening": 50.0, "max_speed": 500.0, "group": 32,
-                   "parallelism": f"locally-essential-tree x{world}: sampled key-range ownership, per-peer export walk, "
-                                  "NCCL all-to-all of point masses, ordinary step on own + imported bodies",
+                   "parallelism": f"locally-essential-tree x{world}: work-weighted sampled key splitters, body migration, "
+                                  "per-peer export walk against octree-aligned domain boxes, NCCL all-to-all of point "
+                                  "masses, ordinary step on own + imported bodies",
                    "l2": "state far larger than L2; no flush between steps"},
         "interactions_per_body": float(inter.item()) / n, "interactions_per_s": float(inter.item()) * args.steps / (total_ms * 1e-3),
-        "let_points_exported_imported_local_per_rank": [[int(x) for x in row] for row in stats_all.tolist()],
+        "let_exported_imported_local_migrated_per_rank": [[int(x) for x in row[:4]] for row in stats_all.tolist()],
+        "union_step_ms_per_rank": [round(row[4], 3) for row in stats_all.tolist()],
+        "trace_ms_rank0_last_step": {k: round(v, 3) for k, v in sim.trace.items()} if sim.trace is not None else None,
         "wall_s_timed_loop": wall, "e2e": None, "gpu_launches": None, "clocks": ck,
     }
     dist.destroy_process_group()

@@ -213,3 +213,67 @@ def cell_tuples(meta, keys_sorted):
         prefix = int(keys_sorted[first]) >> (30 - 3 * L) if L > 0 else 0
         out.add((L, prefix, int(first), int(count)))
     return out
+
+
+# ---- locally-essential-tree export (csrc/bh_let.cu) -----------------------------------------------------
+# The reference has no multi-GPU path, so there is nothing of its own to restate here; this is the CPU
+# statement of OUR export rule, used only to check the kernel: walk the tree from the root; a cell whose
+# width passes the reference's acceptance test (bench:207-208, squared) at the nearest point of the peer's
+# boxes is emitted as {com, mass}; otherwise it is opened; loose bodies and the bodies of rejected buckets are
+# emitted as they are.  Same float32 operation order as the kernel (the hull shortcut included).
+def _box_centre_half(lohi):
+    lohi = np.asarray(lohi, np.float32)
+    return ((lohi[..., :3] + lohi[..., 3:]) * np.float32(0.5)).astype(np.float32), \
+           ((lohi[..., 3:] - lohi[..., :3]) * np.float32(0.5)).astype(np.float32)
+
+
+def _fma32(a, b, c):
+    return np.float32(np.float64(a) * np.float64(b) + np.float64(c))
+
+
+def _box_dist2(c, h, p):
+    d = np.maximum(np.float32(0), (np.abs((p[:3] - c).astype(np.float32)) - h).astype(np.float32)).astype(np.float32)
+    return _fma32(d[2], d[2], _fma32(d[1], d[1], np.float32(d[0] * d[0])))
+
+
+def let_export_points(meta, child, com, posm_sorted, root, boxes_lohi, root_w, theta=THETA, soft=SOFT):
+    """Points (k,4 float32, order unspecified) the export walk emits for ONE peer described by boxes_lohi [K,6]."""
+    boxes = np.asarray(boxes_lohi, np.float32).reshape(-1, 6)
+    boxes = boxes[boxes[:, 0] <= boxes[:, 3]]
+    if len(boxes) == 0:
+        return np.zeros((0, 4), np.float32)
+    bc, bh_ = _box_centre_half(boxes)
+    hull = np.concatenate([boxes[:, :3].min(0), boxes[:, 3:].max(0)]).astype(np.float32)
+    hc, hh = _box_centre_half(hull)
+    theta2, soft = np.float32(np.float32(theta) * np.float32(theta)), np.float32(soft)
+    w2_root = np.float32(np.float32(root_w) * np.float32(root_w))
+
+    def accepts(p, level):
+        w2 = np.float32(w2_root * np.float32(4.0 ** -level))
+        if w2 < np.float32(theta2 * np.float32(_box_dist2(hc, hh, p) + soft)):
+            return True
+        d2 = min(_box_dist2(bc[k], bh_[k], p) for k in range(len(boxes)))
+        return bool(w2 < np.float32(theta2 * np.float32(d2 + soft)))
+
+    out = []
+
+    def visit(cell):
+        first, count, lvflag, _ = (int(v) for v in meta[cell])
+        if accepts(com[cell], lvflag & 0xFF):
+            out.append(com[cell])
+        elif (lvflag >> 8) & 1:
+            out.extend(posm_sorted[first:first + count])
+        else:
+            for c in child[cell]:
+                c = int(c)
+                if c == 0x7F7F7F7F:
+                    continue
+                if c < 0:
+                    out.append(posm_sorted[c & 0x7FFFFFFF])
+                else:
+                    stack.append(c)
+
+    stack = [int(root)]
+    while stack:
+        visit(stack.pop())
+    return np.array(out, np.float32).reshape(-1, 4)

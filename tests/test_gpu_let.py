@@ -41,8 +41,9 @@ def test_let_forces_match_the_replicated_engine_and_the_direct_sum(bh, kind, n, 
     posm_all, _, _ = O.soa_to_internal(soa)
     total_mass = soa[6].astype(np.float64).sum()
     ranks = make_ranks(bh, soa, world)
-    local_mass = [float(r.posm[:, 3].double().sum().item()) for r in ranks]
-    counts = let_step_emulated(ranks)
+    counts, edges = let_step_emulated(ranks)
+    assert edges[0] == 0 and edges[-1] == 1 << 30 and (np.diff(edges) >= 0).all()
+    local_mass = [float(r.posm[:, 3].double().sum().item()) for r in ranks]   # ownership after the migration
     acc = np.zeros((n, 3), np.float64)
     seen = np.zeros(n, int)
     for i, r in enumerate(ranks):
@@ -81,6 +82,7 @@ def test_let_multi_step_tracks_the_replicated_run(bh):
     ranks = make_ranks(bh, soa, world)
     for _ in range(steps):
         let_step_emulated(ranks)
+    assert sum(r.n for r in ranks) == n
     pos = np.zeros((n, 3), f)
     for r in ranks:
         pos[r.ids.cpu().numpy()] = r.posm[:, :3].cpu().numpy()
@@ -91,6 +93,128 @@ def test_let_multi_step_tracks_the_replicated_run(bh):
         ref.simulation_step(steps)
         want = np.stack(ref.read_soa()[:3], 1)
     assert O.rel_rms(pos, want) < 1e-5            # same physics, forces differ at the multipole-error level
+
+
+def test_migration_returns_strays_and_balances_the_work(bh):
+    """Bodies handed to the WRONG owners at start-up end up with the owner of their key after one step, and
+    the cost-weighted splitters move work towards the cheaper ranks."""
+    import torch
+
+    from nbody_barnes_hut_cuda_b200.let import LetRank, let_step_emulated
+
+    n, world = 40000, 4
+    soa = bh.ic_plummer(n, 9, 200.0, 10.0, 4.5, 0.5)
+    dev = torch.device("cuda:0")
+    rng = np.random.default_rng(1)
+    owner = rng.integers(0, world, n)                      # ownership unrelated to position
+    ranks = []
+    for r in range(world):
+        sel = np.nonzero(owner == r)[0]
+        posm = torch.from_numpy(np.stack([soa[0][sel], soa[1][sel], soa[2][sel], soa[6][sel]], 1).astype(f)).to(dev)
+        vel = torch.from_numpy(np.stack([soa[3][sel], soa[4][sel], soa[5][sel], np.zeros(len(sel), f)], 1).astype(f)).to(dev)
+        ranks.append(LetRank(bh, torch, dev, posm, vel, torch.from_numpy(sel.astype(np.int32)).to(dev), capacity=2 * n,
+                             cap_per_peer=n, npeers=world))
+    _, edges = let_step_emulated(ranks)
+    b = O.bounds(*soa[:3])
+    keys, _ = O.morton_keys(*soa[:3], b)
+    seen = np.zeros(n, int)
+    for i, r in enumerate(ranks):
+        ids = r.ids.cpu().numpy()
+        seen[ids] += 1
+        k = keys[ids].astype(np.int64)
+        assert ((k >= edges[i]) & (k < edges[i + 1])).all()   # every body sits with the owner of its key
+    assert (seen == 1).all()
+    counts0 = np.array([r.n for r in ranks])
+    assert counts0.max() - counts0.min() < 0.05 * n / world + 64   # first election: equal counts (unit costs)
+    for r in ranks:
+        r.eng.check_device_error()
+    # every body now carries the work of its chunk; tripling it on rank 1 shrinks that rank's next key range
+    for r in ranks:
+        assert float(r.vel[:, 3].min().item()) > 0
+    ranks[1].vel[:, 3] *= 3.0
+    let_step_emulated(ranks)
+    assert ranks[1].n < 0.7 * counts0[1]
+    assert sum(r.n for r in ranks) == n
+    for r in ranks:
+        r.eng.check_device_error()
+        r.close()
+
+
+@pytest.mark.parametrize("kind,n", [("disk", 20000), ("plummer", 12000)])
+def test_export_walk_emits_exactly_the_oracle_point_set(bh, kind, n):
+    """bh_let_export against the CPU statement of the export rule (oracle_lib.let_export_points) on the SAME
+    tree: identical multisets of float4 points for a near, a touching and a far peer domain."""
+    import torch
+
+    from nbody_barnes_hut_cuda_b200.engine import PHASE
+    from nbody_barnes_hut_cuda_b200.let import EMPTY_BOX
+
+    soa = bh.ic_refdisk(n, 3) if kind == "disk" else bh.ic_plummer(n, 3, 200.0, 10.0, 4.5, 0.5)
+    with bh.BHEngine(n) as eng:
+        eng.load_soa(*soa)
+        for ph in (PHASE.KEYS, PHASE.SORT, PHASE.BUILD, PHASE.COM):
+            eng.run_phase(ph)
+        b = eng.debug_get(bh.DBG.BOUNDS)
+        meta, child, com = eng.debug_get(bh.DBG.CELL_META), eng.debug_get(bh.DBG.CELL_CHILD), eng.debug_get(bh.DBG.CELL_COM)
+        ps = eng.debug_get(bh.DBG.POSM_SORTED)
+        root = eng.stat(bh.STAT.ROOT)
+        lo, hi = ps[:, :3].min(0), ps[:, :3].max(0)
+        ext = hi - lo
+        peers = np.tile(EMPTY_BOX, (4, 3, 1))
+        peers[0, 0] = np.concatenate([hi + 0.02 * ext, hi + 0.3 * ext])                  # just outside one corner
+        peers[0, 2] = np.concatenate([lo - 0.5 * ext, lo - 0.1 * ext])                   # second box of the same peer
+        peers[1, 1] = np.concatenate([lo + 0.4 * ext, lo + 0.6 * ext])                   # inside the body cloud
+        peers[2, 0] = np.concatenate([hi + 40 * ext, hi + 41 * ext])                     # far away: a handful of points
+        out = torch.empty((4, n, 4), dtype=torch.float32, device="cuda")
+        counts = eng.let_export(peers, out, n)
+        eng.check_device_error()
+        meta_l = meta.copy()
+        meta_l[:, 2] = meta[:, 2] & 0x1FF                                                 # level | bucket<<8 (drop the slot bits)
+        assert counts[3] == 0
+        for p in range(3):
+            want = O.let_export_points(meta_l, child.reshape(-1, 8), com, ps, root, peers[p], float(b[3] - b[0]))
+            got = out[p, : int(counts[p])].cpu().numpy()
+            assert len(got) == len(want)
+            assert sorted(map(bytes, got.view(np.uint8).reshape(len(got), 16))) == sorted(map(bytes, want.view(np.uint8).reshape(len(want), 16)))
+        assert counts[2] < counts[0] < counts[1]
+
+
+def test_ghosts_attract_but_are_not_traversed(bh):
+    """Bodies with id < 0 (imported point masses) act as sources only: the real bodies feel them (direct-sum
+    check over ALL points), and skipping the sparse all-ghost groups saves most of their traversal work."""
+    import torch
+
+    n, k = 30000, 3000
+    soa = bh.ic_refdisk(n, 11)
+    rng = np.random.default_rng(2)
+    ghosts = np.concatenate([rng.uniform(-20000, 20000, (k, 3)), rng.uniform(50, 500, (k, 1))], 1).astype(f)   # sparse, heavy, far
+    posm = np.concatenate([np.stack([soa[0], soa[1], soa[2], soa[6]], 1).astype(f), ghosts])
+    vel = np.zeros((n + k, 4), f)
+    dev = torch.device("cuda:0")
+    out = {}
+    for name, ids in (("ghost", np.concatenate([np.arange(n), np.full(k, -1)])), ("real", np.arange(n + k))):
+        with bh.BHEngine(n + k) as eng:
+            eng.import_state(torch.from_numpy(posm).to(dev), torch.from_numpy(vel).to(dev),
+                             torch.from_numpy(ids.astype(np.int32)).to(dev), n + k)
+            eng.simulation_step(1)
+            eng.check_device_error()
+            ids_s, acc = eng.debug_get(bh.DBG.IDS_SORTED), eng.debug_get(bh.DBG.ACC)
+            ps = eng.debug_get(bh.DBG.POSM_SORTED)
+            inter = eng.stat(bh.STAT.INTERACTIONS_CELL) + eng.stat(bh.STAT.INTERACTIONS_BODY)
+        out[name] = (ids_s, acc, ps, inter)
+    ids_s, acc, ps, inter_g = out["ghost"]
+    real = np.nonzero(ids_s >= 0)[0]
+    sample = real[:: 40].astype(np.int32)
+    direct = O.direct_sum(ps, sample)
+    assert (acc[real, 3] > 0).all()                          # every real body carries its chunk's work
+    a_real = np.zeros((n + k, 3)); a_real[out["real"][0]] = out["real"][1][:, :3]
+    a_gh = np.zeros((n + k, 3)); a_gh[ids_s[real]] = acc[real, :3]
+    a_dir = np.zeros((n + k, 3)); a_dir[ids_s[sample]] = direct
+    who = ids_s[sample]
+    e_ghost, e_real = O.rel_rms(a_gh[who], a_dir[who]), O.rel_rms(a_real[who], a_dir[who])
+    assert e_ghost < max(1.5 * e_real, 3e-3)                 # same multipole-error class with and without the ghost rule
+    assert O.rel_rms(a_gh[:n], a_real[:n]) < 3.0 * max(e_real, 1e-3)
+    assert inter_g < 0.8 * out["real"][3]                    # the ghosts' own traversals are gone
 
 
 def test_global_cube_matches_the_reference_bounds(bh):

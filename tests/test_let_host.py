@@ -1,0 +1,152 @@
+"""Host logic of the locally-essential-tree mode on CPU: octree-aligned domain cuts, the work-weighted splitter
+election, box compaction, the export-walk oracle on a hand-made tree, and a world_size-2 gloo run of the
+election + migration exchange (keys only — the engine itself has no CPU path)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_domain_cuts_are_octree_aligned():
+    from nbody_barnes_hut_cuda_b200.let import KEY_END, MAX_BOXES, domain_cuts
+
+    rng = np.random.default_rng(0)
+    for t in range(400):
+        a, b = sorted(rng.integers(0, KEY_END + 1, 2).tolist())
+        if t % 3 == 0:
+            b = min(KEY_END, a + int(rng.integers(0, 5000)))
+        c = domain_cuts(a, b).astype(np.int64)
+        assert len(c) == MAX_BOXES + 1 and c[0] == a and c[-1] == b and (np.diff(c) >= 0).all()
+        u = np.unique(c)
+        for lo_, hi_ in zip(u[:-1], u[1:]):                  # every interval lies inside ONE cell of its size class
+            size = 1
+            while size < hi_ - lo_:
+                size *= 8
+            assert lo_ // size == (hi_ - 1) // size
+    full = np.unique(domain_cuts(0, KEY_END))
+    assert len(full) == 9 and (np.diff(full.astype(np.int64)) == 1 << 27).all()   # the 8 octants
+    assert len(np.unique(domain_cuts(77, 77))) == 1                               # empty range
+
+
+def _work_spaced_sample(keys, work, m):
+    cum = np.cumsum(work)
+    return keys[np.minimum(np.searchsorted(cum, (np.arange(m) + 0.5) * cum[-1] / m), len(keys) - 1)]
+
+
+def test_splitter_election_balances_weighted_work():
+    from nbody_barnes_hut_cuda_b200.let import KEY_END, SAMPLE, elect_splitters
+
+    rng = np.random.default_rng(3)
+    world = 4
+    allkeys = np.sort(rng.integers(0, KEY_END, 400_000))
+    owned = np.array_split(allkeys, world)                    # current ownership: equal-count key ranges
+    ones = [np.ones(len(o)) for o in owned]
+    samples = np.stack([_work_spaced_sample(o, w, SAMPLE) for o, w in zip(owned, ones)])
+    e = elect_splitters(samples, np.array([w.sum() for w in ones]))
+    assert e[0] == 0 and e[-1] == KEY_END
+    got = np.diff(np.searchsorted(allkeys, e))
+    assert abs(got - len(allkeys) / world).max() < 0.01 * len(allkeys)            # unit work: equal counts
+    # work that varies inside and between the ranks (rank 1 is 3x as expensive, with a hot spot)
+    work = [np.ones(len(o)) for o in owned]
+    work[1] *= 3.0
+    work[1][1000:3000] *= 10.0
+    samples = np.stack([_work_spaced_sample(o, w, SAMPLE) for o, w in zip(owned, work)])
+    e2 = elect_splitters(samples, np.array([w.sum() for w in work]))
+    allwork = np.concatenate(work)
+    cum = np.concatenate([[0], np.cumsum(allwork)])
+    per_rank = np.diff(cum[np.searchsorted(allkeys, e2)])
+    assert abs(per_rank - allwork.sum() / world).max() < 0.01 * allwork.sum()      # equal work afterwards
+    # ranks without bodies are ignored, edges stay monotone
+    e3 = elect_splitters(samples, np.array([100.0, 0, 100, 100]))
+    assert (np.diff(e3) >= 0).all() and e3[-1] == KEY_END
+    assert (elect_splitters(samples, np.zeros(world)) == [0] + [KEY_END] * world).all()
+
+
+def test_compact_boxes_keeps_used_boxes_in_front():
+    from nbody_barnes_hut_cuda_b200.let import EMPTY_BOX, compact_boxes
+
+    b = np.tile(EMPTY_BOX, (3, 10, 1))
+    b[0, 4] = [0, 0, 0, 1, 1, 1]
+    b[0, 7] = [2, 2, 2, 3, 3, 3]
+    b[2, 9] = [5, 5, 5, 6, 6, 6]
+    c = compact_boxes(b)
+    assert c.shape == (3, 2, 6)
+    assert (c[0, 0] == b[0, 4]).all() and (c[0, 1] == b[0, 7]).all() and (c[2, 0] == b[2, 9]).all()
+    assert c[1, 0, 0] > c[1, 0, 3] and c[2, 1, 0] > c[2, 1, 3]
+
+
+def test_export_oracle_on_a_two_level_tree(orc):
+    """Root with one loose body and one child cell of two bodies.  A far box receives one point (the root), a
+    box at the child's distance scale receives the loose body + the child's monopole, a box on top of the
+    child receives the three bodies."""
+    posm = np.array([[0, 0, 0, 1], [100, 100, 100, 2], [101, 100, 100, 4]], np.float32)
+    meta = np.array([[0, 3, 0, -1], [1, 2, 6, 0]], np.int32)                      # root level 0, child level 6
+    E = 0x7F7F7F7F
+    child = np.array([[-2147483648 | 0, 1, E, E, E, E, E, E], [-2147483648 | 1, -2147483648 | 2, E, E, E, E, E, E]]).astype(np.int64).astype(np.int32)
+    com = np.array([[(200 + 404) / 7.0, 600 / 7.0, 600 / 7.0, 7], [(200 + 404) / 6.0, 100, 100, 6]], np.float32)
+    root_w = 1024.0                                                                 # child width 16
+
+    def pts(box):
+        p = orc.let_export_points(meta, child, com, posm, 0, np.array([box], np.float32), root_w)
+        return sorted(map(tuple, p.tolist()))
+
+    far = pts([1e5, 0, 0, 1e5 + 1, 1, 1])
+    assert far == [tuple(com[0].tolist())]
+    mid = pts([300, 100, 100, 301, 101, 101])                                       # 200 away: root opens, child (16 < 0.5*200) accepted
+    assert mid == sorted([tuple(posm[0].tolist()), tuple(com[1].tolist())])
+    near = pts([100, 100, 100, 101, 101, 101])
+    assert near == sorted(map(tuple, posm.tolist()))
+    assert len(orc.let_export_points(meta, child, com, posm, 0, np.array([[1, 1, 1, -1, -1, -1]], np.float32), root_w)) == 0
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    import torch
+    import torch.distributed as dist
+
+    from nbody_barnes_hut_cuda_b200.let import KEY_END, SAMPLE, elect_splitters
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(100 + rank)
+    n = 5000 + 3000 * rank                                     # unequal ranks, overlapping key ranges
+    keys = np.sort(rng.integers(0, KEY_END // (1 + rank), n))
+    sample = keys[np.linspace(0, n - 1, SAMPLE).astype(int)]
+    mine = torch.from_numpy(np.concatenate([sample.astype(np.float64), [float(n)]]))
+    pooled = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(pooled, mine)
+    pooled = torch.stack(pooled).numpy()
+    edges = elect_splitters(pooled[:, :SAMPLE].astype(np.int64), pooled[:, SAMPLE])
+    pos = np.searchsorted(keys, edges[1:-1])
+    sc = np.diff(np.concatenate([[0], pos, [n]])).astype(np.int64)
+    rc_t = torch.empty(world, dtype=torch.int64)
+    dist.all_to_all_single(rc_t, torch.from_numpy(sc))
+    rc = rc_t.numpy()
+    recv = torch.empty(int(rc.sum()), dtype=torch.int64)
+    dist.all_to_all_single(recv, torch.from_numpy(keys.astype(np.int64)), output_split_sizes=rc.tolist(), input_split_sizes=sc.tolist())
+    got = recv.numpy()
+    q.put((rank, edges.tolist(), len(got), bool(((got >= edges[rank]) & (got < edges[rank + 1])).all())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_election_and_migration_over_gloo():
+    import torch.multiprocessing as mp
+
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] == res[1][1]                              # both ranks elected the same edges
+    assert res[0][2] + res[1][2] == 5000 + 8000                # no body lost or duplicated
+    assert res[0][3] and res[1][3]                             # every received key lies in the receiver's range
+    assert abs(res[0][2] - res[1][2]) < 0.03 * 13000           # equal counts at unit cost
