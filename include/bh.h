@@ -232,6 +232,11 @@ int  bh_sorted_ptrs(bh_ctx* ctx, void** keys, void** posm, void** vel, void** id
 int  bh_let_export(bh_ctx* ctx, const float* boxes_lohi, int npeers, int K, void* out, int64_t cap_per_peer,
                    int32_t* counts, void* stream);
 
+/* After a step on own bodies + ghosts: copy the bodies with id >= 0 of the current state, in their (Morton)
+ * order, to the DEVICE arrays posm_out / vel_out (float4) / ids_out, with vel.w = the work of the body's
+ * traversal chunk in that step (see BH_DBG_ACC).  *n_real = bodies written.  Synchronises `stream`.      */
+int  bh_export_real(bh_ctx* ctx, void* posm_out, void* vel_out, int32_t* ids_out, int64_t* n_real, void* stream);
+
 /* ---- standalone pieces -------------------------------------------------- */
 /* Stable LSD radix sort of (u32 key, u32 value) pairs over bits
  * [begin_bit,end_bit) — replaces thrust::sort_by_key (bench:262-264).

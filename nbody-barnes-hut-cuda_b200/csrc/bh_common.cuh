@@ -124,4 +124,6 @@ int bh_let_export_launch(const int4* cell_meta, const int32_t* cell_child, const
                          const float* hull_dev, int npeers, int K, float4* out, unsigned int* out_count, long long cap, int2* queue, unsigned int* qcounts,
                          long long qcap, float theta, float softening, float root_w, cudaStream_t st);
 int bh_domain_boxes_launch(const uint32_t* keys, const float4* posm, long long n, const uint32_t* cuts_dev, int K,
-                           float* out_dev, int* counts_dev, cudaStream_t st);
+                           float* out_dev, int* counts_dev, unsigned int* enc_dev, cudaStream_t st);
+int bh_compact_real_launch(const float4* posm, const float4* vel, const int32_t* ids, const float4* acc, int64_t n,
+                           int32_t* tile_scratch, float4* posm_out, float4* vel_out, int32_t* ids_out, cudaStream_t st);

@@ -400,8 +400,9 @@ int bh_let_domain_boxes(bh_ctx* c, const uint32_t* cuts, int K, float* lohi, int
     // scratch: boxes at the front of let_boxes, cuts and counts behind them (the export call rewrites all of it)
     uint32_t* d_cuts = (uint32_t*)(c->let_boxes + (size_t)6 * BH_LET_MAX_BOXES);
     int* d_counts = (int*)(d_cuts + BH_LET_MAX_BOXES + 1);
+    unsigned int* d_enc = (unsigned int*)(d_counts + BH_LET_MAX_BOXES);
     BH_CUDA_TRY(cudaMemcpy(d_cuts, cuts, sizeof(uint32_t) * (K + 1), cudaMemcpyHostToDevice));
-    e = bh_domain_boxes_launch(c->keys0, c->posm_s, c->n, d_cuts, K, c->let_boxes, d_counts, 0);
+    e = bh_domain_boxes_launch(c->keys0, c->posm_s, c->n, d_cuts, K, c->let_boxes, d_counts, d_enc, 0);
     if (e) return e;
     BH_CUDA_TRY(cudaMemcpy(lohi, c->let_boxes, sizeof(float) * 6 * K, cudaMemcpyDeviceToHost));
     if (body_counts) BH_CUDA_TRY(cudaMemcpy(body_counts, d_counts, sizeof(int) * K, cudaMemcpyDeviceToHost));
@@ -417,6 +418,23 @@ int bh_sorted_ptrs(bh_ctx* c, void** keys, void** posm, void** vel, void** ids, 
     if (ids) *ids = c->ids_s;
     if (acc) *acc = c->acc;
     if (n) *n = c->n;
+    return 0;
+}
+
+int bh_export_real(bh_ctx* c, void* posm_out, void* vel_out, int32_t* ids_out, int64_t* n_real, void* stream) {
+    if (!c || !posm_out || !vel_out || !ids_out || !n_real) return BH_E_INVAL;
+    if (!c->have_state || !c->have_sorted) return BH_E_STATE;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    // tile_sums holds n_alloc/2048 + 16 ints: enough for the per-tile counts and the total
+    int e = bh_compact_real_launch(c->posm, c->vel, c->ids, c->acc, c->n, c->tile_sums, (float4*)posm_out, (float4*)vel_out,
+                                   ids_out, st);
+    if (e) return e;
+    const int tiles = (int)((c->n + 2047) / 2048);
+    int32_t total = 0;
+    BH_CUDA_TRY(cudaMemcpyAsync(&total, c->tile_sums + tiles, 4, cudaMemcpyDeviceToHost, st));
+    BH_CUDA_TRY(cudaStreamSynchronize(st));
+    *n_real = total;
     return 0;
 }
 

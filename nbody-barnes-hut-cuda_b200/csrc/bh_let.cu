@@ -146,15 +146,26 @@ __device__ __forceinline__ long long lower_bound_key(const uint32_t* __restrict_
     return lo;
 }
 
+constexpr int DOMAIN_SLICES = 48;   // blocks per interval: K x 48 blocks keep all SMs busy for K >= 4
+
+__global__ void domain_boxes_init_kernel(unsigned int* __restrict__ enc, int K) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 6 * K) enc[i] = (i % 6) < 3 ? 0xFFFFFFFFu : 0u;   // identity of min / max on the ordered images
+}
+
 __global__ void __launch_bounds__(LT) domain_boxes_kernel(const uint32_t* __restrict__ keys, const float4* __restrict__ posm,
                                                          long long n, const uint32_t* __restrict__ cuts, int K,
-                                                         float* __restrict__ out, int* __restrict__ counts) {
+                                                         unsigned int* __restrict__ enc, int* __restrict__ counts) {
     const int k = blockIdx.x;
     const long long b0 = lower_bound_key(keys, n, cuts[k]);
     // the last cut may be 2^30 = "past every key"
     const long long b1 = cuts[k + 1] >= (1u << BH_KEY_BITS) ? n : lower_bound_key(keys, n, cuts[k + 1]);
+    if (blockIdx.y == 0 && threadIdx.x == 0) counts[k] = (int)(b1 - b0);
+    const long long per = (b1 - b0 + gridDim.y - 1) / gridDim.y;
+    const long long s0 = b0 + per * blockIdx.y, s1 = min(b1, s0 + per);
+    if (s0 >= s1) return;
     float lo[3] = {3.0e38f, 3.0e38f, 3.0e38f}, hi[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
-    for (long long i = b0 + threadIdx.x; i < b1; i += LT) {
+    for (long long i = s0 + threadIdx.x; i < s1; i += LT) {
         const float4 p = __ldg(posm + i);
         lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
         hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
@@ -173,16 +184,26 @@ __global__ void __launch_bounds__(LT) domain_boxes_kernel(const uint32_t* __rest
     if (threadIdx.x < 6) {
         float v = s[threadIdx.x][0];
         for (int w = 1; w < LT / 32; ++w) v = threadIdx.x < 3 ? fminf(v, s[threadIdx.x][w]) : fmaxf(v, s[threadIdx.x][w]);
-        out[6 * k + threadIdx.x] = v;
+        if (threadIdx.x < 3) atomicMin(enc + 6 * k + threadIdx.x, bh_f2ord(v));
+        else atomicMax(enc + 6 * k + threadIdx.x, bh_f2ord(v));
     }
-    if (threadIdx.x == 0) counts[k] = (int)(b1 - b0);
+}
+
+__global__ void domain_boxes_finish_kernel(const unsigned int* __restrict__ enc, const int* __restrict__ counts, int K,
+                                           float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 6 * K) return;
+    out[i] = counts[i / 6] > 0 ? bh_ord2f(enc[i]) : ((i % 6) < 3 ? 3.0e38f : -3.0e38f);
 }
 
 }  // namespace
 
+// enc_dev: 6*K u32 scratch
 int bh_domain_boxes_launch(const uint32_t* keys, const float4* posm, long long n, const uint32_t* cuts_dev, int K,
-                           float* out_dev, int* counts_dev, cudaStream_t st) {
-    domain_boxes_kernel<<<K, LT, 0, st>>>(keys, posm, n, cuts_dev, K, out_dev, counts_dev);
+                           float* out_dev, int* counts_dev, unsigned int* enc_dev, cudaStream_t st) {
+    domain_boxes_init_kernel<<<(6 * K + 255) / 256, 256, 0, st>>>(enc_dev, K);
+    domain_boxes_kernel<<<dim3(K, DOMAIN_SLICES), LT, 0, st>>>(keys, posm, n, cuts_dev, K, enc_dev, counts_dev);
+    domain_boxes_finish_kernel<<<(6 * K + 255) / 256, 256, 0, st>>>(enc_dev, counts_dev, K, out_dev);
     return (int)cudaGetLastError();
 }
 

@@ -146,6 +146,106 @@ __global__ void __launch_bounds__(kThreads) integrate_kernel(const float4* __res
     }
 }
 
+// ---- drop the ghosts (locally-essential-tree mode) ------------------------------------------
+// Stable compaction of the bodies with id >= 0 (the rank's own bodies) out of a state that also holds
+// imported point masses (id < 0), keeping the Morton order; vel.w of every kept body is set to the work
+// its traversal chunk cost (acc.w).  Three launches: per-tile counts, one-block scan of the tile counts,
+// scatter with warp ballots (one warp = 256 consecutive bodies, 32 at a time, so loads stay coalesced).
+constexpr int kCompactTile = 2048;   // bodies per block: 8 warps x 256
+
+__global__ void __launch_bounds__(kThreads) compact_count_kernel(const int32_t* __restrict__ ids, int64_t n,
+                                                                int32_t* __restrict__ tile_count) {
+    const int64_t base = (int64_t)blockIdx.x * kCompactTile;
+    int c = 0;
+#pragma unroll
+    for (int k = 0; k < kCompactTile / kThreads; ++k) {
+        const int64_t i = base + k * kThreads + threadIdx.x;
+        c += (i < n && __ldg(ids + i) >= 0) ? 1 : 0;
+    }
+    c = __reduce_add_sync(0xffffffffu, c);
+    __shared__ int s[kThreads / 32];
+    if ((threadIdx.x & 31) == 0) s[threadIdx.x >> 5] = c;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int t = 0;
+        for (int w = 0; w < kThreads / 32; ++w) t += s[w];
+        tile_count[blockIdx.x] = t;
+    }
+}
+
+// exclusive scan in place; the grand total lands in tile_count[tiles]
+__global__ void __launch_bounds__(1024) compact_scan_kernel(int32_t* __restrict__ tile_count, int tiles) {
+    __shared__ int s[32];
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < tiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int v = i < tiles ? tile_count[i] : 0;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((threadIdx.x & 31) >= o) incl += t;
+        }
+        if ((threadIdx.x & 31) == 31) s[threadIdx.x >> 5] = incl;
+        __syncthreads();
+        if (threadIdx.x < 32) {
+            int w = s[threadIdx.x];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, w, o);
+                if (threadIdx.x >= o) w += t;
+            }
+            s[threadIdx.x] = w;
+        }
+        __syncthreads();
+        const int before = carry + ((threadIdx.x >> 5) ? s[(threadIdx.x >> 5) - 1] : 0) + incl - v;
+        if (i < tiles) tile_count[i] = before;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry = before + v;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) tile_count[tiles] = carry;
+}
+
+__global__ void __launch_bounds__(kThreads) compact_scatter_kernel(const float4* __restrict__ posm, const float4* __restrict__ vel,
+                                                                  const int32_t* __restrict__ ids, const float4* __restrict__ acc,
+                                                                  int64_t n, const int32_t* __restrict__ tile_offset,
+                                                                  float4* __restrict__ posm_out, float4* __restrict__ vel_out,
+                                                                  int32_t* __restrict__ ids_out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t wbase = (int64_t)blockIdx.x * kCompactTile + warp * 256;
+    int id[8];
+    unsigned keep[8];
+    int wcount = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int64_t i = wbase + k * 32 + lane;
+        id[k] = i < n ? __ldg(ids + i) : -1;
+        keep[k] = __ballot_sync(0xffffffffu, id[k] >= 0);
+        wcount += __popc(keep[k]);
+    }
+    __shared__ int s[kThreads / 32];
+    if (lane == 0) s[warp] = wcount;
+    __syncthreads();
+    int64_t o = tile_offset[blockIdx.x];
+    for (int w = 0; w < warp; ++w) o += s[w];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+        const int64_t i = wbase + k * 32 + lane;
+        if (id[k] >= 0) {
+            const int64_t d = o + __popc(keep[k] & ((1u << lane) - 1u));
+            float4 v = __ldg(vel + i);
+            v.w = __ldg(acc + i).w;
+            posm_out[d] = __ldg(posm + i);
+            vel_out[d] = v;
+            ids_out[d] = id[k];
+        }
+        o += __popc(keep[k]);
+    }
+}
+
 // ---- SoA import / export at the reference boundary (bench:32-35) --------------------------
 __global__ void __launch_bounds__(kThreads) import_kernel(const float* __restrict__ px, const float* __restrict__ py,
                                                          const float* __restrict__ pz, const float* __restrict__ vx,
@@ -228,5 +328,16 @@ int bh_export_launch(const float4* posm, const float4* vel, const float4* acc, c
                      int64_t n, float* px, float* py, float* pz, float* vx, float* vy, float* vz,
                      float* ax, float* ay, float* az, cudaStream_t st) {
     export_kernel<<<grid_for(n, 2), kThreads, 0, st>>>(posm, vel, acc, ids, n, px, py, pz, vx, vy, vz, ax, ay, az);
+    return (int)cudaGetLastError();
+}
+
+// tile_scratch: n / 2048 + 2 ints.  The number of kept bodies is left in tile_scratch[tiles] (device).
+int bh_compact_real_launch(const float4* posm, const float4* vel, const int32_t* ids, const float4* acc, int64_t n,
+                           int32_t* tile_scratch, float4* posm_out, float4* vel_out, int32_t* ids_out, cudaStream_t st) {
+    if (n <= 0) return 0;
+    const int tiles = (int)((n + kCompactTile - 1) / kCompactTile);
+    compact_count_kernel<<<tiles, kThreads, 0, st>>>(ids, n, tile_scratch);
+    compact_scan_kernel<<<1, 1024, 0, st>>>(tile_scratch, tiles);
+    compact_scatter_kernel<<<tiles, kThreads, 0, st>>>(posm, vel, ids, acc, n, tile_scratch, posm_out, vel_out, ids_out);
     return (int)cudaGetLastError();
 }

@@ -122,6 +122,7 @@ def lib() -> C.CDLL:
     L.bh_local_bounds.argtypes = [vp, vp]
     L.bh_import_state.argtypes = [vp, vp, vp, vp, i64, vp]
     L.bh_let_export.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp]
+    L.bh_export_real.argtypes = [vp, vp, vp, vp, C.POINTER(i64), vp]
     L.bh_let_domain_boxes.argtypes = [vp, vp, i32, vp, vp]
     L.bh_sorted_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
     L.bh_state_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
@@ -368,6 +369,13 @@ class BHEngine:
 
     def import_state(self, posm, vel, ids, n: int, stream: int = 0):
         _check(lib().bh_import_state(self._ctx, _vp(posm), _vp(vel), _vp(ids), n, C.c_void_p(stream)), "bh_import_state")
+
+    def export_real(self, posm_out, vel_out, ids_out, stream: int = 0) -> int:
+        """Own bodies (id >= 0) of the current state -> device arrays, vel.w = chunk work; returns their number."""
+        m = C.c_int64()
+        _check(lib().bh_export_real(self._ctx, _vp(posm_out), _vp(vel_out), _vp(ids_out), C.byref(m), C.c_void_p(stream)),
+               "bh_export_real")
+        return int(m.value)
 
     def let_domain_boxes(self, cuts):
         """cuts: K+1 ascending u32 keys -> (boxes [K,6] lo/hi, body counts [K])."""

@@ -122,19 +122,55 @@ def compact_boxes(boxes: np.ndarray) -> np.ndarray:
 
 
 class LetRank:
+    """One rank's bodies and engine context.  The own bodies live in one of two capacity-sized buffer sets
+    (ping-pong: migration and ghost removal write the other set), so a step allocates nothing."""
+
     def __init__(self, bh, torch, device, posm, vel, ids, capacity: int, cap_per_peer: int, npeers: int, **params):
         self.bh, self.torch, self.device = bh, torch, device
-        self.posm, self.vel, self.ids = posm, vel, ids          # device tensors: [n,4] f32, [n,4] f32, [n] i32
         self.capacity, self.cap, self.npeers = capacity, cap_per_peer, npeers
         dev_index = device.index if device.index is not None else 0
         self.eng = BHEngine(capacity, device=dev_index, flags=FLAG_NO_GRAPH, **params)
         self.out = torch.empty((npeers, cap_per_peer, 4), dtype=torch.float32, device=device)
+        self._sets = [(torch.empty((capacity, 4), dtype=torch.float32, device=device),
+                       torch.empty((capacity, 4), dtype=torch.float32, device=device),
+                       torch.empty((capacity,), dtype=torch.int32, device=device)) for _ in range(2)]
+        self._cur, self._n = 0, 0
         self.last = {}
         self._ev = None
+        self.adopt(posm, vel, ids)
 
     @property
     def n(self) -> int:
-        return int(self.posm.shape[0])
+        return self._n
+
+    # views of the own bodies: device tensors [n,4] f32 {x,y,z,m}, [n,4] f32 {vx,vy,vz,work}, [n] i32
+    @property
+    def posm(self):
+        return self._sets[self._cur][0][: self._n]
+
+    @property
+    def vel(self):
+        return self._sets[self._cur][1][: self._n]
+
+    @property
+    def ids(self):
+        return self._sets[self._cur][2][: self._n]
+
+    def spare(self, rows: int):
+        """Views [rows] of the buffer set that is NOT holding the own bodies (receive target of a migration)."""
+        if rows > self.capacity:
+            raise self.bh.BHError(f"{rows} bodies exceed the LET context capacity {self.capacity}")
+        p, v, i = self._sets[self._cur ^ 1]
+        return p[:rows], v[:rows], i[:rows]
+
+    def adopt(self, posm, vel, ids):
+        """The given bodies become the own bodies (copied into the spare set unless they already are its views)."""
+        rows = int(posm.shape[0])
+        p, v, i = self.spare(rows)
+        if rows and posm.data_ptr() != p.data_ptr():
+            p.copy_(posm); v.copy_(vel); i.copy_(ids)
+        self._cur ^= 1
+        self._n = rows
 
     def _stream(self) -> int:
         return self.torch.cuda.current_stream().cuda_stream
@@ -187,9 +223,6 @@ class LetRank:
         bounds = np.concatenate([[0], pos, [self.n]])
         return np.diff(bounds), (posm, vel, ids)
 
-    def adopt(self, posm, vel, ids):
-        self.posm, self.vel, self.ids = posm, vel, ids
-
     # ---- local tree, domain description, export ----------------------------------------------
     def build_local_tree(self):
         if self.n == 0:
@@ -215,35 +248,41 @@ class LetRank:
             return np.zeros(len(boxes), np.int32)
         return self.eng.let_export(boxes, self.out, self.cap, self._stream())
 
+    def ghost_slot(self, rows: int):
+        """View [rows,4] right behind the own bodies: imported points received there need no further copy."""
+        if self._n + rows > self.capacity:
+            raise self.bh.BHError(f"LET union of {self._n + rows} bodies exceeds the context capacity {self.capacity}")
+        return self._sets[self._cur][0][self._n: self._n + rows]
+
     def union_step(self, received):
-        """received: list of [k,4] device tensors (point masses from the peers)."""
+        """received: list of [k,4] device tensors (point masses from the peers), or the number of points
+        already written to ghost_slot()."""
         torch = self.torch
-        imp = [r for r in received if r.shape[0] > 0]
-        n_imp = sum(int(r.shape[0]) for r in imp)
-        nl = self.n
+        nl = self._n
+        if isinstance(received, int):
+            n_imp = received
+        else:
+            n_imp = sum(int(r.shape[0]) for r in received)
+            slot, o = self.ghost_slot(n_imp), 0
+            for r in received:
+                slot[o: o + int(r.shape[0])].copy_(r)
+                o += int(r.shape[0])
         nu = nl + n_imp
         if nu == 0:
             return
-        if nu > self.capacity:
-            raise self.bh.BHError(f"LET union of {nu} bodies exceeds the context capacity {self.capacity}")
-        posm_u = torch.cat([self.posm] + imp) if imp else self.posm
-        vel_u = torch.cat([self.vel, torch.zeros((n_imp, 4), dtype=torch.float32, device=self.device)]) if n_imp else self.vel
-        ids_u = torch.cat([self.ids, torch.full((n_imp,), -1, dtype=torch.int32, device=self.device)]) if n_imp else self.ids
+        p, v, i = self._sets[self._cur]
+        v[nl:nu].zero_()
+        i[nl:nu].fill_(-1)
         st = self._stream()
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
-        self.eng.import_state(posm_u.contiguous(), vel_u.contiguous(), ids_u.contiguous(), nu, st)
+        self.eng.import_state(p, v, i, nu, st)
         self.eng.simulation_step(1, st)
         ev[1].record()
         self._ev = (ev[0], ev[1], nl)
-        ptr = self.eng.state_ptrs()
-        pu = torch.as_tensor(_DevView(ptr["posm"], (nu, 4), "<f4"), device=self.device)
-        vu = torch.as_tensor(_DevView(ptr["vel"], (nu, 4), "<f4"), device=self.device)
-        iu = torch.as_tensor(_DevView(ptr["ids"], (nu,), "<i4"), device=self.device)
-        au = torch.as_tensor(_DevView(self.eng.sorted_ptrs()["acc"], (nu, 4), "<f4"), device=self.device)
-        keep = iu >= 0
-        self.posm, self.vel, self.ids = pu[keep].clone(), vu[keep].clone(), iu[keep].clone()
-        self.vel[:, 3] = au[keep, 3]                            # the work each body's chunk cost, for the next election
+        sp, sv, si = self._sets[self._cur ^ 1]                  # drop the ghosts: own bodies, still in Morton order
+        self._n = self.eng.export_real(sp, sv, si, st)
+        self._cur ^= 1
         self.last = {"n_union": nu, "n_import": n_imp}
 
     def last_union_ms(self) -> float:
@@ -316,6 +355,7 @@ class LetSimulation:
         vel = torch.from_numpy(np.stack([vx, vy, vz, np.zeros(n, f32)], 1).astype(f32)).to(self.device)
         ids = torch.from_numpy(np.asarray(local_ids, np.int32)).to(self.device)
         self.rank = LetRank(bh, torch, self.device, posm, vel, ids, capacity, cap_per_peer, world, **params)
+        del posm, vel, ids
         self.stats = {}
         self.trace = {} if os.environ.get("BH_LET_TRACE") else None   # phase -> wall ms of the last step (syncs!)
 
@@ -327,8 +367,8 @@ class LetSimulation:
         self.trace[name] = self.trace.get(name, 0.0) + 1e3 * (t1 - t0)
         return t1
 
-    def _all_to_all_rows(self, send, sc, rc, shape_tail, dtype):
-        recv = self.torch.empty((int(sum(rc)),) + shape_tail, dtype=dtype, device=self.device)
+    def _all_to_all_rows(self, send, sc, rc, shape_tail, dtype, out=None):
+        recv = out if out is not None else self.torch.empty((int(sum(rc)),) + shape_tail, dtype=dtype, device=self.device)
         if send is None:
             send = self.torch.empty((0,) + shape_tail, dtype=dtype, device=self.device)
         self.dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=rc, input_split_sizes=sc)
@@ -363,10 +403,11 @@ class LetSimulation:
             sc, rc = sc_np.tolist(), recv_counts.cpu().numpy().tolist()
             migrated = int(sum(sc)) - int(sc[me])
             v = views if views is not None else (None, None, None)
-            new_posm = self._all_to_all_rows(v[0], sc, rc, (4,), torch.float32)
-            new_vel = self._all_to_all_rows(v[1], sc, rc, (4,), torch.float32)
-            new_ids = self._all_to_all_rows(v[2], sc, rc, (), torch.int32)
-            self.rank.adopt(new_posm, new_vel, new_ids)
+            tp, tv, ti = self.rank.spare(int(sum(rc)))
+            self._all_to_all_rows(v[0], sc, rc, (4,), torch.float32, out=tp)
+            self._all_to_all_rows(v[1], sc, rc, (4,), torch.float32, out=tv)
+            self._all_to_all_rows(v[2], sc, rc, (), torch.int32, out=ti)
+            self.rank.adopt(tp, tv, ti)
             t = self._mark("migrate", t)
             # local tree, domain boxes, export
             self.rank.build_local_tree()
@@ -382,9 +423,10 @@ class LetSimulation:
             dist.all_to_all_single(recv_counts, send_counts)
             sc, rc = counts.astype(np.int64).tolist(), recv_counts.cpu().numpy().tolist()
             send = torch.cat([self.rank.out[p, : sc[p]] for p in range(w)]) if sum(sc) else None
-            recv = self._all_to_all_rows(send, sc, rc, (4,), torch.float32)
+            n_imp = int(sum(rc))
+            self._all_to_all_rows(send, sc, rc, (4,), torch.float32, out=self.rank.ghost_slot(n_imp))
             t = self._mark("exchange", t)
-            self.rank.union_step([recv])
+            self.rank.union_step(n_imp)
             t = self._mark("union step", t)
             self.stats = {"exported": int(sum(sc)), "imported": int(sum(rc)), "n_local": self.rank.n, "migrated_out": migrated}
 
