@@ -30,7 +30,7 @@ WORKLOADS = {
     "plummer_1m": dict(n=1_000_000, ic="plummer", desc="configs[2]: 1,000,000-body Plummer sphere a=200 cut 10a"),
     "plummer_16m": dict(n=16_000_000, ic="plummer", desc="configs[3]: 16,000,000-body Plummer sphere a=200 cut 10a"),
     "twodisk_16m": dict(n=16_000_000, ic="twodisk", desc="two-galaxy collision, 16,000,000 bodies (small version of configs[4])"),
-    "twodisk_256m": dict(n=256_000_000, ic="twodisk", desc="configs[4]: 256,000,000-body two-galaxy collision (replicated-tree mode; LET not built)"),
+    "twodisk_256m": dict(n=256_000_000, ic="twodisk", desc="configs[4]: 256,000,000-body two-galaxy collision"),
 }
 
 

@@ -285,6 +285,10 @@ int  bh_ic_uniform_cube(int64_t n, uint64_t seed, float half_edge,
 int  bh_ic_two_disks(int64_t n, uint64_t seed, float sep, float vx, float vy,
                      float* px, float* py, float* pz,
                      float* vx_out, float* vy_out, float* vz_out, float* mass);
+/* bodies [first, first+n) of the same system (slot i - first): a rank generates only its own share */
+int  bh_ic_two_disks_range(int64_t first, int64_t n, uint64_t seed, float sep, float vx, float vy,
+                           float* px, float* py, float* pz,
+                           float* vx_out, float* vy_out, float* vz_out, float* mass);
 int  bh_ic_plummer(int64_t n, uint64_t seed, float scale_a, float rcut_in_a,
                    float body_mass, float G,
                    float* px, float* py, float* pz,

@@ -17,6 +17,7 @@ from .engine import (  # noqa: F401
     ic_plummer,
     ic_refdisk,
     ic_two_disks,
+    ic_two_disks_range,
     ic_uniform_cube,
     lib,
     library_path,

@@ -121,12 +121,16 @@ extern "C" int bh_ic_plummer(int64_t n, uint64_t seed, float scale_a, float rcut
 // BASELINE.json configs[4] / SURVEY §8d(5): two discs built like main()'s (bench:297-307), centred at
 // -/+ (sep/2, 0, 0) and approaching with -/+ (vx, vy, 0).  Body i draws from its own SplitMix64 stream
 // (seed, i), so the result does not depend on the thread count.
-extern "C" int bh_ic_two_disks(int64_t n, uint64_t seed, float sep, float vx0, float vy0,
-                               float* px, float* py, float* pz, float* vx, float* vy, float* vz, float* mass) {
-    if (n < 0 || !px || !py || !pz || !vx || !vy || !vz || !mass) return BH_E_INVAL;
+// Bodies [first, first + n) of that system into arrays of n floats (slot i - first): a rank of a multi-GPU run
+// generates only its own share.
+extern "C" int bh_ic_two_disks_range(int64_t first, int64_t n, uint64_t seed, float sep, float vx0, float vy0,
+                                     float* px_, float* py_, float* pz_, float* vx_, float* vy_, float* vz_, float* mass_) {
+    if (first < 0 || n < 0 || !px_ || !py_ || !pz_ || !vx_ || !vy_ || !vz_ || !mass_) return BH_E_INVAL;
     const float G = 0.5f;
+    float *px = px_ - first, *py = py_ - first, *pz = pz_ - first, *vx = vx_ - first, *vy = vy_ - first, *vz = vz_ - first,
+          *mass = mass_ - first;
     auto work = [&](int64_t lo, int64_t hi) {
-        for (int64_t i = lo; i < hi; ++i) {
+        for (int64_t i = first + lo; i < first + hi; ++i) {
             SplitMix64 rng(seed * 0x9E3779B97F4A7C15ull + (uint64_t)i * 0xD1B54A32D192ED03ull);
             const float side = (i & 1) ? 1.0f : -1.0f;
             float r = 200.0f + rng.uniform() * 1500.0f;
@@ -150,4 +154,9 @@ extern "C" int bh_ic_two_disks(int64_t n, uint64_t seed, float sep, float vx0, f
     for (unsigned t = 0; t < nt; ++t) th.emplace_back(work, n * t / nt, n * (t + 1) / nt);
     for (auto& x : th) x.join();
     return 0;
+}
+
+extern "C" int bh_ic_two_disks(int64_t n, uint64_t seed, float sep, float vx0, float vy0,
+                               float* px, float* py, float* pz, float* vx, float* vy, float* vz, float* mass) {
+    return bh_ic_two_disks_range(0, n, seed, sep, vx0, vy0, px, py, pz, vx, vy, vz, mass);
 }

@@ -137,6 +137,7 @@ def lib() -> C.CDLL:
     L.bh_ic_refdisk.argtypes = [i64, C.c_uint] + [vp] * 7
     L.bh_ic_uniform_cube.argtypes = [i64, C.c_uint64, f32] + [vp] * 7
     L.bh_ic_two_disks.argtypes = [i64, C.c_uint64, f32, f32, f32] + [vp] * 7
+    L.bh_ic_two_disks_range.argtypes = [i64, i64, C.c_uint64, f32, f32, f32] + [vp] * 7
     L.bh_set_flags.argtypes = [vp, i32]
     L.bh_ic_plummer.argtypes = [i64, C.c_uint64, f32, f32, f32, f32] + [vp] * 7
     L.bh_probe_fp32_tflops.argtypes = [i32, C.POINTER(f32)]
@@ -181,6 +182,13 @@ def ic_two_disks(n: int, seed: int = 42, sep: float = 4000.0, vx: float = 20.0, 
     """BASELINE.json configs[4]: two reference-style discs on a collision course."""
     a = _soa(n)
     _check(lib().bh_ic_two_disks(n, seed, sep, vx, vy, *[_vp(x) for x in a]), "bh_ic_two_disks")
+    return a
+
+
+def ic_two_disks_range(first: int, n: int, seed: int = 42, sep: float = 4000.0, vx: float = 20.0, vy: float = 8.0):
+    """Bodies [first, first+n) of ic_two_disks: each rank of a multi-GPU run generates only its share."""
+    a = _soa(n)
+    _check(lib().bh_ic_two_disks_range(first, n, seed, sep, vx, vy, *[_vp(x) for x in a]), "bh_ic_two_disks_range")
     return a
 
 

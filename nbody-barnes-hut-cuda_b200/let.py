@@ -195,7 +195,7 @@ class LetRank:
         keys, _, vel, _ = self._sorted()
         work = vel[:, 3].double() + WORK_FLOOR if by_work else None
         if work is None or float(vel[:, 3].max().item()) <= 0.0:
-            pick = torch.linspace(0, self.n - 1, SAMPLE, device=self.device).long()
+            pick = (torch.arange(SAMPLE, device=self.device, dtype=torch.int64) * (self.n - 1)) // (SAMPLE - 1)   # exact: no float index
             return keys[pick].cpu().numpy().astype(np.int64), float(self.n)
         cum = torch.cumsum(work, 0)
         total = float(cum[-1].item())
@@ -461,20 +461,19 @@ def run_let_bench(args, w, bh, dist, rank, world, local):
     import bench
 
     n = w["n"]
-    soa = bench.make_ic(bh, w)                     # every rank generates the same bodies, keeps its key range
-    lo = np.array([soa[a].min() for a in range(3)], f32)
-    hi = np.array([soa[a].max() for a in range(3)], f32)
-    cube = global_cube(np.concatenate([lo, hi])[None, :])
-    keys = _morton30_numpy(soa[0], soa[1], soa[2], cube)
-    mask = split_by_keys(keys, world)[rank]
-    sel = np.nonzero(mask)[0]
-    del keys, mask
-    local_soa = [a[sel] for a in soa]
-    del soa
-    nl = len(sel)
+    # Start-up ownership is an INDEX range (no key is needed): the first step's migration hands every body to
+    # the owner of its key.  The two-disc generator is counter based, so a rank draws only its own share.
+    first, last = n * rank // world, n * (rank + 1) // world
+    if w["ic"] == "twodisk":
+        local_soa = bh.ic_two_disks_range(first, last - first, 42, 4000.0, 20.0, 8.0)
+    else:
+        soa = bench.make_ic(bh, w)
+        local_soa = [a[first:last].copy() for a in soa]
+        del soa
+    sel = np.arange(first, last, dtype=np.int32)
     cap_peer = max(1 << 20, int(0.15 * n / world))
     # work-balanced key ranges may hold up to ~2x the mean body count; imports come on top
-    sim = LetSimulation(bh, local_soa, sel.astype(np.int32), rank, world, local, dist,
+    sim = LetSimulation(bh, local_soa, sel, rank, world, local, dist,
                         capacity=int(2.2 * n / world) + (world - 1) * cap_peer // 2 + 4096, cap_per_peer=cap_peer,
                         rebalance=not getattr(args, "let_no_rebalance", False))
     dev = sim.device
