@@ -191,7 +191,8 @@ def run_ours(args, w):
     n = w["n"]
     soa = make_ic(bh, w)
     stream = torch.cuda.current_stream().cuda_stream
-    eng = bh.BHEngine(n, device=local)
+    key_bits = args.key_bits or 30
+    eng = bh.BHEngine(n, device=local, key_bits=key_bits)
     eng.load_soa(*soa)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")   # > 126 MB L2
 
@@ -236,7 +237,7 @@ def run_ours(args, w):
     eng.close()
 
     # ---- per-phase breakdown (event between phases, direct launches) + roofline of the dominant kernel
-    engt = bh.BHEngine(n, device=local, flags=2)
+    engt = bh.BHEngine(n, device=local, flags=2, key_bits=key_bits)
     engt.load_soa(*soa)
     engt.simulation_step(args.warmup, stream)
     psteps = max(3, min(args.steps, 20))
@@ -261,7 +262,7 @@ def run_ours(args, w):
     hbm_frac = {k: (bytes_per_body[k] * n / (phases[k] * 1e-3) / 1e9) / hbm_peak for k in bytes_per_body}
 
     # ---- e2e: host SoA in (pinned) -> 1 step -> host SoA out, every copy inside the timed region
-    enge = bh.BHEngine(n, device=local)
+    enge = bh.BHEngine(n, device=local, key_bits=key_bits)
     pinned = [torch.from_numpy(x.copy()).pin_memory() for x in soa]
     harr = [t.numpy() for t in pinned]
     for _ in range(max(3, args.warmup)):
@@ -281,7 +282,7 @@ def run_ours(args, w):
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["desc"], "n_bodies": n, "theta": 0.5, "G": 0.5, "dt": 0.02,
-                   "softening": 50.0, "max_speed": 500.0, "group": 32,
+                   "softening": 50.0, "max_speed": 500.0, "group": 32, "key_bits": key_bits,
                    "l2": "flushed between timed steps (256 MiB fill, untimed); value_l2_warm is the back-to-back loop"},
         "interactions_per_body": inter / n, "interactions_per_s": inter * args.steps / (total_ms * 1e-3),
         "value_l2_warm": n * args.steps / (warm_ms * 1e-3), "ms_per_step_l2_warm": warm_ms / args.steps,
@@ -336,6 +337,8 @@ def main():
     ap.add_argument("--workload", default=None, choices=list(WORKLOADS))
     ap.add_argument("--mode", default=None, choices=["sliced", "let"],
                     help="multi-GPU scheme: replicated tree + Morton slices, or locally-essential-tree exchange")
+    ap.add_argument("--key-bits", type=int, default=None, choices=[30, 60],
+                    help="Morton key width (bh_params.key_bits); default 30 = the reference key, 60 above 100M bodies")
     ap.add_argument("--let-no-rebalance", action="store_true", help="LET mode: equal-count key ranges instead of equal work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scale-ref", action="store_true", help="skip the 16M-body single-GPU reference point")

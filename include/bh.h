@@ -46,7 +46,11 @@ typedef struct bh_params {
     float dt;         /* DT         0.02f  nbody_v5_bench.cu:16 */
     float softening;  /* SOFTENING  50.0f  nbody_v5_bench.cu:17 (added to r^2) */
     float max_speed;  /* MAX_SPEED  500.0f nbody_v5_bench.cu:18 */
-    int   key_bits;   /* 30: 10 bits/axis Morton key, nbody_v5_bench.cu:58-61 */
+    int   key_bits;   /* 30: 10 bits/axis Morton key, nbody_v5_bench.cu:58-61 (default).
+                         60: the same key extended by 10 more bits per axis taken from the
+                         fractional part of the reference's own float (p-min)/size*1023 — the top
+                         30 bits stay the reference key, the tree gains 10 more levels.  For body
+                         counts where a 1024^3 grid holds many bodies per cell.   */
     int   leaf_cap;   /* 1: one body per leaf, as nbody_v5_bench.cu:100-104   */
     int   flags;      /* BH_FLAG_* */
     float group_split;/* 0.5: a 32-body traversal group is cut at its coarsest key
@@ -152,6 +156,8 @@ enum {
                             (Morton order of THIS step, before the drift)   */
     BH_DBG_VEL_SORTED,   /* float4[n]  matching velocities                  */
     BH_DBG_IDS_SORTED,   /* i32[n]     matching original ids                */
+    BH_DBG_KEYS64,       /* u64[n]     key_bits = 60 only: sorted 60-bit keys
+                            (reference key << 30 | low word)                */
     BH_DBG_COUNT
 };
 int  bh_debug_get(bh_ctx* ctx, int what, void* dst, size_t bytes);

@@ -58,6 +58,20 @@ __device__ __forceinline__ int bh_shared_digits(uint32_t a, uint32_t b) {
     return x == 0 ? BH_MAX_LEVEL : (__clz((int)x) - (32 - BH_KEY_BITS)) / 3;
 }
 
+// keys of LEVELS 3-bit digits: 10 = the reference's 30-bit key in a u32, 20 = that key extended by 10 more
+// bits per axis (bh_params.key_bits = 60) in a u64, reference key on top
+template <int LEVELS> struct BhKey;
+template <> struct BhKey<10> { typedef uint32_t type; };
+template <> struct BhKey<20> { typedef uint64_t type; };
+template <int LEVELS>
+__device__ __forceinline__ int bh_shared_digits_t(typename BhKey<LEVELS>::type a, typename BhKey<LEVELS>::type b);
+template <>
+__device__ __forceinline__ int bh_shared_digits_t<10>(uint32_t a, uint32_t b) { return bh_shared_digits(a, b); }
+template <>
+__device__ __forceinline__ int bh_shared_digits_t<20>(uint64_t a, uint64_t b) {
+    const uint64_t x = a ^ b;
+    return x == 0 ? 20 : (__clzll((long long)x) - 4) / 3;
+}
 
 #define BH_CUDA_TRY(expr)                                  \
     do {                                                   \
@@ -83,13 +97,19 @@ int bh_sort_pairs_launch(const uint32_t* keys_src, const uint32_t* vals_src, uin
                          bool vals_in_is_iota, unsigned int* err_flag, int* result_in_q, cudaStream_t st);
 
 int bh_keys_launch(const float4* posm, int64_t n, BhDevScalars* sc, uint32_t* keys, cudaStream_t st);
+// 60-bit keys: hi = the reference key, lo = ten more bits per axis from the fractional part of the same float
+int bh_keys60_launch(const float4* posm, int64_t n, BhDevScalars* sc, uint32_t* hi, uint32_t* lo, cudaStream_t st);
+int bh_gather_u32_launch(const uint32_t* src, const uint32_t* perm, uint32_t* dst, int64_t n, cudaStream_t st);
+// keys64[i] = hi_sorted[i] << 30 | lo_unsorted[perm[i]]
+int bh_combine_keys_launch(const uint32_t* hi_sorted, const uint32_t* lo_unsorted, const uint32_t* perm, uint64_t* keys64,
+                           int64_t n, cudaStream_t st);
 int bh_bounds_launch(const float4* posm, int64_t n, BhDevScalars* sc, cudaStream_t st);
 int bh_reorder_launch(const float4* posm_in, const float4* vel_in, const int32_t* ids_in,
                       const uint32_t* perm, float4* posm_out, float4* vel_out, int32_t* ids_out,
                       int64_t n, cudaStream_t st);
 // kid_src: 8 float4 per cell — the SOURCE each child contributes when its parent is opened (a loose
 // body's {x,y,z,m}, a child cell's {com,mass}); kid_lv: 8 bytes per cell — level | bucket<<7 of child cells.
-int bh_tree_launch(const uint32_t* keys, const float4* posm, int64_t n, int2* pair_info, int32_t* pair_scan,
+int bh_tree_launch(const void* keys, int levels, const float4* posm, int64_t n, int2* pair_info, int32_t* pair_scan,
                    int32_t* scan_block_sums, int4* cell_meta, int32_t* cell_child,
                    int32_t* cell_arrive, float4* kid_src, uint8_t* kid_lv, BhDevScalars* sc, cudaStream_t st);
 int bh_com_launch(const float4* posm, int64_t n, const int4* cell_meta, const int32_t* cell_child,
@@ -97,7 +117,7 @@ int bh_com_launch(const float4* posm, int64_t n, const int4* cell_meta, const in
                   BhDevScalars* sc, cudaStream_t st);
 // heavy_list, heavy_flag: 2 * max_chunks u32 each (see BhDevScalars::epoch)
 // ids: nullptr, or per-body ids where id < 0 marks a ghost (a source whose own acceleration is not wanted)
-int bh_force_launch(const float4* posm, const uint32_t* keys, const int32_t* ids, int64_t n, int64_t first_body,
+int bh_force_launch(const float4* posm, const void* keys, int levels, const int32_t* ids, int64_t n, int64_t first_body,
                     int64_t body_count, const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
                     const float4* kid_src, const uint8_t* kid_lv,
                     float4* acc, BhDevScalars* sc, uint32_t* heavy_list, uint32_t* heavy_flag, int64_t max_chunks,
@@ -122,7 +142,7 @@ int bh_momentum_launch(const float4* posm, const float4* vel, int64_t n, double*
 int bh_let_export_launch(const int4* cell_meta, const int32_t* cell_child, const float4* cell_com, const float4* kid_src,
                          const uint8_t* kid_lv, const float4* posm, BhDevScalars* sc, const float* boxes_dev,
                          const float* hull_dev, int npeers, int K, float4* out, unsigned int* out_count, long long cap, int2* queue, unsigned int* qcounts,
-                         long long qcap, float theta, float softening, float root_w, cudaStream_t st);
+                         long long qcap, float theta, float softening, float root_w, int levels, cudaStream_t st);
 int bh_domain_boxes_launch(const uint32_t* keys, const float4* posm, long long n, const uint32_t* cuts_dev, int K,
                            float* out_dev, int* counts_dev, unsigned int* enc_dev, cudaStream_t st);
 int bh_compact_real_launch(const float4* posm, const float4* vel, const int32_t* ids, const float4* acc, int64_t n,

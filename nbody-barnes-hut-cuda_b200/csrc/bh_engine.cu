@@ -35,6 +35,10 @@ struct bh_ctx {
     float4 *posm = nullptr, *vel = nullptr, *posm_s = nullptr, *vel_s = nullptr, *acc = nullptr;
     int32_t *ids = nullptr, *ids_s = nullptr;
     uint32_t *keys0 = nullptr, *keys1 = nullptr, *vals0 = nullptr, *vals1 = nullptr;
+    // key_bits = 60 only: unsorted low words, a sort ping-pong buffer, the sorted 60-bit keys
+    uint32_t *klo = nullptr, *kaux = nullptr;
+    uint64_t* keys64 = nullptr;
+    int levels = BH_MAX_LEVEL;           // 3-bit digits per key: 10 (30-bit reference key) or 20
     void* sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
     int2* pair_info = nullptr;
@@ -82,7 +86,7 @@ void free_all(bh_ctx* c) {
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     void* ptrs[] = {c->posm, c->vel, c->posm_s, c->vel_s, c->acc, c->ids, c->ids_s, c->keys0, c->keys1, c->vals0,
                     c->vals1, c->sort_tmp, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
-                    c->cell_arrive, c->cell_mom, c->cell_com, c->sc, c->stage, c->d_scratch, c->heavy_list, c->heavy_flag, c->kid_src, c->kid_lv, c->let_boxes, c->let_counts, c->let_queue};
+                    c->cell_arrive, c->cell_mom, c->cell_com, c->sc, c->stage, c->d_scratch, c->heavy_list, c->heavy_flag, c->kid_src, c->kid_lv, c->let_boxes, c->let_counts, c->let_queue, c->klo, c->kaux, c->keys64};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -107,10 +111,30 @@ int phase_keys(bh_ctx* c, cudaStream_t st) {
         e = bh_bounds_launch(c->posm, c->n, c->sc, st);
     }
     if (e) return e;
+    if (c->levels == 20) return bh_keys60_launch(c->posm, c->n, c->sc, c->keys0, c->klo, st);
     return bh_keys_launch(c->posm, c->n, c->sc, c->keys0, st);
 }
 
+// key_bits = 60: LSD over the two 30-bit words with the same u32 sorter — low word first (values = iota),
+// then the high word carried along in that order (stable), then the sorted 60-bit keys are assembled.
+int sort_keys60(bh_ctx* c, cudaStream_t st) {
+    unsigned int* err = (unsigned int*)((char*)c->sc + offsetof(BhDevScalars, err));
+    int in_q = 0;
+    int e = bh_sort_pairs_launch(c->klo, nullptr, c->keys1, c->vals1, c->kaux, c->vals0, c->n, 0, BH_KEY_BITS, c->sort_tmp, true,
+                                 err, &in_q, st);                                   // -> order by low word in vals0
+    if (e) return e;
+    if (!in_q) return BH_E_UNSUPPORTED;
+    e = bh_gather_u32_launch(c->keys0, c->vals0, c->keys1, c->n, st);               // high words in that order
+    if (e) return e;
+    e = bh_sort_pairs_launch(c->keys1, c->vals0, c->kaux, c->vals1, c->keys0, c->vals0, c->n, 0, BH_KEY_BITS, c->sort_tmp, false,
+                             err, &in_q, st);                                       // -> sorted high words in keys0, final order in vals0
+    if (e) return e;
+    if (!in_q) return BH_E_UNSUPPORTED;
+    return bh_combine_keys_launch(c->keys0, c->klo, c->vals0, c->keys64, c->n, st);
+}
+
 int sort_keys_only(bh_ctx* c, cudaStream_t st) {
+    if (c->levels == 20) return sort_keys60(c, st);
     int in_q = 0;
     // pass 0 reads keys0 (+ implicit iota values) -> keys1/vals1 -> keys0/vals0 -> ...; 4 passes end in keys0/vals0
     int e = bh_sort_pairs_launch(c->keys0, nullptr, c->keys1, c->vals1, c->keys0, c->vals0, c->n, 0, BH_KEY_BITS,
@@ -131,7 +155,7 @@ int phase_sort(bh_ctx* c, cudaStream_t st) {
 }
 
 int phase_build(bh_ctx* c, cudaStream_t st) {
-    return bh_tree_launch(c->keys0, c->posm_s, c->n, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
+    return bh_tree_launch(c->levels == 20 ? (const void*)c->keys64 : (const void*)c->keys0, c->levels, c->posm_s, c->n, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
                           c->cell_arrive, c->kid_src, c->kid_lv, c->sc, st);
 }
 
@@ -140,7 +164,7 @@ int phase_com(bh_ctx* c, cudaStream_t st) {
 }
 
 int phase_force(bh_ctx* c, cudaStream_t st) {
-    return bh_force_launch(c->posm_s, c->keys0, c->ids_s, c->n, c->slice_first, c->slice_count, c->cell_meta, c->cell_child,
+    return bh_force_launch(c->posm_s, c->levels == 20 ? (const void*)c->keys64 : (const void*)c->keys0, c->levels, c->ids_s, c->n, c->slice_first, c->slice_count, c->cell_meta, c->cell_child,
                            c->cell_com, c->kid_src, c->kid_lv, c->acc, c->sc, c->heavy_list, c->heavy_flag, c->max_chunks, c->prm.theta,
                            c->prm.softening, c->prm.G, c->prm.group_split, c->num_sms, st);
 }
@@ -247,7 +271,7 @@ int bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device) 
     *out = nullptr;
     bh_params prm;
     if (params) prm = *params; else bh_default_params(&prm);
-    if (prm.key_bits != BH_KEY_BITS || prm.leaf_cap != 1) return BH_E_UNSUPPORTED;
+    if ((prm.key_bits != BH_KEY_BITS && prm.key_bits != 2 * BH_KEY_BITS) || prm.leaf_cap != 1) return BH_E_UNSUPPORTED;
     if (!(prm.softening > 0.0f) || !(prm.theta >= 0.0f) || !(prm.max_speed > 0.0f)) return BH_E_INVAL;
     if (!(prm.group_split >= 0.0f) || prm.group_split > 1.0f) return BH_E_INVAL;
     BH_CUDA_TRY(cudaSetDevice(device));
@@ -255,6 +279,7 @@ int bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device) 
     bh_ctx* c = new (std::nothrow) bh_ctx();
     if (!c) return BH_E_NOMEM;
     c->device = device; c->prm = prm; c->n_max = n_max;
+    c->levels = prm.key_bits / 3;
     c->n_alloc = ((n_max + 4095) / 4096 + 1) * 4096;  // room for slice padding in all-gathers
     int sms = 0;
     if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && sms > 0) c->num_sms = sms;
@@ -267,6 +292,7 @@ int bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device) 
     TRYA(dev_alloc(&c->vel_s, na)); TRYA(dev_alloc(&c->acc, na)); TRYA(dev_alloc(&c->ids, na)); TRYA(dev_alloc(&c->ids_s, na));
     TRYA(dev_alloc(&c->keys0, na)); TRYA(dev_alloc(&c->keys1, na)); TRYA(dev_alloc(&c->vals0, na)); TRYA(dev_alloc(&c->vals1, na));
     TRYA(cudaMalloc(&c->sort_tmp, plan.total_bytes));
+    if (c->levels == 20) { TRYA(dev_alloc(&c->klo, na)); TRYA(dev_alloc(&c->kaux, na)); TRYA(dev_alloc(&c->keys64, na)); }
     TRYA(dev_alloc(&c->pair_info, na)); TRYA(dev_alloc(&c->pair_scan, na)); TRYA(dev_alloc(&c->tile_sums, na / 2048 + 16));
     TRYA(dev_alloc(&c->cell_meta, na)); TRYA(dev_alloc(&c->cell_child, na * 8)); TRYA(dev_alloc(&c->cell_arrive, na));
     TRYA(dev_alloc(&c->cell_mom, na)); TRYA(dev_alloc(&c->cell_com, na));
@@ -483,7 +509,7 @@ int bh_let_export(bh_ctx* c, const float* boxes_lohi, int npeers, int K, void* o
         int e = bh_let_export_launch(c->cell_meta, c->cell_child, c->cell_com, c->kid_src, c->kid_lv, c->posm_s, c->sc,
                                      c->let_boxes, c->let_boxes + (size_t)npeers * K * 6, npeers, K, (float4*)out, c->let_counts, cap_per_peer, c->let_queue,
                                      c->let_counts + BH_LET_MAX_PEERS, c->let_qcap, c->prm.theta, c->prm.softening,
-                                     h.bounds[3] - h.bounds[0], st);
+                                     h.bounds[3] - h.bounds[0], c->levels, st);
         if (e) return e;
         unsigned int hc[BH_LET_MAX_PEERS];
         BH_CUDA_TRY(cudaMemcpyAsync(hc, c->let_counts, sizeof(unsigned int) * npeers, cudaMemcpyDeviceToHost, st));
@@ -665,6 +691,9 @@ static int dbg_locate(bh_ctx* c, int what, void** ptr, size_t* bytes) {
     switch (what) {
         case BH_DBG_BOUNDS: *ptr = (char*)c->sc + offsetof(BhDevScalars, bounds); *bytes = 24; break;
         case BH_DBG_KEYS: *ptr = c->keys0; *bytes = n * 4; break;
+        case BH_DBG_KEYS64:
+            if (c->levels != 20) return BH_E_UNSUPPORTED;
+            *ptr = c->keys64; *bytes = n * 8; break;
         case BH_DBG_PERM: *ptr = c->vals0; *bytes = n * 4; break;
         case BH_DBG_IDS: *ptr = c->ids; *bytes = n * 4; break;
         case BH_DBG_POSM: *ptr = c->posm; *bytes = n * 16; break;

@@ -150,8 +150,9 @@ __device__ __forceinline__ void eval_tile(const SrcPair* __restrict__ src, f32x2
     }
 }
 
+template <int LEVELS>
 __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
-    const float4* __restrict__ posm, const uint32_t* __restrict__ keys, const int32_t* __restrict__ ids,
+    const float4* __restrict__ posm, const typename BhKey<LEVELS>::type* __restrict__ keys, const int32_t* __restrict__ ids,
     int64_t first_body, int64_t body_count, const int4* __restrict__ cell_meta, const int32_t* __restrict__ cell_child, const float4* __restrict__ cell_com,
     const float4* __restrict__ kid_src, const uint8_t* __restrict__ kid_lv, float4* __restrict__ acc, BhDevScalars* sc,
     uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_flag, int64_t max_chunks, float theta, float soft,
@@ -208,9 +209,9 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
         const bool sink = valid && (ids == nullptr || __ldg(ids + my) >= 0);   // someone wants this body's acceleration
 
         // ---- split the chunk into spatially compact sub-groups (see the file header) ----
-        const uint32_t mykey = __ldg(keys + (valid ? my : end_body - 1));
-        const uint32_t nextkey = __shfl_down_sync(0xffffffffu, mykey, 1);
-        const int lvp = (lane + 1 < nb) ? bh_shared_digits(mykey, nextkey) : 99;   // pair (lane, lane+1)
+        const typename BhKey<LEVELS>::type mykey = __ldg(keys + (valid ? my : end_body - 1));
+        const typename BhKey<LEVELS>::type nextkey = __shfl_down_sync(0xffffffffu, mykey, 1);
+        const int lvp = (lane + 1 < nb) ? bh_shared_digits_t<LEVELS>(mykey, nextkey) : 99;   // pair (lane, lane+1)
         const unsigned ox = bh_f2ord(me.x), oy = bh_f2ord(me.y), oz = bh_f2ord(me.z);
         const f32x2 npx = pack2(-me.x, -me.x), npy = pack2(-me.y, -me.y), npz = pack2(-me.z, -me.z);
         const f32x2 soft2 = pack2(soft, soft);
@@ -237,7 +238,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
         while (gb - ga >= 2 && split_alpha > 0.0f) {
             const int cand = (lane >= ga && lane + 1 < gb) ? ((lvp << 5) | lane) : 0x7FFFFFFF;
             const int best = __reduce_min_sync(0xffffffffu, cand);   // fewest shared digits, first such pair
-            if ((best >> 5) >= BH_MAX_LEVEL) break;
+            if ((best >> 5) >= LEVELS) break;
             const int gk = (best & 31) + 1;
             const bool inA = lane >= ga && lane < gk && sink, inB = lane >= gk && lane < gb && sink;
             const unsigned sA = __ballot_sync(0xffffffffu, inA), sB = __ballot_sync(0xffffffffu, inB);
@@ -484,14 +485,16 @@ static int g_force_ctas_per_sm = 0;
 // occupancy query done once, outside any stream capture
 int bh_force_prepare() {
     if (g_force_ctas_per_sm > 0) return 0;
-    int max_ctas = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&max_ctas, force_kernel, FORCE_THREADS, 0);
+    int a = 0, b = 0;
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, force_kernel<10>, FORCE_THREADS, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, force_kernel<20>, FORCE_THREADS, 0);
     if (e != cudaSuccess) return (int)e;
+    const int max_ctas = a < b ? a : b;
     g_force_ctas_per_sm = max_ctas < 1 ? 1 : max_ctas;
     return 0;
 }
 
-int bh_force_launch(const float4* posm, const uint32_t* keys, const int32_t* ids, int64_t n, int64_t first_body,
+int bh_force_launch(const float4* posm, const void* keys, int levels, const int32_t* ids, int64_t n, int64_t first_body,
                     int64_t body_count, const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
                     const float4* kid_src, const uint8_t* kid_lv,
                     float4* acc, BhDevScalars* sc, uint32_t* heavy_list, uint32_t* heavy_flag, int64_t max_chunks,
@@ -508,8 +511,13 @@ int bh_force_launch(const float4* posm, const uint32_t* keys, const int32_t* ids
     int64_t want = (ngroups + FORCE_WARPS - 1) / FORCE_WARPS;
     int64_t grid = (int64_t)(num_sms > 0 ? num_sms : BH_NUM_SMS_FALLBACK) * max_ctas;  // persistent: fill the chip once
     if (grid > want) grid = want;
-    force_kernel<<<(int)grid, FORCE_THREADS, 0, st>>>(posm, keys, ids, first_body, body_count, cell_meta, cell_child, cell_com,
-                                                     kid_src, kid_lv, acc, sc, heavy_list, heavy_flag, max_chunks, theta,
-                                                     softening, G, split_alpha);
+    if (levels == 20)
+        force_kernel<20><<<(int)grid, FORCE_THREADS, 0, st>>>(posm, (const uint64_t*)keys, ids, first_body, body_count, cell_meta,
+                                                             cell_child, cell_com, kid_src, kid_lv, acc, sc, heavy_list,
+                                                             heavy_flag, max_chunks, theta, softening, G, split_alpha);
+    else
+        force_kernel<10><<<(int)grid, FORCE_THREADS, 0, st>>>(posm, (const uint32_t*)keys, ids, first_body, body_count, cell_meta,
+                                                             cell_child, cell_com, kid_src, kid_lv, acc, sc, heavy_list,
+                                                             heavy_flag, max_chunks, theta, softening, G, split_alpha);
     return (int)cudaGetLastError();
 }

@@ -19,7 +19,7 @@
 // Cells that pass the test already against the AABB of all of the peer's boxes skip the per-box loop.
 //
 // Level-synchronous: a queue of (cell to open, peer) pairs is expanded once per tree level by a grid-wide
-// kernel (at most BH_MAX_LEVEL + 1 launches for all peers together); outputs are appended with atomics.
+// kernel (at most levels + 1 launches for all peers together); outputs are appended with atomics.
 #include "bh_common.cuh"
 
 namespace {
@@ -211,7 +211,7 @@ int bh_domain_boxes_launch(const uint32_t* keys, const float4* posm, long long n
 int bh_let_export_launch(const int4* cell_meta, const int32_t* cell_child, const float4* cell_com, const float4* kid_src,
                          const uint8_t* kid_lv, const float4* posm, BhDevScalars* sc, const float* boxes_dev,
                          const float* hull_dev, int npeers, int K, float4* out, unsigned int* out_count, long long cap, int2* queue, unsigned int* qcounts,
-                         long long qcap, float theta, float softening, float root_w, cudaStream_t st) {
+                         long long qcap, float theta, float softening, float root_w, int levels, cudaStream_t st) {
     LetArgs a;
     a.cell_meta = cell_meta; a.cell_child = cell_child; a.cell_com = cell_com; a.kid_src = kid_src; a.kid_lv = kid_lv;
     a.posm = posm; a.boxes = boxes_dev; a.hull = hull_dev; a.K = K; a.out = out; a.out_count = out_count; a.cap = cap;
@@ -222,7 +222,7 @@ int bh_let_export_launch(const int4* cell_meta, const int32_t* cell_child, const
     BH_CUDA_TRY(cudaMemsetAsync(out_count, 0, sizeof(unsigned int) * npeers, st));
     BH_CUDA_TRY(cudaMemsetAsync(qcounts, 0, 2 * sizeof(unsigned int), st));
     let_seed_kernel<<<(npeers + 63) / 64, 64, 0, st>>>(a, npeers, sc, queue, qcounts);
-    for (int level = 0; level <= BH_MAX_LEVEL; ++level) {
+    for (int level = 0; level <= levels; ++level) {
         const int in = level & 1, outq = in ^ 1;
         BH_CUDA_TRY(cudaMemsetAsync(qcounts + outq, 0, sizeof(unsigned int), st));
         let_level_kernel<<<BH_NUM_SMS_FALLBACK * 8, LT, 0, st>>>(a, queue + (size_t)in * qcap, qcounts + in,

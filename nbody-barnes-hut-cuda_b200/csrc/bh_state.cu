@@ -102,6 +102,44 @@ __global__ void __launch_bounds__(kThreads) keys_kernel(const float4* __restrict
     }
 }
 
+// key_bits = 60 (oracle: orc_morton_keys60): the fractional part of the SAME float t = (p-min)/size*1023 — exact,
+// t and trunc(t) share their exponent range — gives ten more bits per axis; (hi << 30 | lo) refines the reference
+// order without ever contradicting it.
+__device__ __forceinline__ void quantise2(float p, float lo, float size, uint32_t& q, uint32_t& fr) {
+    const float t = __fmul_rn(__fdiv_rn(__fsub_rn(p, lo), size), 1023.0f);
+    q = __float2uint_rz(t);
+    const float g = __fmul_rn(__fsub_rn(t, __uint2float_rn(q)), 1024.0f);
+    fr = !(g > 0.0f) ? 0u : (g >= 1023.0f ? 1023u : __float2uint_rz(g));
+}
+
+__global__ void __launch_bounds__(kThreads) keys60_kernel(const float4* __restrict__ posm, int64_t n,
+                                                         const BhDevScalars* __restrict__ sc,
+                                                         uint32_t* __restrict__ hi, uint32_t* __restrict__ lo) {
+    const float minX = sc->bounds[0], minY = sc->bounds[1], minZ = sc->bounds[2];
+    const float size = fmaxf(__fsub_rn(sc->bounds[3], sc->bounds[0]), 1.0f);  // bench:57
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        const float4 p = __ldg(posm + i);
+        uint32_t qx, qy, qz, fx, fy, fz;
+        quantise2(p.x, minX, size, qx, fx); quantise2(p.y, minY, size, qy, fy); quantise2(p.z, minZ, size, qz, fz);
+        hi[i] = (spread10(qx) << 2) | (spread10(qy) << 1) | spread10(qz);
+        lo[i] = (spread10(fx) << 2) | (spread10(fy) << 1) | spread10(fz);
+    }
+}
+
+__global__ void __launch_bounds__(kThreads) gather_u32_kernel(const uint32_t* __restrict__ src, const uint32_t* __restrict__ perm,
+                                                             uint32_t* __restrict__ dst, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+        dst[i] = __ldg(src + perm[i]);
+}
+
+__global__ void __launch_bounds__(kThreads) combine_keys_kernel(const uint32_t* __restrict__ hi_sorted,
+                                                               const uint32_t* __restrict__ lo_unsorted,
+                                                               const uint32_t* __restrict__ perm, uint64_t* __restrict__ keys64,
+                                                               int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+        keys64[i] = ((uint64_t)hi_sorted[i] << 30) | (uint64_t)__ldg(lo_unsorted + perm[i]);
+}
+
 // ---- Morton reorder -----------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) reorder_kernel(const float4* __restrict__ posm_in,
                                                           const float4* __restrict__ vel_in,
@@ -298,6 +336,22 @@ int bh_bounds_launch(const float4* posm, int64_t n, BhDevScalars* sc, cudaStream
 
 int bh_keys_launch(const float4* posm, int64_t n, BhDevScalars* sc, uint32_t* keys, cudaStream_t st) {
     keys_kernel<<<grid_for(n, 2), kThreads, 0, st>>>(posm, n, sc, keys);
+    return (int)cudaGetLastError();
+}
+
+int bh_keys60_launch(const float4* posm, int64_t n, BhDevScalars* sc, uint32_t* hi, uint32_t* lo, cudaStream_t st) {
+    keys60_kernel<<<grid_for(n, 2), kThreads, 0, st>>>(posm, n, sc, hi, lo);
+    return (int)cudaGetLastError();
+}
+
+int bh_gather_u32_launch(const uint32_t* src, const uint32_t* perm, uint32_t* dst, int64_t n, cudaStream_t st) {
+    gather_u32_kernel<<<grid_for(n, 2), kThreads, 0, st>>>(src, perm, dst, n);
+    return (int)cudaGetLastError();
+}
+
+int bh_combine_keys_launch(const uint32_t* hi_sorted, const uint32_t* lo_unsorted, const uint32_t* perm, uint64_t* keys64,
+                           int64_t n, cudaStream_t st) {
+    combine_keys_kernel<<<grid_for(n, 2), kThreads, 0, st>>>(hi_sorted, lo_unsorted, perm, keys64, n);
     return (int)cudaGetLastError();
 }
 

@@ -30,16 +30,19 @@ constexpr int TB = 256;           // threads per CTA
 constexpr int SCAN_ITEMS = 8;     // pairs per thread in the flag scan
 constexpr int SCAN_TILE = TB * SCAN_ITEMS;
 
-__device__ __forceinline__ int lv_pair(const uint32_t* __restrict__ K, int j, int n) {
+template <int LEVELS>
+__device__ __forceinline__ int lv_pair(const typename BhKey<LEVELS>::type* __restrict__ K, int j, int n) {
     if (j < 0 || j >= n - 1) return -1;
-    return bh_shared_digits(__ldg(K + j), __ldg(K + j + 1));
+    return bh_shared_digits_t<LEVELS>(__ldg(K + j), __ldg(K + j + 1));
 }
 
 // smallest index t <= j whose key shares L digits with K[j] (keys ascending)
-__device__ int find_left(const uint32_t* __restrict__ K, int j, int L) {
+template <int LEVELS>
+__device__ int find_left(const typename BhKey<LEVELS>::type* __restrict__ K, int j, int L) {
+    typedef typename BhKey<LEVELS>::type KeyT;
     if (L <= 0) return 0;
-    const int s = BH_KEY_BITS - 3 * L;
-    const uint32_t p = __ldg(K + j) >> s;
+    const int s = 3 * LEVELS - 3 * L;
+    const KeyT p = __ldg(K + j) >> s;
     int good = j, bad = -1, step = 1;
     for (;;) {
         int t = good - step;
@@ -55,10 +58,12 @@ __device__ int find_left(const uint32_t* __restrict__ K, int j, int L) {
 }
 
 // largest index t >= j whose key shares L digits with K[j]
-__device__ int find_right(const uint32_t* __restrict__ K, int n, int j, int L) {
+template <int LEVELS>
+__device__ int find_right(const typename BhKey<LEVELS>::type* __restrict__ K, int n, int j, int L) {
+    typedef typename BhKey<LEVELS>::type KeyT;
     if (L <= 0) return n - 1;
-    const int s = BH_KEY_BITS - 3 * L;
-    const uint32_t p = __ldg(K + j) >> s;
+    const int s = 3 * LEVELS - 3 * L;
+    const KeyT p = __ldg(K + j) >> s;
     int good = j, bad = n, step = 1;
     for (;;) {
         int t = good + step;
@@ -74,7 +79,8 @@ __device__ int find_right(const uint32_t* __restrict__ K, int n, int j, int L) {
 }
 
 // ---- pass A: leader of every pair + per-tile leader counts ---------------------------------
-__global__ void __launch_bounds__(TB) pair_kernel(const uint32_t* __restrict__ K, int n, int2* __restrict__ pair_info,
+template <int LEVELS>
+__global__ void __launch_bounds__(TB) pair_kernel(const typename BhKey<LEVELS>::type* __restrict__ K, int n, int2* __restrict__ pair_info,
                                                  int32_t* __restrict__ tile_sums) {
     const int npairs = n - 1;
     const int tile0 = blockIdx.x * SCAN_TILE;
@@ -83,16 +89,16 @@ __global__ void __launch_bounds__(TB) pair_kernel(const uint32_t* __restrict__ K
     for (int k = 0; k < SCAN_ITEMS; ++k) {
         const int j = tile0 + k * TB + threadIdx.x;
         if (j < npairs) {
-            const uint32_t a = __ldg(K + j), b = __ldg(K + j + 1);
-            const int L = bh_shared_digits(a, b);
+            const typename BhKey<LEVELS>::type a = __ldg(K + j), b = __ldg(K + j + 1);
+            const int L = bh_shared_digits_t<LEVELS>(a, b);
             int lead, first;
-            if (L == BH_MAX_LEVEL) {  // inside a run of identical keys: the run's first pair leads
+            if (L == LEVELS) {  // inside a run of identical keys: the run's first pair leads
                 first = j;
                 lead = (j == 0 || __ldg(K + j - 1) != a) ? j : -1;
             } else {
-                first = find_left(K, j, L);
+                first = find_left<LEVELS>(K, j, L);
                 // j leads iff it closes the first child, i.e. K[j] still shares L+1 digits with K[first]
-                lead = (bh_shared_digits(__ldg(K + first), a) >= L + 1) ? j : find_right(K, n, first, L + 1);
+                lead = (bh_shared_digits_t<LEVELS>(__ldg(K + first), a) >= L + 1) ? j : find_right<LEVELS>(K, n, first, L + 1);
             }
             pair_info[j] = make_int2(lead, first);
             leaders += (lead == j);
@@ -194,22 +200,23 @@ __global__ void __launch_bounds__(TB) init_cells_kernel(int4* __restrict__ child
 }
 
 // ---- pass E: every cell and every loose body links itself under its parent -------------------
-__global__ void __launch_bounds__(TB) link_kernel(const uint32_t* __restrict__ K, const float4* __restrict__ posm, int n,
+template <int LEVELS>
+__global__ void __launch_bounds__(TB) link_kernel(const typename BhKey<LEVELS>::type* __restrict__ K, const float4* __restrict__ posm, int n,
                                                  const int2* __restrict__ pair_info,
                                                  const int32_t* __restrict__ pair_scan, int4* __restrict__ cell_meta,
                                                  int32_t* __restrict__ cell_child, float4* __restrict__ kid_src,
                                                  uint8_t* __restrict__ kid_lv, BhDevScalars* sc) {
     for (int i = blockIdx.x * TB + threadIdx.x; i < n; i += gridDim.x * TB) {
-        const uint32_t ki = __ldg(K + i);
-        const int lv_left = lv_pair(K, i - 1, n);   // pair (i-1, i)
-        const int lv_here = lv_pair(K, i, n);       // pair (i, i+1)
+        const typename BhKey<LEVELS>::type ki = __ldg(K + i);
+        const int lv_left = lv_pair<LEVELS>(K, i - 1, n);   // pair (i-1, i)
+        const int lv_here = lv_pair<LEVELS>(K, i, n);       // pair (i, i+1)
 
         // (1) body i as a loose child (skipped when it belongs to a bucket)
         const int Lb = max(lv_left, lv_here);
-        if (Lb >= 0 && Lb < BH_MAX_LEVEL) {
+        if (Lb >= 0 && Lb < LEVELS) {
             const int sp = (lv_left >= lv_here) ? i - 1 : i;
             const int parent = pair_scan[pair_info[sp].x];
-            const int slot = (ki >> (BH_KEY_BITS - 3 * (Lb + 1))) & 7;
+            const int slot = (int)(ki >> (3 * LEVELS - 3 * (Lb + 1))) & 7;
             cell_child[(size_t)parent * 8 + slot] = (int)(0x80000000u | (uint32_t)i);
             kid_src[(size_t)parent * 8 + slot] = __ldg(posm + i);   // what the traversal reads when it opens `parent`
         }
@@ -221,21 +228,21 @@ __global__ void __launch_bounds__(TB) link_kernel(const uint32_t* __restrict__ K
                 const int c = pair_scan[i];
                 const int L = lv_here;
                 const int l = info.y;
-                const int r = find_right(K, n, i, L);
-                const int a = lv_pair(K, l - 1, n), b = lv_pair(K, r, n);
+                const int r = find_right<LEVELS>(K, n, i, L);
+                const int a = lv_pair<LEVELS>(K, l - 1, n), b = lv_pair<LEVELS>(K, r, n);
                 const int Lp = max(a, b);
                 int parent = -1, slot = 0;
                 if (Lp >= 0) {
                     if (Lp >= L) atomicOr(&sc->err, BH_DERR_TREE);
                     const int sp = (a >= b) ? l - 1 : r;
                     parent = pair_scan[pair_info[sp].x];
-                    slot = (ki >> (BH_KEY_BITS - 3 * (Lp + 1))) & 7;
+                    slot = (int)(ki >> (3 * LEVELS - 3 * (Lp + 1))) & 7;
                     cell_child[(size_t)parent * 8 + slot] = c;
-                    kid_lv[(size_t)parent * 8 + slot] = (uint8_t)(L | ((L == BH_MAX_LEVEL) << 7));
+                    kid_lv[(size_t)parent * 8 + slot] = (uint8_t)(L | ((L == LEVELS) << 7));
                 } else {
                     sc->root = c;
                 }
-                cell_meta[c] = make_int4(l, r - l + 1, L | ((L == BH_MAX_LEVEL) << 8) | (slot << 12), parent);
+                cell_meta[c] = make_int4(l, r - l + 1, L | ((L == LEVELS) << 8) | (slot << 12), parent);
             }
         }
     }
@@ -326,17 +333,23 @@ inline int capped_grid(int64_t work_items, int per_block) {
 
 }  // namespace
 
-int bh_tree_launch(const uint32_t* keys, const float4* posm, int64_t n64, int2* pair_info, int32_t* pair_scan,
+// keys: ascending u32 keys of 10 digits (levels == 10, the reference's 30-bit key) or u64 keys of 20 digits
+// (levels == 20, bh_params.key_bits = 60)
+int bh_tree_launch(const void* keys, int levels, const float4* posm, int64_t n64, int2* pair_info, int32_t* pair_scan,
                    int32_t* scan_block_sums, int4* cell_meta, int32_t* cell_child,
                    int32_t* cell_arrive, float4* kid_src, uint8_t* kid_lv, BhDevScalars* sc, cudaStream_t st) {
     const int n = (int)n64;
     if (n < 2) return 0;
     const int ntiles = (n - 1 + SCAN_TILE - 1) / SCAN_TILE;
-    pair_kernel<<<ntiles, TB, 0, st>>>(keys, n, pair_info, scan_block_sums);
+    if (levels == 20) pair_kernel<20><<<ntiles, TB, 0, st>>>((const uint64_t*)keys, n, pair_info, scan_block_sums);
+    else pair_kernel<10><<<ntiles, TB, 0, st>>>((const uint32_t*)keys, n, pair_info, scan_block_sums);
     scan_tiles_kernel<<<1, 1024, 0, st>>>(scan_block_sums, ntiles, sc);
     scan_pairs_kernel<<<ntiles, TB, 0, st>>>(pair_info, n, scan_block_sums, pair_scan);
     init_cells_kernel<<<capped_grid(n, TB), TB, 0, st>>>(reinterpret_cast<int4*>(cell_child), cell_arrive, sc);
-    link_kernel<<<capped_grid(n, TB), TB, 0, st>>>(keys, posm, n, pair_info, pair_scan, cell_meta, cell_child, kid_src, kid_lv, sc);
+    if (levels == 20)
+        link_kernel<20><<<capped_grid(n, TB), TB, 0, st>>>((const uint64_t*)keys, posm, n, pair_info, pair_scan, cell_meta, cell_child, kid_src, kid_lv, sc);
+    else
+        link_kernel<10><<<capped_grid(n, TB), TB, 0, st>>>((const uint32_t*)keys, posm, n, pair_info, pair_scan, cell_meta, cell_child, kid_src, kid_lv, sc);
     return (int)cudaGetLastError();
 }
 

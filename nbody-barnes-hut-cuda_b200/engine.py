@@ -48,7 +48,7 @@ class PHASE:
 
 class DBG:
     (BOUNDS, KEYS, PERM, IDS, POSM, VEL, ACC, CELL_META, CELL_COM, CELL_CHILD,
-     POSM_SORTED, VEL_SORTED, IDS_SORTED) = range(13)
+     POSM_SORTED, VEL_SORTED, IDS_SORTED, KEYS64) = range(14)
 
 
 class STAT:
@@ -324,7 +324,7 @@ class BHEngine:
             DBG.IDS: ((n,), np.int32), DBG.POSM: ((n, 4), np.float32), DBG.VEL: ((n, 4), np.float32),
             DBG.ACC: ((n, 4), np.float32), DBG.CELL_META: ((M, 4), np.int32), DBG.CELL_COM: ((M, 4), np.float32),
             DBG.CELL_CHILD: ((M, 8), np.int32), DBG.POSM_SORTED: ((n, 4), np.float32),
-            DBG.VEL_SORTED: ((n, 4), np.float32), DBG.IDS_SORTED: ((n,), np.int32),
+            DBG.VEL_SORTED: ((n, 4), np.float32), DBG.IDS_SORTED: ((n,), np.int32), DBG.KEYS64: ((n,), np.uint64),
         }
         shape, dt = shapes[what]
         out = np.zeros(shape, dt)

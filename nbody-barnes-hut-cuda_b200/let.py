@@ -471,11 +471,12 @@ def run_let_bench(args, w, bh, dist, rank, world, local):
         local_soa = [a[first:last].copy() for a in soa]
         del soa
     sel = np.arange(first, last, dtype=np.int32)
+    key_bits = getattr(args, "key_bits", None) or (60 if n > 100_000_000 else 30)
     cap_peer = max(1 << 20, int(0.15 * n / world))
     # work-balanced key ranges may hold up to ~2x the mean body count; imports come on top
     sim = LetSimulation(bh, local_soa, sel, rank, world, local, dist,
                         capacity=int(2.2 * n / world) + (world - 1) * cap_peer // 2 + 4096, cap_per_peer=cap_peer,
-                        rebalance=not getattr(args, "let_no_rebalance", False))
+                        rebalance=not getattr(args, "let_no_rebalance", False), key_bits=key_bits)
     dev = sim.device
 
     def barrier():
@@ -513,7 +514,7 @@ def run_let_bench(args, w, bh, dist, rank, world, local):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["desc"], "n_bodies": n, "theta": 0.5, "G": 0.5, "dt": 0.02,
-                   "softening": 50.0, "max_speed": 500.0, "group": 32,
+                   "softening": 50.0, "max_speed": 500.0, "group": 32, "key_bits": key_bits,
                    "parallelism": f"locally-essential-tree x{world}: work-weighted sampled key splitters, body migration, "
                                   "per-peer export walk against octree-aligned domain boxes, NCCL all-to-all of point "
                                   "masses, ordinary step on own + imported bodies",

@@ -1,0 +1,133 @@
+"""bh_params.key_bits = 60 on the GPU against the oracle's 60-bit statement (orc_morton_keys60, orc_tree_build64,
+orc_make_groups64, orc_engine_step key_bits=60): the reference's 30-bit key stays on top bit for bit, ten more
+bits per axis come from the fractional part of the reference's own float, the tree gains ten levels."""
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from test_gpu_parity import make_case
+
+pytestmark = pytest.mark.gpu
+f = np.float32
+
+CASES = [("uniform", 2), ("uniform", 33), ("uniform", 16384), ("disk", 50001), ("clustered", 20000), ("coincident", 500),
+         ("lattice", 4096), ("plummer", 30000), ("line", 20000), ("bigbucket", 12000)]
+
+
+@pytest.mark.parametrize("kind,n", CASES)
+def test_every_phase_against_oracle_with_60_bit_keys(bh, kind, n):
+    soa = make_case(bh, kind, n)
+    posm, vel, ids = O.soa_to_internal(soa)
+    P, D, S = bh.PHASE, bh.DBG, bh.STAT
+    with bh.BHEngine(n, flags=1, key_bits=60) as eng:
+        eng.load_soa(*soa)
+        eng.run_phase(P.KEYS)
+        b = O.bounds(*soa[:3])
+        hi, lo = O.morton_keys60(*soa[:3], b)
+        ref30, _ = O.morton_keys(*soa[:3], b)
+        assert (hi == ref30).all()                                # the reference key is untouched
+        assert (eng.debug_get(D.KEYS) == hi).all()
+        eng.run_phase(P.SORT)
+        k64 = (hi.astype(np.uint64) << np.uint64(30)) | lo.astype(np.uint64)
+        ks, perm = O.stable_sort64(k64, np.arange(n, dtype=np.int32))
+        assert (eng.debug_get(D.KEYS64) == ks).all()
+        assert (eng.debug_get(D.KEYS) == (ks >> np.uint64(30)).astype(np.uint32)).all()
+        assert (eng.debug_get(D.PERM) == perm).all()
+        ps = np.ascontiguousarray(posm[perm])
+        assert eng.debug_get(D.POSM_SORTED).tobytes() == ps.tobytes()
+        eng.run_phase(P.BUILD)
+        meta, child, root = O.tree_build64(ks, 20)
+        assert eng.stat(S.DEVICE_ERROR) == 0
+        assert eng.stat(S.CELLS) == len(meta) and eng.stat(S.ROOT) == root
+        gmeta, gchild = eng.debug_get(D.CELL_META), eng.debug_get(D.CELL_CHILD)
+        assert (gmeta == meta).all()
+        internal = ((meta[:, 2] >> 8) & 1) == 0
+        assert (gchild[internal] == child[internal]).all()
+        if n >= 2 and kind != "coincident":
+            assert (meta[:, 2] & 0xFF).max() <= 20
+        eng.run_phase(P.COM)
+        mom, com = O.tree_com(ps, meta, child, root)
+        assert eng.debug_get(D.CELL_COM).tobytes() == com.tobytes()
+        eng.run_phase(P.FORCE)
+        assert eng.stat(S.DEVICE_ERROR) == 0
+        groups = O.make_groups64(ps, ks, 20)
+        acc, counts = O.force_groups(ps, b, meta, child, com, root, groups)
+        gacc = eng.debug_get(D.ACC)
+        assert eng.stat(S.INTERACTIONS_CELL) == counts[0]
+        assert eng.stat(S.INTERACTIONS_BODY) == counts[1]
+        scale = np.abs(acc[:, :3]).max() if n > 1 else 1.0
+        if scale > 0:
+            assert O.rel_rms(gacc[:, :3], acc[:, :3]) < 1e-4
+            assert np.abs(gacc[:, :3] - acc[:, :3]).max() < 1e-4 * scale
+
+
+@pytest.mark.parametrize("kind,n,steps", [("plummer", 20000, 5), ("lattice", 3000, 3)])
+def test_multi_step_60_bit_against_oracle_and_graph_equals_direct(bh, kind, n, steps):
+    soa = make_case(bh, kind, n)
+    posm, vel, ids = O.soa_to_internal(soa)
+    want = O.engine_step(posm, vel, ids, steps, key_bits=60)
+    outs = []
+    for flags in (0, 1):
+        with bh.BHEngine(n, flags=flags, key_bits=60) as eng:
+            eng.load_soa(*soa)
+            eng.simulation_step(steps)
+            eng.check_device_error()
+            outs.append((eng.debug_get(bh.DBG.POSM), eng.debug_get(bh.DBG.VEL), eng.debug_get(bh.DBG.IDS)))
+    assert outs[0][0].tobytes() == outs[1][0].tobytes() and outs[0][1].tobytes() == outs[1][1].tobytes()
+    gp, gv, gid = outs[0]
+    assert (gid == want["ids"]).all()
+    assert O.rel_rms(gp[:, :3], want["posm"][:, :3]) < 1e-6
+
+
+def test_deep_core_needs_fewer_interactions_with_60_bit_keys(bh):
+    """A tight cluster inside a wide system: the 1024^3 grid lumps the core into large identical-key buckets
+    (all-pairs work); ten more levels resolve it.  Accuracy against the direct sum stays in the same class.
+    (The core is kept wider than theta*sqrt(SOFTENING) = 3.5: below that width the reference's acceptance test
+    bench:207-208 passes at ANY distance, so deeper cells are monopoles by definition — see DESIGN.md.)"""
+    n = 60000
+    rng = np.random.default_rng(5)
+    pos = np.concatenate([rng.normal(0, 30.0, (n // 2, 3)), rng.uniform(-40000, 40000, (n - n // 2, 3))]).astype(f)
+    z = np.zeros(n, f)
+    soa = [pos[:, 0].copy(), pos[:, 1].copy(), pos[:, 2].copy(), z.copy(), z.copy(), z.copy(), rng.uniform(2, 7, n).astype(f)]
+    sample = np.arange(0, n, 30, dtype=np.int32)
+    res = {}
+    for bits in (30, 60):
+        with bh.BHEngine(n, key_bits=bits) as eng:
+            eng.load_soa(*soa)
+            eng.simulation_step(1)
+            eng.check_device_error()
+            out = eng.read_soa()
+            inter = eng.stat(bh.STAT.INTERACTIONS_CELL) + eng.stat(bh.STAT.INTERACTIONS_BODY)
+            res[bits] = (inter, O.rel_rms(np.stack(out[6:9], 1)[sample], eng.direct_sample(sample)))
+    assert res[60][0] < 0.5 * res[30][0]
+    assert res[60][1] < max(2.0 * res[30][1], 3e-3)
+
+
+def test_sliced_and_let_calls_work_with_60_bit_keys(bh):
+    """Domain boxes and the export walk take the level count from the context."""
+    import torch
+
+    from nbody_barnes_hut_cuda_b200.let import LetRank, let_step_emulated, split_by_keys
+
+    n, world = 30000, 3
+    soa = bh.ic_plummer(n, 8, 200.0, 10.0, 4.5, 0.5)
+    posm_all, _, _ = O.soa_to_internal(soa)
+    keys, _ = O.morton_keys(*soa[:3], O.bounds(*soa[:3]))
+    masks = split_by_keys(keys, world)
+    dev = torch.device("cuda:0")
+    ranks = []
+    for r in range(world):
+        sel = np.nonzero(masks[r])[0]
+        posm = torch.from_numpy(np.stack([soa[0][sel], soa[1][sel], soa[2][sel], soa[6][sel]], 1).astype(f)).to(dev)
+        vel = torch.zeros((len(sel), 4), device=dev)
+        ranks.append(LetRank(bh, torch, dev, posm, vel, torch.from_numpy(sel.astype(np.int32)).to(dev), capacity=n + 4096,
+                             cap_per_peer=n, npeers=world, key_bits=60))
+    let_step_emulated(ranks)
+    acc = np.zeros((n, 3))
+    for r in ranks:
+        ids_, a = r.last_accelerations()
+        acc[ids_] = a
+        r.eng.check_device_error()
+        r.close()
+    sample = np.arange(0, n, 16, dtype=np.int32)
+    assert O.rel_rms(acc[sample], O.direct_sum(posm_all, sample)) < 3e-3
