@@ -238,6 +238,16 @@ int  bh_sorted_ptrs(bh_ctx* ctx, void** keys, void** posm, void** vel, void** id
 int  bh_let_export(bh_ctx* ctx, const float* boxes_lohi, int npeers, int K, void* out, int64_t cap_per_peer,
                    int32_t* counts, void* stream);
 
+/* Keys + sort + reorder on the reference's 30-bit key only, whatever key_bits is: enough to elect key-range
+ * splitters and to find the runs of the sorted order that migrate (bh_sorted_ptrs), at half the sorting cost
+ * of a 60-bit context.  The tree phases need a full BH_PHASE_KEYS + BH_PHASE_SORT afterwards.              */
+int  bh_sort_coarse(bh_ctx* ctx, void* stream);
+/* Cross-tree traversal: ADD to the accelerations of ctx's last force phase (BH_PHASE_FORCE) the attraction of
+ * every body of `sources`, traversing sources' tree with ctx's body groups.  Both contexts: same device, same
+ * key_bits, the same fixed cube (bh_set_fixed_bounds), phases KEYS..COM current; sources needs >= 2 bodies.
+ * A rank of the LET mode keeps the points imported from its peers in a small context of their own and never
+ * re-sorts or rebuilds its own tree for them.  Run BH_PHASE_UPDATE on ctx afterwards.                      */
+int  bh_force_from(bh_ctx* ctx, bh_ctx* sources, void* stream);
 /* After a step on own bodies + ghosts: copy the bodies with id >= 0 of the current state, in their (Morton)
  * order, to the DEVICE arrays posm_out / vel_out (float4) / ids_out, with vel.w = the work of the body's
  * traversal chunk in that step (see BH_DBG_ACC).  *n_real = bodies written.  Synchronises `stream`.      */

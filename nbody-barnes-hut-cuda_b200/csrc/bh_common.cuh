@@ -121,7 +121,10 @@ int bh_force_launch(const float4* posm, const void* keys, int levels, const int3
                     int64_t body_count, const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
                     const float4* kid_src, const uint8_t* kid_lv,
                     float4* acc, BhDevScalars* sc, uint32_t* heavy_list, uint32_t* heavy_flag, int64_t max_chunks,
-                    float theta, float softening, float G, float split_alpha, int num_sms, cudaStream_t st);
+                    float theta, float softening, float G, float split_alpha, int num_sms,
+                    // cross-tree pass: the tree (scalars, cells, the bodies its buckets index) of ANOTHER body set;
+                    // nullptr/nullptr/0 = the ordinary pass over the bodies' own tree
+                    const float4* src_posm, const BhDevScalars* tree_sc, int accumulate, cudaStream_t st);
 int bh_force_prepare();
 int bh_integrate_launch(const float4* posm_s, const float4* vel_s, const int32_t* ids_s, const float4* acc,
                         float4* posm, float4* vel, int32_t* ids, int64_t first_body, int64_t body_count,

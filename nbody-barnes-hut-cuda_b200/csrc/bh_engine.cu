@@ -166,7 +166,7 @@ int phase_com(bh_ctx* c, cudaStream_t st) {
 int phase_force(bh_ctx* c, cudaStream_t st) {
     return bh_force_launch(c->posm_s, c->levels == 20 ? (const void*)c->keys64 : (const void*)c->keys0, c->levels, c->ids_s, c->n, c->slice_first, c->slice_count, c->cell_meta, c->cell_child,
                            c->cell_com, c->kid_src, c->kid_lv, c->acc, c->sc, c->heavy_list, c->heavy_flag, c->max_chunks, c->prm.theta,
-                           c->prm.softening, c->prm.G, c->prm.group_split, c->num_sms, st);
+                           c->prm.softening, c->prm.G, c->prm.group_split, c->num_sms, nullptr, nullptr, 0, st);
 }
 
 int phase_update(bh_ctx* c, cudaStream_t st) {
@@ -445,6 +445,47 @@ int bh_sorted_ptrs(bh_ctx* c, void** keys, void** posm, void** vel, void** ids, 
     if (acc) *acc = c->acc;
     if (n) *n = c->n;
     return 0;
+}
+
+int bh_sort_coarse(bh_ctx* c, void* stream) {
+    if (!c) return BH_E_INVAL;
+    if (!c->have_state) return BH_E_STATE;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    int e = 0;
+    if (c->fixed_bounds_set) {
+        BH_CUDA_TRY(cudaMemcpyAsync((char*)c->sc + offsetof(BhDevScalars, bounds), c->fixed_bounds, sizeof(c->fixed_bounds),
+                                    cudaMemcpyHostToDevice, st));
+    } else {
+        e = bh_bounds_launch(c->posm, c->n, c->sc, st);
+        if (e) return e;
+    }
+    e = bh_keys_launch(c->posm, c->n, c->sc, c->keys0, st);
+    if (e) return e;
+    int in_q = 0;
+    e = bh_sort_pairs_launch(c->keys0, nullptr, c->keys1, c->vals1, c->keys0, c->vals0, c->n, 0, BH_KEY_BITS, c->sort_tmp, true,
+                             (unsigned int*)((char*)c->sc + offsetof(BhDevScalars, err)), &in_q, st);
+    if (e) return e;
+    if (!in_q) return BH_E_UNSUPPORTED;
+    e = reorder_only(c, st);
+    if (e) return e;
+    c->have_sorted = true;
+    return 0;
+}
+
+int bh_force_from(bh_ctx* c, bh_ctx* src, void* stream) {
+    if (!c || !src || c == src) return BH_E_INVAL;
+    if (!c->have_state || !c->have_sorted || !src->have_state || !src->have_sorted) return BH_E_STATE;
+    if (c->device != src->device || c->levels != src->levels) return BH_E_INVAL;
+    if (!c->fixed_bounds_set || !src->fixed_bounds_set || memcmp(c->fixed_bounds, src->fixed_bounds, sizeof(c->fixed_bounds)) != 0)
+        return BH_E_STATE;   // cell widths are derived from the cube: both trees must live on the same grid
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    if (src->n < 2) return BH_E_UNSUPPORTED;   // a single body has no tree
+    return bh_force_launch(c->posm_s, c->levels == 20 ? (const void*)c->keys64 : (const void*)c->keys0, c->levels, c->ids_s, c->n,
+                           c->slice_first, c->slice_count, src->cell_meta, src->cell_child, src->cell_com, src->kid_src,
+                           src->kid_lv, c->acc, c->sc, c->heavy_list, c->heavy_flag, c->max_chunks, c->prm.theta,
+                           c->prm.softening, c->prm.G, c->prm.group_split, c->num_sms, src->posm_s, src->sc, 1,
+                           (cudaStream_t)stream);
 }
 
 int bh_export_real(bh_ctx* c, void* posm_out, void* vel_out, int32_t* ids_out, int64_t* n_real, void* stream) {

@@ -34,6 +34,11 @@
 // sub-group without real bodies is skipped, and a cut that separates ghosts from real bodies is always
 // taken.  Without ghosts (ids == nullptr or all ids >= 0) nothing changes.
 //
+// Cross-tree pass (accumulate != 0; locally-essential-tree mode): the groups are still runs of `posm`, but the
+// tree — its scalars tree_sc, its cells and the bodies src_posm its buckets index — belongs to ANOTHER body
+// set (the points imported from the other ranks); the result is added to acc.  That pass hands the chunks out
+// in plain Morton order and leaves the heavy-chunk bookkeeping of the main pass alone.
+//
 // acc[i].w carries the work of body i's chunk (its interaction-list entries, all sub-groups) so that a
 // driver can balance key ranges by measured work (let.py).
 #include "bh_common.cuh"
@@ -156,17 +161,18 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
     int64_t first_body, int64_t body_count, const int4* __restrict__ cell_meta, const int32_t* __restrict__ cell_child, const float4* __restrict__ cell_com,
     const float4* __restrict__ kid_src, const uint8_t* __restrict__ kid_lv, float4* __restrict__ acc, BhDevScalars* sc,
     uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_flag, int64_t max_chunks, float theta, float soft,
-    float G, float split_alpha) {
+    float G, float split_alpha, const float4* __restrict__ src_posm, const BhDevScalars* __restrict__ tree_sc,
+    int accumulate) {
     __shared__ WarpScratch s_warp[FORCE_WARPS];
 
     const int lane = bh_lane();
     WarpScratch& W = s_warp[threadIdx.x >> 5];
     SrcPair* const slist = reinterpret_cast<SrcPair*>(W.src);
     const float theta2 = __fmul_rn(theta, theta);
-    const int root = sc->root;
+    const int root = tree_sc->root;
     // bench:208 maxX - minX of the root; a level-L cell is root_w * 2^-L wide, so its squared width is
     // root_w^2 with 2L taken off the exponent (exact: power-of-two scaling commutes with rounding)
-    const float root_w = __fsub_rn(sc->bounds[3], sc->bounds[0]);
+    const float root_w = __fsub_rn(tree_sc->bounds[3], tree_sc->bounds[0]);
     const int root_w2_bits = __float_as_int(__fmul_rn(root_w, root_w));
     const int4* child4 = reinterpret_cast<const int4*>(cell_child);
     const uint2* lv2 = reinterpret_cast<const uint2*>(kid_lv);
@@ -182,7 +188,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
     // a chunk is on the list being replayed iff its tag equals this launch's epoch
     const unsigned epoch = sc->epoch;
     const unsigned cur = epoch & 1u, nxt = cur ^ 1u;
-    const unsigned heavy_n = min(sc->heavy_n[cur], (unsigned)min(ngroups, max_chunks));
+    const unsigned heavy_n = accumulate ? 0u : min(sc->heavy_n[cur], (unsigned)min(ngroups, max_chunks));
     const unsigned heavy_thresh = sc->heavy_thresh;
     const uint32_t* list_cur = heavy_list + (size_t)cur * max_chunks;
     const uint32_t* flag_cur = heavy_flag + (size_t)cur * max_chunks;
@@ -196,7 +202,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
                 const unsigned t = atomicAdd(&sc->group_ticket, 1u);
                 if (t < heavy_n) { g = list_cur[t]; break; }
                 g = t - heavy_n;
-                if ((int64_t)g >= ngroups || flag_cur[g] != epoch) break;   // tagged chunks were served from the list
+                if ((int64_t)g >= ngroups || accumulate || flag_cur[g] != epoch) break;   // tagged chunks were served from the list
             }
         }
         g = __shfl_sync(0xffffffffu, g, 0);
@@ -305,7 +311,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
             dir_bodies += bcount;
             for (int b = 0; b < bcount; b += 32) {
                 const int m = min(32, bcount - b);
-                if (lane < m) store_source(slist, ns + lane, __ldg(posm + bfirst + b + lane));
+                if (lane < m) store_source(slist, ns + lane, __ldg(src_posm + bfirst + b + lane));
                 ns += m;
                 __syncwarp();
                 drain();
@@ -438,12 +444,16 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
         ga = gb;
         }   // sub-groups of the chunk
         tot_entries += chunk_entries;
-        if (lane == 0 && chunk_entries > heavy_thresh && (int64_t)g < max_chunks) {
+        if (lane == 0 && !accumulate && chunk_entries > heavy_thresh && (int64_t)g < max_chunks) {
             const unsigned slot = atomicAdd(&sc->heavy_n[nxt], 1u);
             if ((int64_t)slot < max_chunks) { list_nxt[slot] = g; flag_nxt[g] = epoch + 1u; }
         }
 
-        if (valid) acc[my] = make_float4(G * ax, G * ay, G * az, (float)chunk_entries);
+        if (valid) {
+            float4 a = make_float4(G * ax, G * ay, G * az, (float)chunk_entries);
+            if (accumulate) { const float4 o = acc[my]; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
+            acc[my] = a;
+        }
         tot_cell += acc_cells_w;
         tot_body += dir_bodies_w;
     }
@@ -451,7 +461,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
     if (lane == 0) {
         if (tot_cell) atomicAdd(&sc->inter_cell, tot_cell);
         if (tot_body) atomicAdd(&sc->inter_body, tot_body);
-        if (tot_entries) atomicAdd(&sc->entries_total, tot_entries);
+        if (tot_entries && !accumulate) atomicAdd(&sc->entries_total, tot_entries);
         atomicMax(&sc->max_stack, max_sp);
     }
 }
@@ -472,6 +482,10 @@ __global__ void reset_force_scalars(BhDevScalars* sc, int64_t ngroups) {
         sc->inter_body = 0;
         sc->max_stack = 0;
     }
+}
+
+__global__ void reset_ticket_only(BhDevScalars* sc) {
+    if (threadIdx.x == 0) sc->group_ticket = 0;
 }
 
 __global__ void __launch_bounds__(256) zero_acc_kernel(float4* acc, int64_t first, int64_t count) {
@@ -498,10 +512,17 @@ int bh_force_launch(const float4* posm, const void* keys, int levels, const int3
                     int64_t body_count, const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
                     const float4* kid_src, const uint8_t* kid_lv,
                     float4* acc, BhDevScalars* sc, uint32_t* heavy_list, uint32_t* heavy_flag, int64_t max_chunks,
-                    float theta, float softening, float G, float split_alpha, int num_sms, cudaStream_t st) {
+                    float theta, float softening, float G, float split_alpha, int num_sms, const float4* src_posm,
+                    const BhDevScalars* tree_sc, int accumulate, cudaStream_t st) {
     if (body_count <= 0) return 0;
-    reset_force_scalars<<<1, 32, 0, st>>>(sc, (body_count + BH_GROUP - 1) / BH_GROUP);
-    if (n < 2) {  // a single body feels nothing (its self term is exactly zero, bench:205-213)
+    if (!src_posm) src_posm = posm;
+    if (!tree_sc) tree_sc = sc;
+    if (accumulate) {
+        reset_ticket_only<<<1, 32, 0, st>>>(sc);
+    } else {
+        reset_force_scalars<<<1, 32, 0, st>>>(sc, (body_count + BH_GROUP - 1) / BH_GROUP);
+    }
+    if (n < 2 && !accumulate) {  // a single body feels nothing (its self term is exactly zero, bench:205-213)
         zero_acc_kernel<<<1, 256, 0, st>>>(acc, first_body, body_count);
         return (int)cudaGetLastError();
     }
@@ -514,10 +535,12 @@ int bh_force_launch(const float4* posm, const void* keys, int levels, const int3
     if (levels == 20)
         force_kernel<20><<<(int)grid, FORCE_THREADS, 0, st>>>(posm, (const uint64_t*)keys, ids, first_body, body_count, cell_meta,
                                                              cell_child, cell_com, kid_src, kid_lv, acc, sc, heavy_list,
-                                                             heavy_flag, max_chunks, theta, softening, G, split_alpha);
+                                                             heavy_flag, max_chunks, theta, softening, G, split_alpha, src_posm, tree_sc,
+                                                             accumulate);
     else
         force_kernel<10><<<(int)grid, FORCE_THREADS, 0, st>>>(posm, (const uint32_t*)keys, ids, first_body, body_count, cell_meta,
                                                              cell_child, cell_com, kid_src, kid_lv, acc, sc, heavy_list,
-                                                             heavy_flag, max_chunks, theta, softening, G, split_alpha);
+                                                             heavy_flag, max_chunks, theta, softening, G, split_alpha, src_posm, tree_sc,
+                                                             accumulate);
     return (int)cudaGetLastError();
 }

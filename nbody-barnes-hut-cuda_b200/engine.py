@@ -122,6 +122,8 @@ def lib() -> C.CDLL:
     L.bh_local_bounds.argtypes = [vp, vp]
     L.bh_import_state.argtypes = [vp, vp, vp, vp, i64, vp]
     L.bh_let_export.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp]
+    L.bh_force_from.argtypes = [vp, vp, vp]
+    L.bh_sort_coarse.argtypes = [vp, vp]
     L.bh_export_real.argtypes = [vp, vp, vp, vp, C.POINTER(i64), vp]
     L.bh_let_domain_boxes.argtypes = [vp, vp, i32, vp, vp]
     L.bh_sorted_ptrs.argtypes = [vp, C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(vp), C.POINTER(i64)]
@@ -377,6 +379,14 @@ class BHEngine:
 
     def import_state(self, posm, vel, ids, n: int, stream: int = 0):
         _check(lib().bh_import_state(self._ctx, _vp(posm), _vp(vel), _vp(ids), n, C.c_void_p(stream)), "bh_import_state")
+
+    def sort_coarse(self, stream: int = 0):
+        """keys + sort + reorder on the 30-bit reference key only (splitter election / migration)."""
+        _check(lib().bh_sort_coarse(self._ctx, C.c_void_p(stream)), "bh_sort_coarse")
+
+    def force_from(self, sources: "BHEngine", stream: int = 0):
+        """acc += attraction of every body of `sources`, traversing ITS tree with this context's groups."""
+        _check(lib().bh_force_from(self._ctx, sources._ctx, C.c_void_p(stream)), "bh_force_from")
 
     def export_real(self, posm_out, vel_out, ids_out, stream: int = 0) -> int:
         """Own bodies (id >= 0) of the current state -> device arrays, vel.w = chunk work; returns their number."""

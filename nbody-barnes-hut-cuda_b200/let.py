@@ -9,13 +9,17 @@ Each rank owns the bodies of one Morton-key range and never sees the others' bod
              taken at equal increments of its cumulative work; the weighted quantiles of the pooled sample
              are the new key ranges (SURVEY §8e "sampled key splitters") — equal WORK, not equal count;
   migrate    the bodies that left the rank's range are runs of its sorted order: one all-to-all;
+             (every step: a body outside its owner's key range would have to be covered by a box that is no
+             longer a run of whole cells — measured: boxes around such strays span the domain faces and the
+             export lists overflow)
   local tree keys, sort, tree, centre of mass over the rank's own bodies;
   domain     the key range is cut at octree-cell boundaries (domain_cuts) and described by the tight body
              AABB of every interval (bh_let_domain_boxes) — a key range is not convex, whole cells are;
   export     one walk of the local tree per peer against the peer's boxes (csrc/bh_let.cu) -> point masses;
   exchange   all-to-all of the point lists (variable sizes);
-  union step own bodies + received points (ids = -1) go through the ordinary step; received points are
-             dropped afterwards.
+  forces     traversal of the local tree; the received points get a small tree of their own (second context,
+             same cube) that the rank's body groups traverse as well (bh_force_from, accumulating) — the own
+             tree is never rebuilt for them; then the ordinary kick-drift-clamp.
 `LetRank` is the per-rank logic; `let_step_emulated` drives several ranks on ONE device (tests — the
 guide forbids emulating ranks with kernels that wait on each other, this path has no such kernels);
 `LetSimulation` is the torch.distributed driver (NCCL all-gather + all-to-all).
@@ -130,6 +134,12 @@ class LetRank:
         self.capacity, self.cap, self.npeers = capacity, cap_per_peer, npeers
         dev_index = device.index if device.index is not None else 0
         self.eng = BHEngine(capacity, device=dev_index, flags=FLAG_NO_GRAPH, **params)
+        # the points imported from the peers live in a context of their own (see forces_and_update)
+        self.ghost_cap = max(2, min(capacity, (npeers - 1) * cap_per_peer))
+        self.geng = BHEngine(self.ghost_cap, device=dev_index, flags=FLAG_NO_GRAPH, **params)
+        self.gposm = torch.zeros((self.ghost_cap, 4), dtype=torch.float32, device=device)
+        self.gvel = torch.zeros((self.ghost_cap, 4), dtype=torch.float32, device=device)
+        self.gids = torch.full((self.ghost_cap,), -1, dtype=torch.int32, device=device)
         self.out = torch.empty((npeers, cap_per_peer, 4), dtype=torch.float32, device=device)
         self._sets = [(torch.empty((capacity, 4), dtype=torch.float32, device=device),
                        torch.empty((capacity, 4), dtype=torch.float32, device=device),
@@ -181,17 +191,20 @@ class LetRank:
         self.eng.import_state(self.posm, self.vel, self.ids, self.n, self._stream())
         return self.eng.local_bounds()
 
+    def fix_cube(self, cube: np.ndarray):
+        self.cube = np.asarray(cube, f32).copy()
+        self.eng.set_fixed_bounds(self.cube)
+        self.geng.set_fixed_bounds(self.cube)
+
     # ---- ownership: splitter election and migration ------------------------------------------
-    def sort_own(self, cube: np.ndarray, by_work: bool = True):
-        """Fix the global cube, key + sort the own bodies.  Returns (SAMPLE sorted keys taken at equal increments
+    def sort_own(self, by_work: bool = True):
+        """Key + sort the own bodies (after fix_cube + local_box).  Returns (SAMPLE sorted keys taken at equal increments
         of the cumulative work the bodies carry in vel.w, total work); bodies without a measurement yet (first
         step) or by_work=False count 1 each."""
-        self.eng.set_fixed_bounds(cube)
         if self.n == 0:
             return np.zeros(SAMPLE, np.int64), 0.0
         torch, st = self.torch, self._stream()
-        self.eng.run_phase(PHASE.KEYS, st)                      # state imported by local_box()
-        self.eng.run_phase(PHASE.SORT, st)
+        self.eng.sort_coarse(st)                                # state imported by local_box(); 30-bit keys are enough here
         keys, _, vel, _ = self._sorted()
         work = vel[:, 3].double() + WORK_FLOOR if by_work else None
         if work is None or float(vel[:, 3].max().item()) <= 0.0:
@@ -233,7 +246,7 @@ class LetRank:
             self.eng.run_phase(ph, st)
 
     def domain_boxes(self, k_lo: int, k_hi: int) -> np.ndarray:
-        """[MAX_BOXES, 6] tight body AABBs of the octree-aligned key intervals of [k_lo, k_hi)."""
+        """[MAX_BOXES, 6] tight body AABBs of the octree-aligned key intervals of [k_lo, k_hi) (see domain_cuts)."""
         if self.n == 0:
             return np.tile(EMPTY_BOX, (MAX_BOXES, 1))
         boxes, counts = self.eng.let_domain_boxes(domain_cuts(k_lo, k_hi))
@@ -249,16 +262,16 @@ class LetRank:
         return self.eng.let_export(boxes, self.out, self.cap, self._stream())
 
     def ghost_slot(self, rows: int):
-        """View [rows,4] right behind the own bodies: imported points received there need no further copy."""
-        if self._n + rows > self.capacity:
-            raise self.bh.BHError(f"LET union of {self._n + rows} bodies exceeds the context capacity {self.capacity}")
-        return self._sets[self._cur][0][self._n: self._n + rows]
+        """View [rows,4] of the ghost buffer: imported points received there need no further copy."""
+        if rows > self.ghost_cap:
+            raise self.bh.BHError(f"{rows} imported points exceed the ghost capacity {self.ghost_cap}")
+        return self.gposm[:rows]
 
-    def union_step(self, received):
-        """received: list of [k,4] device tensors (point masses from the peers), or the number of points
-        already written to ghost_slot()."""
+    def forces_and_update(self, received):
+        """Forces on the own bodies from the local tree (built by build_local_tree) and from the imported
+        points, then kick-drift-clamp.  received: list of [k,4] device tensors (point masses from the peers), or
+        the number of points already written to ghost_slot()."""
         torch = self.torch
-        nl = self._n
         if isinstance(received, int):
             n_imp = received
         else:
@@ -267,23 +280,28 @@ class LetRank:
             for r in received:
                 slot[o: o + int(r.shape[0])].copy_(r)
                 o += int(r.shape[0])
-        nu = nl + n_imp
-        if nu == 0:
+        self.last = {"n_import": n_imp}
+        if self.n == 0:
             return
-        p, v, i = self._sets[self._cur]
-        v[nl:nu].zero_()
-        i[nl:nu].fill_(-1)
         st = self._stream()
         ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
         ev[0].record()
-        self.eng.import_state(p, v, i, nu, st)
-        self.eng.simulation_step(1, st)
+        self.eng.run_phase(PHASE.FORCE, st)
+        if n_imp > 0:
+            if n_imp == 1:                                      # a tree needs two bodies: split the point in two halves
+                self.gposm[1] = self.gposm[0]
+                self.gposm[:2, 3] *= 0.5
+                n_imp = 2
+            self.geng.import_state(self.gposm, self.gvel, self.gids, n_imp, st)
+            for ph in (PHASE.KEYS, PHASE.SORT, PHASE.BUILD, PHASE.COM):
+                self.geng.run_phase(ph, st)
+            self.eng.force_from(self.geng, st)
+        self.eng.run_phase(PHASE.UPDATE, st)
         ev[1].record()
-        self._ev = (ev[0], ev[1], nl)
-        sp, sv, si = self._sets[self._cur ^ 1]                  # drop the ghosts: own bodies, still in Morton order
+        self._ev = (ev[0], ev[1], self.n)
+        sp, sv, si = self._sets[self._cur ^ 1]                  # own bodies in Morton order, vel.w = the work they cost
         self._n = self.eng.export_real(sp, sv, si, st)
         self._cur ^= 1
-        self.last = {"n_union": nu, "n_import": n_imp}
 
     def last_union_ms(self) -> float:
         """Device time of the last union step (import + ordinary step); synchronises on its end event."""
@@ -301,6 +319,7 @@ class LetRank:
 
     def close(self):
         self.eng.close()
+        self.geng.close()
 
 
 def let_step_emulated(ranks, rebalance: bool = True):
@@ -309,7 +328,9 @@ def let_step_emulated(ranks, rebalance: bool = True):
     torch = ranks[0].torch
     world = len(ranks)
     cube = global_cube(np.stack([r.local_box() for r in ranks]))
-    sw = [r.sort_own(cube, rebalance) for r in ranks]
+    for r in ranks:
+        r.fix_cube(cube)
+    sw = [r.sort_own(rebalance) for r in ranks]
     edges = elect_splitters(np.stack([x[0] for x in sw]), np.array([x[1] for x in sw]))
     plans = [r.migration_plan(edges) for r in ranks]
     for dst, r in enumerate(ranks):
@@ -327,15 +348,16 @@ def let_step_emulated(ranks, rebalance: bool = True):
             new = [torch.empty((0, 4), dtype=torch.float32, device=r.device), torch.empty((0, 4), dtype=torch.float32, device=r.device),
                    torch.empty((0,), dtype=torch.int32, device=r.device)]
         r._new = new
-    for r in ranks:                                            # adopt only after every rank's runs were copied out
+    for r in ranks:                                        # adopt only after every rank's runs were copied out
         r.adopt(*r._new)
         del r._new
+    for r in ranks:
         r.build_local_tree()
     boxes = compact_boxes(np.stack([r.domain_boxes(int(edges[i]), int(edges[i + 1])) for i, r in enumerate(ranks)]))
     counts = [r.export(boxes, i) for i, r in enumerate(ranks)]
     sent = [[r.out[p, : int(counts[i][p])].clone() for p in range(world)] for i, r in enumerate(ranks)]
     for i, r in enumerate(ranks):
-        r.union_step([sent[s][i] for s in range(world) if s != i])
+        r.forces_and_update([sent[s][i] for s in range(world) if s != i])
     return counts, edges
 
 
@@ -349,6 +371,7 @@ class LetSimulation:
         self.torch, self.dist, self.rankno, self.world = torch, dist, rank, world
         self.device = torch.device(f"cuda:{local}")
         self.rebalance = rebalance
+        self.steps_done = 0
         px, py, pz, vx, vy, vz, m = local_soa
         n = len(px)
         posm = torch.from_numpy(np.stack([px, py, pz, m], 1).astype(f32)).to(self.device)
@@ -385,10 +408,10 @@ class LetSimulation:
             box = torch.from_numpy(self.rank.local_box()).to(self.device)
             boxes = torch.empty((w, 6), dtype=torch.float32, device=self.device)
             dist.all_gather_into_tensor(boxes, box)
-            cube = global_cube(boxes.cpu().numpy())
+            self.rank.fix_cube(global_cube(boxes.cpu().numpy()))
             t = self._mark("cube", t)
             # splitter election: every rank's work-spaced key sample + its total work
-            sample, work = self.rank.sort_own(cube, self.rebalance)
+            sample, work = self.rank.sort_own(self.rebalance)
             mine = torch.from_numpy(np.concatenate([sample.astype(np.float64), [work]])).to(self.device)
             pooled = torch.empty((w, SAMPLE + 1), dtype=torch.float64, device=self.device)
             dist.all_gather_into_tensor(pooled, mine)
@@ -426,8 +449,13 @@ class LetSimulation:
             n_imp = int(sum(rc))
             self._all_to_all_rows(send, sc, rc, (4,), torch.float32, out=self.rank.ghost_slot(n_imp))
             t = self._mark("exchange", t)
-            self.rank.union_step(n_imp)
-            t = self._mark("union step", t)
+            self.rank.forces_and_update(n_imp)
+            t = self._mark("forces+update", t)
+            self.steps_done += 1
+            if self.trace is not None:
+                self.trace_all = getattr(self, "trace_all", []) + [dict(self.trace)]
+                if "migrate" in self.trace:
+                    self.trace_migration_step = dict(self.trace)
             self.stats = {"exported": int(sum(sc)), "imported": int(sum(rc)), "n_local": self.rank.n, "migrated_out": migrated}
 
     def close(self):
@@ -483,7 +511,9 @@ def run_let_bench(args, w, bh, dist, rank, world, local):
         dist.barrier()
         torch.cuda.synchronize()
 
-    sim.step(args.warmup)
+    # the warm-up covers the first work-weighted election (start-up ownership -> equal counts -> equal work)
+    # and one step on the elected ranges
+    sim.step(max(args.warmup, 3))
     barrier()
     sim.rank.eng.check_device_error()
     clocks = bench.ClockSampler(local)
@@ -517,12 +547,15 @@ def run_let_bench(args, w, bh, dist, rank, world, local):
                    "softening": 50.0, "max_speed": 500.0, "group": 32, "key_bits": key_bits,
                    "parallelism": f"locally-essential-tree x{world}: work-weighted sampled key splitters, body migration, "
                                   "per-peer export walk against octree-aligned domain boxes, NCCL all-to-all of point "
-                                  "masses, ordinary step on own + imported bodies",
+                                  "masses, traversal of the own tree + of a small tree of the imported points",
                    "l2": "state far larger than L2; no flush between steps"},
         "interactions_per_body": float(inter.item()) / n, "interactions_per_s": float(inter.item()) * args.steps / (total_ms * 1e-3),
         "let_exported_imported_local_migrated_per_rank": [[int(x) for x in row[:4]] for row in stats_all.tolist()],
-        "union_step_ms_per_rank": [round(row[4], 3) for row in stats_all.tolist()],
+        "forces_update_ms_per_rank": [round(row[4], 3) for row in stats_all.tolist()],
         "trace_ms_rank0_last_step": {k: round(v, 3) for k, v in sim.trace.items()} if sim.trace is not None else None,
+        "trace_ms_rank0_step_totals": [round(sum(tr.values()), 2) for tr in getattr(sim, "trace_all", [])] or None,
+        "trace_ms_rank0_forces": [round(tr.get("forces+update", 0), 2) for tr in getattr(sim, "trace_all", [])] or None,
+        "trace_ms_rank0_last_migration_step": {k: round(v, 3) for k, v in getattr(sim, "trace_migration_step", {}).items()} or None,
         "wall_s_timed_loop": wall, "e2e": None, "gpu_launches": None, "clocks": ck,
     }
     dist.destroy_process_group()
