@@ -459,6 +459,40 @@ class LetSimulation:
                     self.trace_migration_step = dict(self.trace)
             self.stats = {"exported": int(sum(sc)), "imported": int(sum(rc)), "n_local": self.rank.n, "migrated_out": migrated}
 
+    def step_host(self, host):
+        """End-to-end step: the rank's bodies come from pinned HOST buffers and go back there.
+        host = dict(posm [cap,4] f32, vel [cap,4] f32, ids [cap] i32, n) — pinned tensors sized for the rank's
+        capacity; n bodies are valid.  Uploads them, takes one step (the rank may own different bodies
+        afterwards), downloads the new own bodies and updates host["n"].  Returns (h2d_bytes, d2h_bytes)."""
+        torch, r = self.torch, self.rank
+        n0 = int(host["n"])
+        tp, tv, ti = r.spare(n0)
+        tp.copy_(host["posm"][:n0], non_blocking=True)
+        tv.copy_(host["vel"][:n0], non_blocking=True)
+        ti.copy_(host["ids"][:n0], non_blocking=True)
+        r.adopt(tp, tv, ti)
+        self.step(1)
+        n1 = r.n
+        host["posm"][:n1].copy_(r.posm, non_blocking=True)
+        host["vel"][:n1].copy_(r.vel, non_blocking=True)
+        host["ids"][:n1].copy_(r.ids, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        host["n"] = n1
+        return 36 * n0, 36 * n1
+
+    def host_buffers(self):
+        """Pinned host mirror of the rank's bodies for step_host."""
+        torch, r = self.torch, self.rank
+        cap = r.capacity
+        host = {"posm": torch.empty((cap, 4), dtype=torch.float32).pin_memory(),
+                "vel": torch.empty((cap, 4), dtype=torch.float32).pin_memory(),
+                "ids": torch.empty((cap,), dtype=torch.int32).pin_memory(), "n": r.n}
+        host["posm"][: r.n].copy_(r.posm)
+        host["vel"][: r.n].copy_(r.vel)
+        host["ids"][: r.n].copy_(r.ids)
+        torch.cuda.synchronize()
+        return host
+
     def close(self):
         self.rank.close()
 
@@ -479,6 +513,16 @@ def _morton30_numpy(px, py, pz, cube):
         return v
 
     return (spread(q(px, cube[0])) << np.uint32(2)) | (spread(q(py, cube[1])) << np.uint32(1)) | spread(q(pz, cube[2]))
+
+
+def launches_per_let_step(key_bits: int) -> int:
+    """This library's kernel launches in one LET step of one rank that received imports (torch's and NCCL's own
+    kernels not counted): bounds 3, coarse election sort 8, local tree (keys, sort, reorder, tree 5, com), domain
+    boxes 3, export walk (seed + one per level), force 2, ghost tree, cross-tree force 2, update 1, compaction 3."""
+    levels = key_bits // 3
+    sort = 6 if key_bits == 30 else 14        # histogram + scan + 4 passes; twice + gather + combine for 60 bits
+    tree = 1 + sort + 1 + 5 + 1
+    return 3 + 8 + tree + 3 + (1 + levels + 1) + 2 + tree + 2 + 1 + 3
 
 
 def run_let_bench(args, w, bh, dist, rank, world, local):
@@ -538,6 +582,28 @@ def run_let_bench(args, w, bh, dist, rank, world, local):
                        float(sim.stats["migrated_out"]), sim.rank.last_union_ms()], device=dev, dtype=torch.float64)
     stats_all = torch.empty((world, 5), dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(stats_all, st)
+    # ---- e2e: every rank's bodies come from pinned host memory and go back there, every step
+    e2e = None
+    if not getattr(args, "no_e2e", False):
+        host = sim.host_buffers()
+        esteps = max(3, min(args.steps, 5))
+        sim.step_host(host)
+        barrier()
+        t1 = time.perf_counter()
+        nbytes = [0, 0]
+        for _ in range(esteps):
+            hb, db = sim.step_host(host)
+            nbytes[0] += hb; nbytes[1] += db
+        barrier()
+        e2e_s = torch.tensor([(time.perf_counter() - t1) / esteps], device=dev, dtype=torch.float64)
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+        tot = torch.tensor([float(nbytes[0]), float(nbytes[1])], device=dev, dtype=torch.float64)
+        dist.all_reduce(tot)
+        e2e = {"value": n / float(e2e_s.item()), "unit": "body-steps/s", "h2d_bytes_per_step": int(tot[0].item() / esteps),
+               "d2h_bytes_per_step": int(tot[1].item() / esteps), "ms_per_step": float(e2e_s.item()) * 1e3,
+               "api": "LetSimulation.step_host: each rank uploads its own bodies (posm, vel, ids: 36 B/body) from pinned "
+                      "host memory, one LET step, downloads the bodies it owns afterwards"}
+        del host
     sim.close()
     total_ms = float(ms.item())
     line = {
@@ -557,7 +623,8 @@ def run_let_bench(args, w, bh, dist, rank, world, local):
         "trace_ms_rank0_step_totals": [round(sum(tr.values()), 2) for tr in getattr(sim, "trace_all", [])] or None,
         "trace_ms_rank0_forces": [round(tr.get("forces+update", 0), 2) for tr in getattr(sim, "trace_all", [])] or None,
         "trace_ms_rank0_last_migration_step": {k: round(v, 3) for k, v in getattr(sim, "trace_migration_step", {}).items()} or None,
-        "wall_s_timed_loop": wall, "e2e": None, "gpu_launches": None, "clocks": ck,
+        "wall_s_timed_loop": wall, "e2e": e2e, "gpu_launches": launches_per_let_step(key_bits) * args.steps,
+        "clocks": ck,
     }
     dist.destroy_process_group()
     return line if rank == 0 else None
