@@ -10,10 +10,11 @@ import nbody_barnes_hut_cuda_b200 as bh  # noqa: E402
 
 runs = [("uniform_16k", bench.WORKLOADS["uniform_16k"]), ("plummer_64k", dict(n=65536, ic="plummer", desc="Plummer a=200 cut 10a")),
         ("refdisk_100k", dict(n=100_000, ic="refdisk", desc="reference disk"))]
-out = {}
+key_bits = int(sys.argv[1]) if len(sys.argv) > 1 else 30
+out = {"key_bits": key_bits}
 for name, w in runs:
     soa = bench.make_ic(bh, w)
-    eng = bh.BHEngine(w["n"])
+    eng = bh.BHEngine(w["n"], key_bits=key_bits)
     eng.load_soa(*soa)
     ke0, pe0 = eng.energy()
     e0 = ke0 + pe0
