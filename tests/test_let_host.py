@@ -150,3 +150,52 @@ def test_two_rank_election_and_migration_over_gloo():
     assert res[0][2] + res[1][2] == 5000 + 8000                # no body lost or duplicated
     assert res[0][3] and res[1][3]                             # every received key lies in the receiver's range
     assert abs(res[0][2] - res[1][2]) < 0.03 * 13000           # equal counts at unit cost
+
+
+@pytest.mark.parametrize("kind", ["uniform", "disk"])
+def test_export_oracle_properties_on_oracle_trees(orc, kind):
+    """The CPU statement of the export rule on trees the oracle itself builds: the emitted points always carry
+    the whole mass, every emitted cell passes the acceptance test at the peer's nearest box, a peer far away
+    receives the root alone, and a peer box on top of the bodies receives (almost) every body individually."""
+    import nbody_barnes_hut_cuda_b200 as bh
+
+    n = 1500
+    soa = bh.ic_uniform_cube(n, 3, 1000.0) if kind == "uniform" else bh.ic_refdisk(n, 3)
+    posm, _, _ = orc.soa_to_internal(soa)
+    b = orc.bounds(*soa[:3])
+    keys, idx = orc.morton_keys(*soa[:3], b)
+    ks, perm = orc.stable_sort(keys, idx)
+    ps = np.ascontiguousarray(posm[perm])
+    meta, child, root = orc.tree_build(ks)
+    _, com = orc.tree_com(ps, meta, child, root)
+    meta_l = meta.copy()
+    meta_l[:, 2] &= 0x1FF
+    root_w = float(b[3] - b[0])
+    total = ps[:, 3].astype(np.float64).sum()
+    lo, hi = ps[:, :3].min(0), ps[:, :3].max(0)
+    ext = hi - lo
+    cells = {tuple(c.tolist()): int(m[2]) & 0xFF for c, m in zip(com, meta_l)}
+    bodies = set(map(tuple, ps.tolist()))
+    for name, boxes in (("far", [np.concatenate([hi + 60 * ext, hi + 61 * ext])]),
+                        ("near", [np.concatenate([hi + 0.05 * ext, hi + 0.4 * ext]), np.concatenate([lo - 0.4 * ext, lo - 0.05 * ext])]),
+                        ("inside", [np.concatenate([lo, hi])])):
+        pts = orc.let_export_points(meta_l, child, com, ps, root, np.array(boxes, np.float32), root_w)
+        assert abs(pts[:, 3].astype(np.float64).sum() - total) < 1e-5 * total, name
+        if name == "far":
+            assert len(pts) == 1 and tuple(pts[0].tolist()) == tuple(com[root].tolist())
+        n_cells = 0
+        for p in pts:
+            t = tuple(p.tolist())
+            if t in bodies:
+                continue
+            assert t in cells, name                        # everything else is a cell's {com, mass}
+            n_cells += 1
+            c = np.array(boxes, np.float64)
+            d = np.maximum(0.0, np.maximum(c[:, :3] - p[:3], p[:3] - c[:, 3:]))
+            d2 = (d * d).sum(1).min()
+            w = root_w / 2.0 ** cells[t]
+            assert w * w < 0.25 * (d2 + 50.0) * (1 + 1e-5), name
+        if name == "inside":
+            # a box over everything: only cells narrower than theta*sqrt(SOFTENING) = 3.5 survive as monopoles
+            assert all(root_w / 2.0 ** cells[tuple(p.tolist())] < 3.54 for p in pts if tuple(p.tolist()) not in bodies)
+            assert len(pts) > 0.9 * n
