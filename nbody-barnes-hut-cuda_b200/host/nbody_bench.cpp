@@ -6,8 +6,8 @@
 // prints: per-phase times, transfer timings, body-steps/s and interactions/s.  Options replace the
 // reference's edit-and-recompile knobs (N is a global at bench:31, 1000 frames at bench:353).
 //
-//   nbody_bench [--n N] [--frames F] [--ic refdisk|uniform|plummer] [--theta T] [--quiet]
-//               [--phases] [--dump out.txt] [--save ckpt.bin] [--resume ckpt.bin]
+//   nbody_bench [--n N] [--frames F] [--ic refdisk|uniform|plummer|twodisk] [--theta T] [--key-bits 30|60]
+//               [--quiet] [--phases] [--dump out.txt] [--save ckpt.bin] [--resume ckpt.bin]
 #include <cuda_runtime.h>
 
 #include <cstdio>
@@ -26,7 +26,7 @@ static void die(const char* what, int code) {
 
 int main(int argc, char** argv) {
     long long n = 1000000;   // README.md:23 (the code's global says 500000, bench:31)
-    int frames = 100, quiet = 0, phases = 0;
+    int frames = 100, quiet = 0, phases = 0, key_bits = 30;
     float theta = 0.5f;
     std::string ic = "refdisk", dump, save, resume;
     for (int i = 1; i < argc; ++i) {
@@ -36,6 +36,7 @@ int main(int argc, char** argv) {
         else if (a == "--frames") frames = atoi(next());
         else if (a == "--ic") ic = next();
         else if (a == "--theta") theta = (float)atof(next());
+        else if (a == "--key-bits") key_bits = atoi(next());
         else if (a == "--quiet") quiet = 1;
         else if (a == "--phases") phases = 1;
         else if (a == "--dump") dump = next();
@@ -48,6 +49,7 @@ int main(int argc, char** argv) {
     bh_params p;
     bh_default_params(&p);
     p.theta = theta;
+    p.key_bits = key_bits;   // 60: the reference key + 10 more bits per axis (deep trees for > 10^7 bodies)
     if (phases) p.flags |= BH_FLAG_PHASE_TIMER;
     bh_ctx* ctx = nullptr;
     CHECK(bh_create(&ctx, n, &p, 0));
@@ -64,6 +66,7 @@ int main(int argc, char** argv) {
         if (ic == "refdisk") CHECK(bh_ic_refdisk(n, 42, a[0].data(), a[1].data(), a[2].data(), a[3].data(), a[4].data(), a[5].data(), a[6].data()));
         else if (ic == "uniform") CHECK(bh_ic_uniform_cube(n, 42, 1000.0f, a[0].data(), a[1].data(), a[2].data(), a[3].data(), a[4].data(), a[5].data(), a[6].data()));
         else if (ic == "plummer") CHECK(bh_ic_plummer(n, 42, 200.0f, 10.0f, 4.5f, 0.5f, a[0].data(), a[1].data(), a[2].data(), a[3].data(), a[4].data(), a[5].data(), a[6].data()));
+        else if (ic == "twodisk") CHECK(bh_ic_two_disks(n, 42, 4000.0f, 20.0f, 8.0f, a[0].data(), a[1].data(), a[2].data(), a[3].data(), a[4].data(), a[5].data(), a[6].data()));
         else { fprintf(stderr, "unknown --ic %s\n", ic.c_str()); return 2; }
         cudaEventRecord(start);
         CHECK(bh_import_soa_host(ctx, a[0].data(), a[1].data(), a[2].data(), a[3].data(), a[4].data(), a[5].data(), a[6].data(), n));
