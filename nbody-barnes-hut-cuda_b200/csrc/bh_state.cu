@@ -87,7 +87,9 @@ __device__ __forceinline__ uint32_t spread10(uint32_t v) {  // bench:42-49 bit s
 
 __device__ __forceinline__ uint32_t quantise(float p, float lo, float size) {
     // bench:58 — IEEE divide, multiply by 1023.0f (not 1024: SURVEY F5), truncate to u32
-    return __float2uint_rz(__fmul_rn(__fdiv_rn(__fsub_rn(p, lo), size), 1023.0f));
+    // min(.,1023): a no-op for the reference's own cube (p <= min+size), it keeps the key on the grid when a
+    // fixed cube (bh_set_fixed_bounds) is momentarily too small for a body
+    return min(__float2uint_rz(__fmul_rn(__fdiv_rn(__fsub_rn(p, lo), size), 1023.0f)), 1023u);
 }
 
 __global__ void __launch_bounds__(kThreads) keys_kernel(const float4* __restrict__ posm, int64_t n,
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(kThreads) keys_kernel(const float4* __restrict
 // order without ever contradicting it.
 __device__ __forceinline__ void quantise2(float p, float lo, float size, uint32_t& q, uint32_t& fr) {
     const float t = __fmul_rn(__fdiv_rn(__fsub_rn(p, lo), size), 1023.0f);
-    q = __float2uint_rz(t);
+    q = min(__float2uint_rz(t), 1023u);
     const float g = __fmul_rn(__fsub_rn(t, __uint2float_rn(q)), 1024.0f);
     fr = !(g > 0.0f) ? 0u : (g >= 1023.0f ? 1023u : __float2uint_rz(g));
 }

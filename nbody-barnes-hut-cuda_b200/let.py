@@ -9,9 +9,12 @@ Each rank owns the bodies of one Morton-key range and never sees the others' bod
              taken at equal increments of its cumulative work; the weighted quantiles of the pooled sample
              are the new key ranges (SURVEY §8e "sampled key splitters") — equal WORK, not equal count;
   migrate    the bodies that left the rank's range are runs of its sorted order: one all-to-all;
-             (every step: a body outside its owner's key range would have to be covered by a box that is no
-             longer a run of whole cells — measured: boxes around such strays span the domain faces and the
-             export lists overflow)
+             (cube, election and migration run every INTERVAL steps, on a cube enlarged by the distance a body
+             can travel in that time so that the key grid — and with it the meaning of a key range — stays put;
+             in between a rank keeps its bodies, and the few that crossed out of its key range ("strays", at
+             the two ends of its sorted order) are added to the NEAREST of its boxes.  Putting them into boxes
+             of their own key intervals does not work: those are no longer runs of whole cells, they span the
+             domain faces and the export lists overflow — measured.)
   local tree keys, sort, tree, centre of mass over the rank's own bodies;
   domain     the key range is cut at octree-cell boundaries (domain_cuts) and described by the tight body
              AABB of every interval (bh_let_domain_boxes) — a key range is not convex, whole cells are;
@@ -39,6 +42,7 @@ KEY_END = 1 << 30      # one past the largest 30-bit key
 SAMPLE = 4096          # keys every rank contributes to the splitter election
 WORK_FLOOR = 300.0     # added to every body's measured work: the per-body cost of the non-traversal phases in units of
                        # list entries (256M two-disc on 8 GPUs: ~10 ms of sort+tree per 27M bodies vs 1.1 ps per entry)
+INTERVAL = 4           # steps between cube / election / migration rounds
 MAX_BOXES = 200        # boxes that describe one rank's domain (<= BH_LET_MAX_BOXES)
 EMPTY_BOX = np.array([1, 1, 1, -1, -1, -1], f32)   # lo > hi
 
@@ -51,6 +55,14 @@ def global_cube(boxes_lohi: np.ndarray) -> np.ndarray:
     hi = b[:, 3:].max(0).astype(f32)
     ext = (hi - lo).astype(f32)
     size = f32(max(ext[0], max(ext[1], ext[2])))
+    return np.array([lo[0], lo[1], lo[2], f32(lo[0] + size), f32(lo[1] + size), f32(lo[2] + size)], f32)
+
+
+def expand_cube(cube: np.ndarray, margin: float) -> np.ndarray:
+    """The cube grown by `margin` on every side (bodies may move that far before the next election)."""
+    c = np.asarray(cube, f32)
+    lo = (c[:3] - f32(margin)).astype(f32)
+    size = f32(f32(c[3] - c[0]) + f32(2.0) * f32(margin))
     return np.array([lo[0], lo[1], lo[2], f32(lo[0] + size), f32(lo[1] + size), f32(lo[2] + size)], f32)
 
 
@@ -239,6 +251,7 @@ class LetRank:
 
     # ---- local tree, domain description, export ----------------------------------------------
     def build_local_tree(self):
+        self.last = {}
         if self.n == 0:
             return
         st = self._stream()
@@ -246,13 +259,44 @@ class LetRank:
         for ph in (PHASE.KEYS, PHASE.SORT, PHASE.BUILD, PHASE.COM):
             self.eng.run_phase(ph, st)
 
+    def travel_margin(self, steps: int) -> float:
+        """How far a body can get in `steps` steps (speed clamp x dt): the cube is enlarged by this much."""
+        return float(self.eng.params.max_speed) * float(self.eng.params.dt) * steps
+
     def domain_boxes(self, k_lo: int, k_hi: int) -> np.ndarray:
-        """[MAX_BOXES, 6] tight body AABBs of the octree-aligned key intervals of [k_lo, k_hi) (see domain_cuts)."""
+        """[MAX_BOXES, 6] tight body AABBs of the octree-aligned key intervals of [k_lo, k_hi) (see domain_cuts);
+        own bodies whose key left the range since the last migration are added to the nearest box."""
         if self.n == 0:
             return np.tile(EMPTY_BOX, (MAX_BOXES, 1))
         boxes, counts = self.eng.let_domain_boxes(domain_cuts(k_lo, k_hi))
-        assert int(counts.sum()) == self.n, "own bodies outside the own key range"
+        if int(counts.sum()) != self.n:
+            self._add_strays(boxes, counts, k_lo)
         return boxes
+
+    def _add_strays(self, boxes: np.ndarray, counts: np.ndarray, k_lo: int):
+        """The bodies outside [k_lo, k_hi) are the two end runs of the sorted order; each one extends the box it is
+        nearest to (they crossed a face of the domain a few steps ago, so that box hardly grows)."""
+        torch, dev = self.torch, self.device
+        keys, posm, _, _ = self._sorted()
+        a = int(torch.searchsorted(keys, torch.tensor([k_lo], dtype=torch.int32, device=dev)).item())
+        b = a + int(counts.sum())
+        strays = torch.cat([posm[:a, :3], posm[b:, :3]])
+        used = np.nonzero(counts > 0)[0]
+        self.last["strays"] = int(strays.shape[0])
+        if len(used) == 0:                                      # everything strayed: one box around all of it
+            boxes[0, :3] = strays.amin(0).cpu().numpy()
+            boxes[0, 3:] = strays.amax(0).cpu().numpy()
+            return
+        B = torch.from_numpy(boxes[used]).to(dev)
+        lo, hi = B[:, :3].clone(), B[:, 3:].clone()
+        for c0 in range(0, int(strays.shape[0]), 16384):
+            sc = strays[c0:c0 + 16384]
+            d = torch.clamp(torch.maximum(B[None, :, :3] - sc[:, None, :], sc[:, None, :] - B[None, :, 3:]), min=0)
+            idx = (d * d).sum(2).argmin(1)[:, None].expand(-1, 3)
+            lo.scatter_reduce_(0, idx, sc, "amin", include_self=True)
+            hi.scatter_reduce_(0, idx, sc, "amax", include_self=True)
+        boxes[used, :3] = lo.cpu().numpy()
+        boxes[used, 3:] = hi.cpu().numpy()
 
     def export(self, boxes_lohi: np.ndarray, me: int) -> np.ndarray:
         """boxes_lohi: [world, K, 6].  Returns the number of points emitted for every peer."""
@@ -281,7 +325,7 @@ class LetRank:
             for r in received:
                 slot[o: o + int(r.shape[0])].copy_(r)
                 o += int(r.shape[0])
-        self.last = {"n_import": n_imp}
+        self.last["n_import"] = n_imp
         if self.n == 0:
             return
         st = self._stream()
@@ -323,35 +367,39 @@ class LetRank:
         self.geng.close()
 
 
-def let_step_emulated(ranks, rebalance: bool = True):
+def let_step_emulated(ranks, rebalance: bool = True, elect: bool = True, edges=None, margin: float = 0.0):
     """One LET step of several LetRank objects living on one device; the all-to-alls are list shuffles.
+    elect=False: no cube / election / migration — the ranks keep their bodies, the cube and `edges` of the last
+    election step (which must have used a margin that covers the travel since).
     Returns (export counts per rank, key-range edges)."""
     torch = ranks[0].torch
     world = len(ranks)
-    cube = global_cube(np.stack([r.local_box() for r in ranks]))
-    for r in ranks:
-        r.fix_cube(cube)
-    sw = [r.sort_own(rebalance) for r in ranks]
-    edges = elect_splitters(np.stack([x[0] for x in sw]), np.array([x[1] for x in sw]))
-    plans = [r.migration_plan(edges) for r in ranks]
-    for dst, r in enumerate(ranks):
-        parts = [[], [], []]
-        for src in range(world):
-            sc, views = plans[src]
-            if views is None or sc[dst] == 0:
-                continue
-            a = int(sc[:dst].sum())
-            for k in range(3):
-                parts[k].append(views[k][a:a + int(sc[dst])].clone())
-        if parts[0]:
-            new = [torch.cat(p) for p in parts]
-        else:
-            new = [torch.empty((0, 4), dtype=torch.float32, device=r.device), torch.empty((0, 4), dtype=torch.float32, device=r.device),
-                   torch.empty((0,), dtype=torch.int32, device=r.device)]
-        r._new = new
-    for r in ranks:                                        # adopt only after every rank's runs were copied out
-        r.adopt(*r._new)
-        del r._new
+    if elect:
+        cube = expand_cube(global_cube(np.stack([r.local_box() for r in ranks])), margin)
+        for r in ranks:
+            r.fix_cube(cube)
+        sw = [r.sort_own(rebalance) for r in ranks]
+        edges = elect_splitters(np.stack([x[0] for x in sw]), np.array([x[1] for x in sw]))
+        plans = [r.migration_plan(edges) for r in ranks]
+        for dst, r in enumerate(ranks):
+            parts = [[], [], []]
+            for src in range(world):
+                sc, views = plans[src]
+                if views is None or sc[dst] == 0:
+                    continue
+                a = int(sc[:dst].sum())
+                for k in range(3):
+                    parts[k].append(views[k][a:a + int(sc[dst])].clone())
+            if parts[0]:
+                new = [torch.cat(p) for p in parts]
+            else:
+                new = [torch.empty((0, 4), dtype=torch.float32, device=r.device), torch.empty((0, 4), dtype=torch.float32, device=r.device),
+                       torch.empty((0,), dtype=torch.int32, device=r.device)]
+            r._new = new
+        for r in ranks:                                        # adopt only after every rank's runs were copied out
+            r.adopt(*r._new)
+            del r._new
+    assert edges is not None, "a step without election needs the edges of the last election"
     for r in ranks:
         r.build_local_tree()
     boxes = compact_boxes(np.stack([r.domain_boxes(int(edges[i]), int(edges[i + 1])) for i, r in enumerate(ranks)]))
@@ -366,13 +414,13 @@ class LetSimulation:
     """torch.distributed driver: one process per GPU, NCCL all-gather of boxes and all-to-all of point lists."""
 
     def __init__(self, bh, local_soa, local_ids, rank: int, world: int, local: int, dist, capacity: int,
-                 cap_per_peer: int, rebalance: bool = True, **params):
+                 cap_per_peer: int, rebalance: bool = True, interval: int = INTERVAL, **params):
         import torch
 
         self.torch, self.dist, self.rankno, self.world = torch, dist, rank, world
         self.device = torch.device(f"cuda:{local}")
-        self.rebalance = rebalance
-        self.steps_done = 0
+        self.rebalance, self.interval = rebalance, max(1, int(interval))
+        self.steps_done, self.edges = 0, None
         px, py, pz, vx, vy, vz, m = local_soa
         n = len(px)
         posm = torch.from_numpy(np.stack([px, py, pz, m], 1).astype(f32)).to(self.device)
@@ -405,34 +453,38 @@ class LetSimulation:
                 self.trace.clear()
                 torch.cuda.synchronize()
             t = time.perf_counter()
-            # global cube
-            box = torch.from_numpy(self.rank.local_box()).to(self.device)
-            boxes = torch.empty((w, 6), dtype=torch.float32, device=self.device)
-            dist.all_gather_into_tensor(boxes, box)
-            self.rank.fix_cube(global_cube(boxes.cpu().numpy()))
-            t = self._mark("cube", t)
-            # splitter election: every rank's work-spaced key sample + its total work
-            sample, work = self.rank.sort_own(self.rebalance)
-            mine = torch.from_numpy(np.concatenate([sample.astype(np.float64), [work]])).to(self.device)
-            pooled = torch.empty((w, SAMPLE + 1), dtype=torch.float64, device=self.device)
-            dist.all_gather_into_tensor(pooled, mine)
-            pooled = pooled.cpu().numpy()
-            edges = elect_splitters(pooled[:, :SAMPLE].astype(np.int64), pooled[:, SAMPLE])
-            t = self._mark("sort+elect", t)
-            # migration: runs of the sorted order
-            sc_np, views = self.rank.migration_plan(edges)
-            send_counts = torch.from_numpy(sc_np).to(self.device)
-            recv_counts = torch.empty_like(send_counts)
-            dist.all_to_all_single(recv_counts, send_counts)
-            sc, rc = sc_np.tolist(), recv_counts.cpu().numpy().tolist()
-            migrated = int(sum(sc)) - int(sc[me])
-            v = views if views is not None else (None, None, None)
-            tp, tv, ti = self.rank.spare(int(sum(rc)))
-            self._all_to_all_rows(v[0], sc, rc, (4,), torch.float32, out=tp)
-            self._all_to_all_rows(v[1], sc, rc, (4,), torch.float32, out=tv)
-            self._all_to_all_rows(v[2], sc, rc, (), torch.int32, out=ti)
-            self.rank.adopt(tp, tv, ti)
-            t = self._mark("migrate", t)
+            migrated = 0
+            if self.steps_done % self.interval == 0:
+                # global cube, enlarged by what a body can travel before the next election
+                box = torch.from_numpy(self.rank.local_box()).to(self.device)
+                boxes = torch.empty((w, 6), dtype=torch.float32, device=self.device)
+                dist.all_gather_into_tensor(boxes, box)
+                margin = self.rank.travel_margin(self.interval) if self.interval > 1 else 0.0
+                self.rank.fix_cube(expand_cube(global_cube(boxes.cpu().numpy()), margin))
+                t = self._mark("cube", t)
+                # splitter election: every rank's work-spaced key sample + its total work
+                sample, work = self.rank.sort_own(self.rebalance)
+                mine = torch.from_numpy(np.concatenate([sample.astype(np.float64), [work]])).to(self.device)
+                pooled = torch.empty((w, SAMPLE + 1), dtype=torch.float64, device=self.device)
+                dist.all_gather_into_tensor(pooled, mine)
+                pooled = pooled.cpu().numpy()
+                self.edges = elect_splitters(pooled[:, :SAMPLE].astype(np.int64), pooled[:, SAMPLE])
+                t = self._mark("sort+elect", t)
+                # migration: runs of the sorted order
+                sc_np, views = self.rank.migration_plan(self.edges)
+                send_counts = torch.from_numpy(sc_np).to(self.device)
+                recv_counts = torch.empty_like(send_counts)
+                dist.all_to_all_single(recv_counts, send_counts)
+                sc, rc = sc_np.tolist(), recv_counts.cpu().numpy().tolist()
+                migrated = int(sum(sc)) - int(sc[me])
+                v = views if views is not None else (None, None, None)
+                tp, tv, ti = self.rank.spare(int(sum(rc)))
+                self._all_to_all_rows(v[0], sc, rc, (4,), torch.float32, out=tp)
+                self._all_to_all_rows(v[1], sc, rc, (4,), torch.float32, out=tv)
+                self._all_to_all_rows(v[2], sc, rc, (), torch.int32, out=ti)
+                self.rank.adopt(tp, tv, ti)
+                t = self._mark("migrate", t)
+            edges = self.edges
             # local tree, domain boxes, export
             self.rank.build_local_tree()
             t = self._mark("local tree", t)
@@ -457,7 +509,8 @@ class LetSimulation:
                 self.trace_all = getattr(self, "trace_all", []) + [dict(self.trace)]
                 if "migrate" in self.trace:
                     self.trace_migration_step = dict(self.trace)
-            self.stats = {"exported": int(sum(sc)), "imported": int(sum(rc)), "n_local": self.rank.n, "migrated_out": migrated}
+            self.stats = {"exported": int(sum(sc)), "imported": int(sum(rc)), "n_local": self.rank.n, "migrated_out": migrated,
+                          "strays": self.rank.last.get("strays", 0)}
 
     def step_host(self, host):
         """End-to-end step: the rank's bodies come from pinned HOST buffers and go back there.
@@ -549,7 +602,8 @@ def run_let_bench(args, w, bh, dist, rank, world, local):
     # work-balanced key ranges may hold up to ~2x the mean body count; imports come on top
     sim = LetSimulation(bh, local_soa, sel, rank, world, local, dist,
                         capacity=int(2.2 * n / world) + (world - 1) * cap_peer // 2 + 4096, cap_per_peer=cap_peer,
-                        rebalance=not getattr(args, "let_no_rebalance", False), key_bits=key_bits)
+                        rebalance=not getattr(args, "let_no_rebalance", False),
+                        interval=getattr(args, "let_interval", None) or INTERVAL, key_bits=key_bits)
     dev = sim.device
 
     def barrier():
@@ -557,8 +611,10 @@ def run_let_bench(args, w, bh, dist, rank, world, local):
         torch.cuda.synchronize()
 
     # the warm-up covers the first work-weighted election (start-up ownership -> equal counts -> equal work)
-    # and one step on the elected ranges
-    sim.step(max(args.warmup, 3))
+    # and one step on the elected ranges; the timed steps start on an election step
+    sim.step(max(args.warmup, sim.interval + 1))
+    while sim.steps_done % sim.interval:
+        sim.step(1)
     barrier()
     sim.rank.eng.check_device_error()
     clocks = bench.ClockSampler(local)
@@ -612,12 +668,14 @@ def run_let_bench(args, w, bh, dist, rank, world, local):
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "desc": w["desc"], "n_bodies": n, "theta": 0.5, "G": 0.5, "dt": 0.02,
                    "softening": 50.0, "max_speed": 500.0, "group": 32, "key_bits": key_bits,
+                   "let_interval": sim.interval,
                    "parallelism": f"locally-essential-tree x{world}: work-weighted sampled key splitters, body migration, "
                                   "per-peer export walk against octree-aligned domain boxes, NCCL all-to-all of point "
                                   "masses, traversal of the own tree + of a small tree of the imported points",
                    "l2": "state far larger than L2; no flush between steps"},
         "interactions_per_body": float(inter.item()) / n, "interactions_per_s": float(inter.item()) * args.steps / (total_ms * 1e-3),
         "let_exported_imported_local_migrated_per_rank": [[int(x) for x in row[:4]] for row in stats_all.tolist()],
+        "strays_rank0_last_step": int(sim.stats.get("strays", 0)),
         "forces_update_ms_per_rank": [round(row[4], 3) for row in stats_all.tolist()],
         "trace_ms_rank0_last_step": {k: round(v, 3) for k, v in sim.trace.items()} if sim.trace is not None else None,
         "trace_ms_rank0_step_totals": [round(sum(tr.values()), 2) for tr in getattr(sim, "trace_all", [])] or None,
