@@ -341,6 +341,7 @@ def main():
                     help="Morton key width (bh_params.key_bits); default 30 = the reference key, 60 above 100M bodies")
     ap.add_argument("--let-interval", type=int, default=None, help="LET mode: steps between cube/election/migration rounds")
     ap.add_argument("--let-no-rebalance", action="store_true", help="LET mode: equal-count key ranges instead of equal work")
+    ap.add_argument("--no-e2e", action="store_true", help="LET mode: skip the host-buffer leg")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scale-ref", action="store_true", help="skip the 16M-body single-GPU reference point")
     args = ap.parse_args()
