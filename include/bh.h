@@ -197,16 +197,22 @@ int  bh_state_ptrs(bh_ctx* ctx, void** posm, void** vel, void** ids,
                    int64_t* n, int64_t* slice_first, int64_t* slice_count);
 
 /* ---- multi-GPU: locally-essential-tree exchange (north_star) -----
- * For body counts that are not replicated on every GPU.  A rank owns a subset of the bodies; per step it
+ * For body counts that are not replicated on every GPU.  A rank owns the bodies of one Morton-key range;
+ *   every few steps it
  *   1. agrees on the global bounding cube with its peers and fixes it (bh_set_fixed_bounds) so that every
  *      rank's Morton keys live on the same grid,
- *   2. builds the tree of its OWN bodies (bh_run_phase KEYS..COM),
- *   3. walks that tree once per peer against the peer's domain box (bh_let_export): the coarsest point
- *      masses — accepted cells' {centre of mass, mass}, loose bodies, bodies of rejected buckets — that may
- *      stand in for this rank's bodies anywhere inside that box,
- *   4. exchanges those lists, merges what it received (ids = -1) with its own bodies (bh_import_state) and
- *      runs an ordinary bh_step on the union; imported points are dropped afterwards.
- * nbody-barnes-hut-cuda_b200/let.py is the torch.distributed driver.                                    */
+ *   2. sorts its bodies by the 30-bit key (bh_sort_coarse), takes part in the election of new key ranges
+ *      (equal measured work) and hands the end runs of its sorted order (bh_sorted_ptrs) to their new owners;
+ *   every step it
+ *   3. builds the tree of its OWN bodies (bh_import_state, bh_run_phase KEYS..COM),
+ *   4. describes its domain by the tight boxes of octree-aligned key intervals (bh_let_domain_boxes),
+ *   5. walks its tree once per peer against the peer's boxes (bh_let_export): the coarsest point masses —
+ *      accepted cells' {centre of mass, mass}, loose bodies, bodies of rejected buckets — that may stand in
+ *      for this rank's bodies anywhere inside those boxes,
+ *   6. exchanges those lists, gives what it received a small tree in a second context on the same cube, and
+ *      traverses both trees with its body groups (BH_PHASE_FORCE, then bh_force_from), then BH_PHASE_UPDATE
+ *      and bh_export_real.
+ * nbody-barnes-hut-cuda_b200/let.py is the torch.distributed driver; DESIGN.md §6 has the measurements.   */
 /* Use this cube instead of computing one from the state (NULL switches back).  b = d_bounds layout
  * (min xyz, min+size xyz; nbody_v5_bench.cu:149-154).                                                  */
 int  bh_set_fixed_bounds(bh_ctx* ctx, const float b[6]);

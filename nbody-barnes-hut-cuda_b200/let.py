@@ -348,8 +348,8 @@ class LetRank:
         self._n = self.eng.export_real(sp, sv, si, st)
         self._cur ^= 1
 
-    def last_union_ms(self) -> float:
-        """Device time of the last union step (import + ordinary step); synchronises on its end event."""
+    def last_forces_ms(self) -> float:
+        """Device time of the last forces_and_update (both traversals, ghost tree, update); synchronises on its end event."""
         if self._ev is None:
             return 0.0
         self._ev[1].synchronize()
@@ -635,7 +635,7 @@ def run_let_bench(args, w, bh, dist, rank, world, local):
                          dtype=torch.float64)
     dist.all_reduce(inter)
     st = torch.tensor([float(sim.stats["exported"]), float(sim.stats["imported"]), float(sim.stats["n_local"]),
-                       float(sim.stats["migrated_out"]), sim.rank.last_union_ms()], device=dev, dtype=torch.float64)
+                       float(sim.stats["migrated_out"]), sim.rank.last_forces_ms()], device=dev, dtype=torch.float64)
     stats_all = torch.empty((world, 5), dtype=torch.float64, device=dev)
     dist.all_gather_into_tensor(stats_all, st)
     # ---- e2e: every rank's bodies come from pinned host memory and go back there, every step
