@@ -44,6 +44,20 @@ def make_ic(bh, w):
     return bh.ic_plummer(w["n"], 42, 200.0, 10.0, 4.5, 0.5)
 
 
+def force_roofline(bh, device, interactions_per_gpu, force_ms):
+    """roofline object of the dominant kernel for the multi-GPU lines: per-GPU FP32 rate of the traversal
+    (20 flop per accepted interaction) on the slowest rank against the FMA issue-rate probe."""
+    try:
+        peak = bh.probe_fp32_tflops(device)
+        achieved = FLOP_PER_INTERACTION * interactions_per_gpu / (force_ms * 1e-3) / 1e12
+        return {"bound": "fp32", "kernel": "force_kernel", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak if peak else None, "traffic": None, "per": "GPU (mean interactions / slowest rank's force phase)",
+                "peak_source": "bh_probe_fp32_tflops (FMA issue-rate probe run in this process)",
+                "flop_per_interaction": FLOP_PER_INTERACTION}
+    except Exception as e:   # the line must not be lost over a diagnostic
+        return {"error": repr(e)}
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
 

@@ -662,6 +662,8 @@ def run_let_bench(args, w, bh, dist, rank, world, local):
         del host
     sim.close()
     total_ms = float(ms.item())
+    # the force phases include the small ghost tree and the update: a lower bound of the traversal's rate
+    roofline = bench.force_roofline(bh, local, float(inter.item()) / world, max(row[4] for row in stats_all.tolist()))
     line = {
         "metric": "body-steps/s", "value": n * args.steps / (total_ms * 1e-3), "unit": "body-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -681,7 +683,7 @@ def run_let_bench(args, w, bh, dist, rank, world, local):
         "trace_ms_rank0_step_totals": [round(sum(tr.values()), 2) for tr in getattr(sim, "trace_all", [])] or None,
         "trace_ms_rank0_forces": [round(tr.get("forces+update", 0), 2) for tr in getattr(sim, "trace_all", [])] or None,
         "trace_ms_rank0_last_migration_step": {k: round(v, 3) for k, v in getattr(sim, "trace_migration_step", {}).items()} or None,
-        "wall_s_timed_loop": wall, "e2e": e2e, "gpu_launches": launches_per_let_step(key_bits) * args.steps,
+        "wall_s_timed_loop": wall, "e2e": e2e, "roofline": roofline, "gpu_launches": launches_per_let_step(key_bits) * args.steps,
         "clocks": ck,
     }
     dist.destroy_process_group()

@@ -217,6 +217,7 @@ def run_sliced_bench(args, w, bh, dist, rank, world, local):
     cells = sim.eng.stat(bh.STAT.CELLS)
     sim.close()
     total_ms = float(ms.item())
+    roofline = bench.force_roofline(bh, local, float(inter.item()) / world, max(force_per_rank))
     line = {
         "metric": "body-steps/s", "value": n * args.steps / (total_ms * 1e-3), "unit": "body-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
@@ -229,7 +230,7 @@ def run_sliced_bench(args, w, bh, dist, rank, world, local):
         "interactions_per_s": float(inter.item()) * args.steps / (total_ms * 1e-3),
         "phase_ms_rank0": {k: round(v, 4) for k, v in acc.items()}, "force_ms_per_rank": force_per_rank,
         "allgather_ms": allgather_ms,
-        "cells": cells, "e2e": e2e,
+        "cells": cells, "e2e": e2e, "roofline": roofline,
         "gpu_launches": bench.LAUNCHES_PER_STEP * args.steps * world, "clocks": ck,
     }
     dist.destroy_process_group()
