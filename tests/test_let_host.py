@@ -199,3 +199,105 @@ def test_export_oracle_properties_on_oracle_trees(orc, kind):
             # a box over everything: only cells narrower than theta*sqrt(SOFTENING) = 3.5 survive as monopoles
             assert all(root_w / 2.0 ** cells[tuple(p.tolist())] < 3.54 for p in pts if tuple(p.tolist()) not in bodies)
             assert len(pts) > 0.9 * n
+
+
+# ---- the whole LET protocol between two ranks over gloo, the oracle standing in for the GPU engine -------------------
+def _let_worker(rank, world, port, n, q):
+    """Each rank: start-up share by index, cube all-gather, election + migration (keys and bodies), oracle tree of the
+    own bodies, octree-aligned boxes, export walk per peer (oracle_lib.let_export_points), all-to-all of the points,
+    forces on the own bodies = direct sum over own bodies + imported points."""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+
+    import nbody_barnes_hut_cuda_b200 as bh
+    import oracle_lib as O
+    from nbody_barnes_hut_cuda_b200.let import SAMPLE, domain_cuts, elect_splitters, global_cube
+
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    soa = bh.ic_refdisk(n, 21)
+    posm_all, _, _ = O.soa_to_internal(soa)
+    first, last = n * rank // world, n * (rank + 1) // world
+    own, ids = posm_all[first:last].copy(), np.arange(first, last)
+
+    def gather(t):
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return torch.stack(out).numpy()
+
+    def exchange(rows, counts):                                # rows [sum(counts), k] float64, split by destination
+        sc = torch.tensor(counts, dtype=torch.int64)
+        rc = torch.empty(world, dtype=torch.int64)
+        dist.all_to_all_single(rc, sc)
+        recv = torch.empty((int(rc.sum()), rows.shape[1]), dtype=torch.float64)
+        dist.all_to_all_single(recv, torch.from_numpy(np.ascontiguousarray(rows, np.float64)), output_split_sizes=rc.tolist(),
+                               input_split_sizes=sc.tolist())
+        return recv.numpy()
+
+    # cube
+    box = np.concatenate([own[:, :3].min(0), own[:, :3].max(0)]).astype(np.float32)
+    cube = global_cube(gather(torch.from_numpy(box)))
+    # election (unit work) + migration
+    keys, _ = O.morton_keys(own[:, 0].copy(), own[:, 1].copy(), own[:, 2].copy(), cube)
+    order = np.argsort(keys, kind="stable")
+    keys, own, ids = keys[order].astype(np.int64), own[order], ids[order]
+    sample = keys[(np.arange(SAMPLE) * (len(keys) - 1)) // (SAMPLE - 1)]
+    pooled = gather(torch.from_numpy(np.concatenate([sample.astype(np.float64), [float(len(keys))]])))
+    edges = elect_splitters(pooled[:, :SAMPLE].astype(np.int64), pooled[:, SAMPLE])
+    cut = np.searchsorted(keys, edges[1:-1])
+    counts = np.diff(np.concatenate([[0], cut, [len(keys)]])).tolist()
+    got = exchange(np.concatenate([own.astype(np.float64), ids[:, None].astype(np.float64)], 1), counts)
+    own, ids = got[:, :4].astype(np.float32), got[:, 4].astype(np.int64)
+    # own tree
+    keys, _ = O.morton_keys(own[:, 0].copy(), own[:, 1].copy(), own[:, 2].copy(), cube)
+    assert ((keys >= edges[rank]) & (keys < edges[rank + 1])).all()
+    order = np.argsort(keys, kind="stable")
+    ks, ps, ids = keys[order], np.ascontiguousarray(own[order]), ids[order]
+    meta, child, root = O.tree_build(ks)
+    _, com = O.tree_com(ps, meta, child, root)
+    meta[:, 2] &= 0x1FF
+    # domain boxes of the octree-aligned intervals
+    cuts = domain_cuts(int(edges[rank]), int(edges[rank + 1])).astype(np.int64)
+    idx = np.searchsorted(ks.astype(np.int64), cuts)
+    mine = np.tile(np.array([1, 1, 1, -1, -1, -1], np.float32), (len(cuts) - 1, 1))
+    for k in range(len(cuts) - 1):
+        if idx[k + 1] > idx[k]:
+            run = ps[idx[k]:idx[k + 1], :3]
+            mine[k] = np.concatenate([run.min(0), run.max(0)])
+    boxes = gather(torch.from_numpy(mine))
+    # export walk per peer, exchange, forces
+    root_w = float(cube[3] - cube[0])
+    lists = [O.let_export_points(meta, child, com, ps, root, boxes[p], root_w) if p != rank else np.zeros((0, 4), np.float32)
+             for p in range(world)]
+    for p in range(world):
+        if p != rank:
+            assert abs(lists[p][:, 3].astype(np.float64).sum() - ps[:, 3].astype(np.float64).sum()) < 1e-5 * ps[:, 3].sum()
+    imports = exchange(np.concatenate(lists).astype(np.float64), [len(x) for x in lists]).astype(np.float32)
+    union = np.ascontiguousarray(np.concatenate([ps, imports]))
+    acc = O.direct_sum(union, np.arange(len(ps), dtype=np.int32))
+    exact = O.direct_sum(posm_all, ids.astype(np.int32))
+    q.put((rank, len(ps), len(imports), O.rel_rms(acc, exact), sorted(ids.tolist())))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_let_protocol_over_gloo():
+    import torch.multiprocessing as mp
+
+    n = 3000
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_let_worker, args=(r, 2, port, n, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in range(2))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1] + res[1][1] == n and sorted(res[0][4] + res[1][4]) == list(range(n))   # every body owned once
+    for _, n_own, n_imp, err, _ in res:
+        assert 0 < n_imp < n - n_own          # the peer was summarised, not copied
+        assert err < 3e-3                     # forces from own bodies + imported points: theta = 0.5 multipole error class
