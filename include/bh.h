@@ -232,6 +232,15 @@ int  bh_import_state(bh_ctx* ctx, const void* posm, const void* vel, const int32
 #define BH_LET_MAX_PEERS 64
 #define BH_LET_MAX_BOXES 256
 int  bh_let_domain_boxes(bh_ctx* ctx, const uint32_t* cuts, int K, float* lohi, int32_t* body_counts);
+/* Host-side decisions of this mode (pure functions; every rank evaluates them on all-gathered data).
+ * bh_let_domain_cuts: max_boxes+1 ascending keys cutting [k_lo, k_hi) at octree-cell boundaries — the 8..64
+ *   whole cells of size 8^j inside the range, its two ragged ends cut again at 8^j/64 — padded with k_hi
+ *   (empty intervals); BH_E_INVAL if max_boxes is too small (190 always suffice).
+ * bh_let_elect_splitters: samples = world x nsample keys (row r: keys of rank r at equal increments of its
+ *   cumulative work), work[r] = total work of rank r; edges[world+1] = key ranges of equal pooled work
+ *   (edges[0] = 0, edges[world] = 2^30).                                                                    */
+int  bh_let_domain_cuts(uint32_t k_lo, uint32_t k_hi, int max_boxes, uint32_t* cuts);
+int  bh_let_elect_splitters(const int64_t* samples, int nsample, const double* work, int world, int64_t* edges);
 /* Device pointers to THIS step's Morton-sorted arrays (u32 keys ascending, float4 posm, float4 vel, int32
  * ids) after phases KEYS+SORT — a key-range owner migrates bodies to their new owners straight from these
  * (runs of the sorted order) — and to the accelerations of the last force phase (float4 ax,ay,az,work;

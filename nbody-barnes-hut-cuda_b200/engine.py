@@ -122,6 +122,8 @@ def lib() -> C.CDLL:
     L.bh_local_bounds.argtypes = [vp, vp]
     L.bh_import_state.argtypes = [vp, vp, vp, vp, i64, vp]
     L.bh_let_export.argtypes = [vp, vp, i32, i32, vp, i64, vp, vp]
+    L.bh_let_domain_cuts.argtypes = [C.c_uint32, C.c_uint32, i32, vp]
+    L.bh_let_elect_splitters.argtypes = [vp, i32, vp, i32, vp]
     L.bh_force_from.argtypes = [vp, vp, vp]
     L.bh_sort_coarse.argtypes = [vp, vp]
     L.bh_export_real.argtypes = [vp, vp, vp, vp, C.POINTER(i64), vp]

@@ -29,12 +29,14 @@ guide forbids emulating ranks with kernels that wait on each other, this path ha
 """
 from __future__ import annotations
 
+import ctypes as C
 import os
 import time
 
 import numpy as np
 
 from .engine import DBG, FLAG_NO_GRAPH, PHASE, BHEngine
+from .engine import lib as _lib
 from .sliced import _DevView
 
 f32 = np.float32
@@ -76,55 +78,34 @@ def split_by_keys(keys: np.ndarray, world: int, sample: int = 1 << 20, seed: int
 
 
 def elect_splitters(samples: np.ndarray, work: np.ndarray) -> np.ndarray:
-    """Key-range edges [world+1] from every rank's key sample.
+    """Key-range edges [world+1] from every rank's key sample (bh_let_elect_splitters, csrc/bh_let_host.cpp).
 
     samples [world, SAMPLE]: keys of rank r at equal increments of its cumulative work, so that every sample
     stands for work[r]/SAMPLE (rows of ranks with work 0 are ignored).  Edge r is the key at r/world of the
     pooled work.  Identical on all ranks (pure function of all-gathered data)."""
+    samples = np.ascontiguousarray(samples, np.int64)
+    work = np.ascontiguousarray(work, np.float64)
     world = len(work)
-    work = np.asarray(work, np.float64)
-    if not (work > 0).any():
-        return np.array([0] + [KEY_END] * world, np.int64)
-    wgt = np.repeat(np.where(work > 0, work / samples.shape[1], 0.0), samples.shape[1])
-    keys = np.asarray(samples, np.int64).reshape(-1)
-    order = np.argsort(keys, kind="stable")
-    keys, cum = keys[order], np.cumsum(wgt[order])
-    edges = [0]
-    for r in range(1, world):
-        k = int(keys[min(int(np.searchsorted(cum, cum[-1] * r / world)), len(keys) - 1)])
-        edges.append(max(k, edges[-1]))
-    edges.append(KEY_END)
-    return np.array(edges, np.int64)
+    edges = np.zeros(world + 1, np.int64)
+    rc = _lib().bh_let_elect_splitters(samples.ctypes.data_as(C.c_void_p), samples.shape[1], work.ctypes.data_as(C.c_void_p),
+                                       world, edges.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise ValueError(f"bh_let_elect_splitters failed: {rc}")
+    return edges
 
 
 def domain_cuts(k_lo: int, k_hi: int) -> np.ndarray:
-    """MAX_BOXES+1 ascending keys that cut [k_lo, k_hi) at octree-cell boundaries.
+    """MAX_BOXES+1 ascending keys that cut [k_lo, k_hi) at octree-cell boundaries (bh_let_domain_cuts).
 
     Interior: the 8..64 cells of size S = 8^j (largest with span/S >= 8) that lie inside the range — whole
     cells, convex, owned by this rank alone.  The two ragged ends (parts of one S-cell each) are cut again
     at S/64 so that their boxes reach at most one small cell into the neighbour's range.  Padded with k_hi
     (empty intervals) to a fixed length so the boxes can be all-gathered."""
-    cuts = {int(k_lo), int(k_hi)}
-    span = int(k_hi) - int(k_lo)
-    if span > 0:
-        S = 1
-        while S * 64 <= span:
-            S *= 8
-        first = -(-int(k_lo) // S) * S
-        last = int(k_hi) // S * S
-        if first <= last:
-            cuts.update(range(first, last + 1, S))
-            fine = max(S // 64, 1)
-            for a, b in ((int(k_lo), first), (last, int(k_hi))):
-                if b - a > fine:
-                    cuts.update(range(-(-a // fine) * fine, b, fine))
-        else:                                  # the whole range lies inside one S-cell
-            fine = max(S // 64, 1)
-            cuts.update(range(-(-int(k_lo) // fine) * fine, int(k_hi), fine))
-    out = sorted(c for c in cuts if k_lo <= c <= k_hi)
-    assert len(out) <= MAX_BOXES + 1, len(out)
-    out += [int(k_hi)] * (MAX_BOXES + 1 - len(out))
-    return np.array(out, np.uint32)
+    cuts = np.zeros(MAX_BOXES + 1, np.uint32)
+    rc = _lib().bh_let_domain_cuts(int(k_lo), int(k_hi), MAX_BOXES, cuts.ctypes.data_as(C.c_void_p))
+    if rc:
+        raise ValueError(f"bh_let_domain_cuts({k_lo}, {k_hi}) failed: {rc}")
+    return cuts
 
 
 def compact_boxes(boxes: np.ndarray) -> np.ndarray:

@@ -277,3 +277,61 @@ def let_export_points(meta, child, com, posm_sorted, root, boxes_lohi, root_w, t
     while stack:
         visit(stack.pop())
     return np.array(out, np.float32).reshape(-1, 4)
+
+
+# ---- host-side decisions of the LET mode: plain-Python statements the native versions (csrc/bh_let_host.cpp:
+# bh_let_elect_splitters, bh_let_domain_cuts) are checked against ------------------------------------------
+LET_KEY_END = 1 << 30
+LET_MAX_BOXES = 200
+
+
+def let_elect_splitters_ref(samples: np.ndarray, work: np.ndarray) -> np.ndarray:
+    """Key-range edges [world+1] from every rank's key sample.
+
+    samples [world, SAMPLE]: keys of rank r at equal increments of its cumulative work, so that every sample
+    stands for work[r]/SAMPLE (rows of ranks with work 0 are ignored).  Edge r is the key at r/world of the
+    pooled work.  Identical on all ranks (pure function of all-gathered data)."""
+    world = len(work)
+    work = np.asarray(work, np.float64)
+    if not (work > 0).any():
+        return np.array([0] + [LET_KEY_END] * world, np.int64)
+    wgt = np.repeat(np.where(work > 0, work / samples.shape[1], 0.0), samples.shape[1])
+    keys = np.asarray(samples, np.int64).reshape(-1)
+    order = np.argsort(keys, kind="stable")
+    keys, cum = keys[order], np.cumsum(wgt[order])
+    edges = [0]
+    for r in range(1, world):
+        k = int(keys[min(int(np.searchsorted(cum, cum[-1] * r / world)), len(keys) - 1)])
+        edges.append(max(k, edges[-1]))
+    edges.append(LET_KEY_END)
+    return np.array(edges, np.int64)
+
+
+def let_domain_cuts_ref(k_lo: int, k_hi: int) -> np.ndarray:
+    """LET_MAX_BOXES+1 ascending keys that cut [k_lo, k_hi) at octree-cell boundaries.
+
+    Interior: the 8..64 cells of size S = 8^j (largest with span/S >= 8) that lie inside the range — whole
+    cells, convex, owned by this rank alone.  The two ragged ends (parts of one S-cell each) are cut again
+    at S/64 so that their boxes reach at most one small cell into the neighbour's range.  Padded with k_hi
+    (empty intervals) to a fixed length so the boxes can be all-gathered."""
+    cuts = {int(k_lo), int(k_hi)}
+    span = int(k_hi) - int(k_lo)
+    if span > 0:
+        S = 1
+        while S * 64 <= span:
+            S *= 8
+        first = -(-int(k_lo) // S) * S
+        last = int(k_hi) // S * S
+        if first <= last:
+            cuts.update(range(first, last + 1, S))
+            fine = max(S // 64, 1)
+            for a, b in ((int(k_lo), first), (last, int(k_hi))):
+                if b - a > fine:
+                    cuts.update(range(-(-a // fine) * fine, b, fine))
+        else:                                  # the whole range lies inside one S-cell
+            fine = max(S // 64, 1)
+            cuts.update(range(-(-int(k_lo) // fine) * fine, int(k_hi), fine))
+    out = sorted(c for c in cuts if k_lo <= c <= k_hi)
+    assert len(out) <= LET_MAX_BOXES + 1, len(out)
+    out += [int(k_hi)] * (LET_MAX_BOXES + 1 - len(out))
+    return np.array(out, np.uint32)

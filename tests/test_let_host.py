@@ -10,6 +10,31 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def test_native_host_decisions_equal_the_python_statements(orc):
+    """bh_let_domain_cuts / bh_let_elect_splitters (C++ in libbh.so) against their plain-Python statements."""
+    from nbody_barnes_hut_cuda_b200.let import KEY_END, SAMPLE, domain_cuts, elect_splitters
+
+    rng = np.random.default_rng(11)
+    for t in range(3000):
+        a, b = sorted(rng.integers(0, KEY_END + 1, 2).tolist())
+        if t % 3 == 0:
+            b = min(KEY_END, a + int(rng.integers(0, 70000)))
+        if t % 7 == 0:
+            a = a // 4096 * 4096
+        assert (domain_cuts(a, b) == orc.let_domain_cuts_ref(a, b)).all(), (a, b)
+    for a, b in ((0, KEY_END), (0, 0), (KEY_END, KEY_END), (5, 6), (0, 1), (KEY_END - 1, KEY_END), (1 << 27, 1 << 28)):
+        assert (domain_cuts(a, b) == orc.let_domain_cuts_ref(a, b)).all(), (a, b)
+    for t in range(60):
+        world = int(rng.integers(1, 9))
+        ns = SAMPLE if t % 2 == 0 else int(rng.integers(1, 50))
+        hi = KEY_END if t % 3 else 1000                         # many duplicate keys in every third case
+        samples = np.sort(rng.integers(0, hi, (world, ns)), 1)
+        work = rng.uniform(0.5, 50.0, world) * rng.integers(0, 2, world) if t % 4 == 0 else rng.uniform(1.0, 1e9, world)
+        assert (elect_splitters(samples, work) == orc.let_elect_splitters_ref(samples, work)).all(), t
+    z = np.zeros((3, 8), np.int64)
+    assert (elect_splitters(z, np.zeros(3)) == orc.let_elect_splitters_ref(z, np.zeros(3))).all()
+
+
 def test_domain_cuts_are_octree_aligned():
     from nbody_barnes_hut_cuda_b200.let import KEY_END, MAX_BOXES, domain_cuts
 
