@@ -22,6 +22,11 @@
 #define BH_DERR_TREE        8   // builder found an inconsistent range
 #define BH_DERR_LET_OVERFLOW 16  // locally-essential-tree export ran out of output / queue space
 
+// kid_info[8c + r].y: level of a child cell in the low bits, plus
+#define BH_KID_LEVEL_MASK 0x1Fu
+#define BH_KID_BUCKET     0x80u    // child cell is an identical-key bucket (contiguous body range, never opened)
+#define BH_KID_BODY       0x100u   // child is a loose body (always a source)
+
 struct BhDevScalars {        // one small device struct, zeroed/filled by kernels
     float bounds[6];         // as d_bounds (nbody_v5_bench.cu:149-154)
     int   num_cells;         // total of the leader-flag scan
@@ -31,6 +36,7 @@ struct BhDevScalars {        // one small device struct, zeroed/filled by kernel
     unsigned long long inter_cell;
     unsigned long long inter_body;
     unsigned int max_stack;
+    unsigned int root_word;      // stack word of the root: id << 3 | children - 1 (written by the centre-of-mass pass)
     unsigned int bbox_enc[6];    // order-preserving uint encoding of min/max during reduction
     // heavy-first scheduling of traversal chunks (bh_force.cu): chunks whose interaction list was long
     // in the previous step are handed out first in this one (costs are temporally coherent)
@@ -107,19 +113,21 @@ int bh_bounds_launch(const float4* posm, int64_t n, BhDevScalars* sc, cudaStream
 int bh_reorder_launch(const float4* posm_in, const float4* vel_in, const int32_t* ids_in,
                       const uint32_t* perm, float4* posm_out, float4* vel_out, int32_t* ids_out,
                       int64_t n, cudaStream_t st);
-// kid_src: 8 float4 per cell — the SOURCE each child contributes when its parent is opened (a loose
-// body's {x,y,z,m}, a child cell's {com,mass}); kid_lv: 8 bytes per cell — level | bucket<<7 of child cells.
-int bh_tree_launch(const void* keys, int levels, const float4* posm, int64_t n, int2* pair_info, int32_t* pair_scan,
+// kid_lv: 8 bytes per cell, digit-indexed like cell_child — level | bucket<<7 of child cells.
+int bh_tree_launch(const void* keys, int levels, int64_t n, int2* pair_info, int32_t* pair_scan,
                    int32_t* scan_block_sums, int4* cell_meta, int32_t* cell_child,
-                   int32_t* cell_arrive, float4* kid_src, uint8_t* kid_lv, BhDevScalars* sc, cudaStream_t st);
+                   int32_t* cell_arrive, uint8_t* kid_lv, BhDevScalars* sc, cudaStream_t st);
+// kid_src / kid_info: 8 entries per cell, DENSE (the r-th existing child in digit order sits at 8c + r) — the SOURCE
+// each child contributes when its parent is opened (a loose body's {x,y,z,m}, a child cell's {com,mass}) and
+// {stack word of a child cell = id << 3 | its child count - 1, level | BH_KID_BUCKET | BH_KID_BODY}.
 int bh_com_launch(const float4* posm, int64_t n, const int4* cell_meta, const int32_t* cell_child,
-                  int32_t* cell_arrive, float4* cell_mom, float4* cell_com, float4* kid_src,
+                  int32_t* cell_arrive, float4* cell_mom, float4* cell_com, float4* kid_src, uint2* kid_info,
                   BhDevScalars* sc, cudaStream_t st);
 // heavy_list, heavy_flag: 2 * max_chunks u32 each (see BhDevScalars::epoch)
 // ids: nullptr, or per-body ids where id < 0 marks a ghost (a source whose own acceleration is not wanted)
 int bh_force_launch(const float4* posm, const void* keys, int levels, const int32_t* ids, int64_t n, int64_t first_body,
-                    int64_t body_count, const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
-                    const float4* kid_src, const uint8_t* kid_lv,
+                    int64_t body_count, const int4* cell_meta, const float4* cell_com,
+                    const float4* kid_src, const uint2* kid_info,
                     float4* acc, BhDevScalars* sc, uint32_t* heavy_list, uint32_t* heavy_flag, int64_t max_chunks,
                     float theta, float softening, float G, float split_alpha, int num_sms,
                     // cross-tree pass: the tree (scalars, cells, the bodies its buckets index) of ANOTHER body set;

@@ -47,7 +47,8 @@ struct bh_ctx {
     int32_t *cell_child = nullptr, *cell_arrive = nullptr;
     float4 *cell_mom = nullptr, *cell_com = nullptr;
     float4* kid_src = nullptr;   // 8 per cell
-    uint8_t* kid_lv = nullptr;   // 8 per cell
+    uint8_t* kid_lv = nullptr;   // 8 per cell (digit-indexed)
+    uint2* kid_info = nullptr;   // 8 per cell (dense, pairs with kid_src)
     uint32_t* heavy_list = nullptr;   // 2 * max_chunks
     uint32_t* heavy_flag = nullptr;   // 2 * max_chunks epoch tags
     int64_t max_chunks = 0;
@@ -86,7 +87,7 @@ void free_all(bh_ctx* c) {
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     void* ptrs[] = {c->posm, c->vel, c->posm_s, c->vel_s, c->acc, c->ids, c->ids_s, c->keys0, c->keys1, c->vals0,
                     c->vals1, c->sort_tmp, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
-                    c->cell_arrive, c->cell_mom, c->cell_com, c->sc, c->stage, c->d_scratch, c->heavy_list, c->heavy_flag, c->kid_src, c->kid_lv, c->let_boxes, c->let_counts, c->let_queue, c->klo, c->kaux, c->keys64};
+                    c->cell_arrive, c->cell_mom, c->cell_com, c->sc, c->stage, c->d_scratch, c->heavy_list, c->heavy_flag, c->kid_src, c->kid_lv, c->kid_info, c->let_boxes, c->let_counts, c->let_queue, c->klo, c->kaux, c->keys64};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -155,17 +156,17 @@ int phase_sort(bh_ctx* c, cudaStream_t st) {
 }
 
 int phase_build(bh_ctx* c, cudaStream_t st) {
-    return bh_tree_launch(c->levels == 20 ? (const void*)c->keys64 : (const void*)c->keys0, c->levels, c->posm_s, c->n, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
-                          c->cell_arrive, c->kid_src, c->kid_lv, c->sc, st);
+    return bh_tree_launch(c->levels == 20 ? (const void*)c->keys64 : (const void*)c->keys0, c->levels, c->n, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
+                          c->cell_arrive, c->kid_lv, c->sc, st);
 }
 
 int phase_com(bh_ctx* c, cudaStream_t st) {
-    return bh_com_launch(c->posm_s, c->n, c->cell_meta, c->cell_child, c->cell_arrive, c->cell_mom, c->cell_com, c->kid_src, c->sc, st);
+    return bh_com_launch(c->posm_s, c->n, c->cell_meta, c->cell_child, c->cell_arrive, c->cell_mom, c->cell_com, c->kid_src, c->kid_info, c->sc, st);
 }
 
 int phase_force(bh_ctx* c, cudaStream_t st) {
-    return bh_force_launch(c->posm_s, c->levels == 20 ? (const void*)c->keys64 : (const void*)c->keys0, c->levels, c->ids_s, c->n, c->slice_first, c->slice_count, c->cell_meta, c->cell_child,
-                           c->cell_com, c->kid_src, c->kid_lv, c->acc, c->sc, c->heavy_list, c->heavy_flag, c->max_chunks, c->prm.theta,
+    return bh_force_launch(c->posm_s, c->levels == 20 ? (const void*)c->keys64 : (const void*)c->keys0, c->levels, c->ids_s, c->n, c->slice_first, c->slice_count, c->cell_meta,
+                           c->cell_com, c->kid_src, c->kid_info, c->acc, c->sc, c->heavy_list, c->heavy_flag, c->max_chunks, c->prm.theta,
                            c->prm.softening, c->prm.G, c->prm.group_split, c->num_sms, nullptr, nullptr, 0, st);
 }
 
@@ -267,7 +268,7 @@ const char* bh_error_string(int code) {
 }
 
 int bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device) {
-    if (!out || n_max <= 0 || n_max >= ((int64_t)1 << 30)) return BH_E_INVAL;
+    if (!out || n_max <= 0 || n_max >= ((int64_t)1 << 29)) return BH_E_INVAL;   // traversal stack words are cell id << 3
     *out = nullptr;
     bh_params prm;
     if (params) prm = *params; else bh_default_params(&prm);
@@ -296,7 +297,7 @@ int bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device) 
     TRYA(dev_alloc(&c->pair_info, na)); TRYA(dev_alloc(&c->pair_scan, na)); TRYA(dev_alloc(&c->tile_sums, na / 2048 + 16));
     TRYA(dev_alloc(&c->cell_meta, na)); TRYA(dev_alloc(&c->cell_child, na * 8)); TRYA(dev_alloc(&c->cell_arrive, na));
     TRYA(dev_alloc(&c->cell_mom, na)); TRYA(dev_alloc(&c->cell_com, na));
-    TRYA(dev_alloc(&c->kid_src, na * 8)); TRYA(dev_alloc(&c->kid_lv, na * 8));
+    TRYA(dev_alloc(&c->kid_src, na * 8)); TRYA(dev_alloc(&c->kid_lv, na * 8)); TRYA(dev_alloc(&c->kid_info, na * 8));
     TRYA(dev_alloc(&c->sc, 1)); TRYA(dev_alloc(&c->d_scratch, 8));
     c->max_chunks = (int64_t)(na / BH_GROUP + 1);
     TRYA(dev_alloc(&c->heavy_list, 2 * (size_t)c->max_chunks)); TRYA(dev_alloc(&c->heavy_flag, 2 * (size_t)c->max_chunks));
@@ -482,8 +483,8 @@ int bh_force_from(bh_ctx* c, bh_ctx* src, void* stream) {
     BH_CUDA_TRY(cudaSetDevice(c->device));
     if (src->n < 2) return BH_E_UNSUPPORTED;   // a single body has no tree
     return bh_force_launch(c->posm_s, c->levels == 20 ? (const void*)c->keys64 : (const void*)c->keys0, c->levels, c->ids_s, c->n,
-                           c->slice_first, c->slice_count, src->cell_meta, src->cell_child, src->cell_com, src->kid_src,
-                           src->kid_lv, c->acc, c->sc, c->heavy_list, c->heavy_flag, c->max_chunks, c->prm.theta,
+                           c->slice_first, c->slice_count, src->cell_meta, src->cell_com, src->kid_src,
+                           src->kid_info, c->acc, c->sc, c->heavy_list, c->heavy_flag, c->max_chunks, c->prm.theta,
                            c->prm.softening, c->prm.G, c->prm.group_split, c->num_sms, src->posm_s, src->sc, 1,
                            (cudaStream_t)stream);
 }

@@ -3,21 +3,26 @@
 // Replaces computeForceKernel  nbody_v5_bench.cu:191-225  (one thread per body, private
 // int stack[64], 76-byte AoS nodes).
 //
-// One warp owns a GROUP of up to 32 Morton-consecutive bodies (one body per lane).  The warp keeps ONE
-// stack of cells TO OPEN in shared memory and pops up to 32 of them at a time, one per lane.  Opening a
-// cell reads one 128-byte line, kid_src[cell][0..8): what each child contributes as a source — a loose
-// body's {x,y,z,m} or a child cell's {centre of mass, mass} — plus the child ids and levels.  The lane
-// then classifies its 8 children in registers:
+// One warp owns a GROUP of up to 32 Morton-consecutive bodies (one body per lane) and keeps ONE stack of cells
+// TO OPEN in shared memory.  A stack word is `cell id << 3 | children - 1`; the children of a cell are a DENSE
+// line in HBM (bh_tree.cu): kid_src[8c + r] = what child r contributes as a source — a loose body's {x,y,z,m}
+// or a child cell's {centre of mass, mass} — and kid_info[8c + r] = {the child's own stack word, level | flags}.
+// A round pops as many cells as have ROUND_ITEMS (= 32 x FORCE_ITEMS) children together and hands every lane
+// FORCE_ITEMS CHILDREN (not cells: the octree holds ~3 children per cell, a lane that classifies 8 slots of one
+// cell wastes most of them).  The lane -> (cell, child) map needs no shuffle chain: the popped words' child
+// counts are prefix-summed with three independent ballots (one per bit of the count), a bit mask of the item
+// numbers where a cell starts is OR-reduced over the warp, and a lane finds its cell as a population count of
+// that mask.  Each child is then classified in registers:
 //   - loose body          -> source
 //   - child cell accepted -> source.  Test: w_L^2 < theta^2 * (d^2 + SOFTENING), d = distance from the
 //     child's centre of mass to the group's bounding box (exact AABB of the positions).  This is
 //     bench:207-208 (`width / sqrtf(d2 + SOFTENING) < THETA`) squared and taken at the group's closest
 //     point, so it is uniform for the warp and every body of the group would have accepted too;
-//   - child cell rejected -> pushed to be opened (identical-key buckets: their body range is appended).
-// One dependent global access per tree level (the child's data lives in the parent's line), warp
-// prefix sums (__shfl_up_sync) place sources and pushes, and whenever 32 sources are pending the warp
-// evaluates a 32x32 tile: each lane keeps its own body in registers and reads the sources as shared
-// memory broadcasts (LDS.128), bench:205-213's arithmetic in packed FP32 with rsqrt.approx.ftz.
+//   - child cell rejected -> its stack word is pushed (identical-key buckets: their body range is appended).
+// One dependent global access per tree level (the child's data lives in the parent's line); ballots place
+// sources and pushes; whenever 32 sources are pending the warp evaluates a 32x32 tile: each lane keeps its own
+// body in registers and reads the sources as shared memory broadcasts (LDS.128), bench:205-213's arithmetic in
+// packed FP32 with rsqrt.approx.ftz.
 //
 // Group splitting: a 32-slot chunk of the Morton order that straddles a coarse cell boundary would
 // get a huge bounding box (measured on the 1M reference disk: median list 1,088 entries, worst
@@ -50,14 +55,26 @@ constexpr int FORCE_THREADS = FORCE_WARPS * 32;
 #ifndef FORCE_MIN_CTAS
 #define FORCE_MIN_CTAS 4
 #endif
-constexpr int STACK_CAP = 768;
-constexpr int STACK_RESERVE = 384;   // >= 224 (one wide pop/push) + 7 * deepest level, see DESIGN.md
-constexpr int SRC_CAP = 320;         // pending sources: < 32 left over + 8 per lane + one bucket slab of 32
+#ifndef FORCE_ITEMS
+#define FORCE_ITEMS 2
+#endif
+constexpr int ITEMS = FORCE_ITEMS;             // children classified per lane and round
+constexpr int ROUND_ITEMS = 32 * ITEMS;
+constexpr int STACK_CAP = 640;
+// A round that pops cells with T children pushes at most T words.  Rounds of ROUND_ITEMS children run only while
+// that fits under the depth-first reserve; otherwise a round takes at most 8 children (one cell, or a few small
+// ones): net growth <= 7 per tree level, the classic DFS bound — no overflow by construction.
+template <int LEVELS> struct StackPlan {
+    static constexpr int DFS_RESERVE = 7 * LEVELS + 8;
+    static constexpr int WIDE_LIMIT = STACK_CAP - ROUND_ITEMS - DFS_RESERVE;
+    static_assert(WIDE_LIMIT >= 64, "stack too small for wide rounds");
+};
+constexpr int SRC_CAP = 32 + ROUND_ITEMS + 32;   // pending sources: < 32 left over + one round + one bucket slab of 32
 constexpr unsigned LOOP_GUARD = 1u << 24;
 
 struct __align__(16) WarpScratch {
     float4 src[SRC_CAP];       // pending sources, stored as PAIRS (see SrcPair)
-    int stack[STACK_CAP];      // cells waiting to be opened
+    unsigned stack[STACK_CAP]; // cells waiting to be opened: id << 3 | children - 1
 };
 
 // r2 >= SOFTENING > 0, never denormal: the flush-to-zero form is a bare MUFU.RSQ (the default
@@ -158,8 +175,8 @@ __device__ __forceinline__ void eval_tile(const SrcPair* __restrict__ src, f32x2
 template <int LEVELS>
 __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
     const float4* __restrict__ posm, const typename BhKey<LEVELS>::type* __restrict__ keys, const int32_t* __restrict__ ids,
-    int64_t first_body, int64_t body_count, const int4* __restrict__ cell_meta, const int32_t* __restrict__ cell_child, const float4* __restrict__ cell_com,
-    const float4* __restrict__ kid_src, const uint8_t* __restrict__ kid_lv, float4* __restrict__ acc, BhDevScalars* sc,
+    int64_t first_body, int64_t body_count, const int4* __restrict__ cell_meta, const float4* __restrict__ cell_com,
+    const float4* __restrict__ kid_src, const uint2* __restrict__ kid_info, float4* __restrict__ acc, BhDevScalars* sc,
     uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_flag, int64_t max_chunks, float theta, float soft,
     float G, float split_alpha, const float4* __restrict__ src_posm, const BhDevScalars* __restrict__ tree_sc,
     int accumulate) {
@@ -174,8 +191,8 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
     // root_w^2 with 2L taken off the exponent (exact: power-of-two scaling commutes with rounding)
     const float root_w = __fsub_rn(tree_sc->bounds[3], tree_sc->bounds[0]);
     const int root_w2_bits = __float_as_int(__fmul_rn(root_w, root_w));
-    const int4* child4 = reinterpret_cast<const int4*>(cell_child);
-    const uint2* lv2 = reinterpret_cast<const uint2*>(kid_lv);
+    const unsigned root_word = tree_sc->root_word;
+    const unsigned lt_mask = (1u << lane) - 1u, le_mask = lt_mask | (1u << lane);
     const int64_t ngroups = (body_count + BH_GROUP - 1) / BH_GROUP;
     const int64_t end_body = first_body + body_count;
 
@@ -290,7 +307,8 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
         Accum t;                                  // this sub-group's pass (kept only by its lanes)
         t.x = t.y = t.z = pack2(0.f, 0.f);
         int sp = 0, ns = 0;                       // stack entries, pending sources
-        unsigned acc_cells = 0, dir_bodies = 0;
+        unsigned my_cells = 0, my_bodies = 0;     // sources this lane emitted (summed over the warp at the end)
+        unsigned bucket_bodies = 0;               // warp-uniform: bodies appended from rejected buckets
 
         // evaluate every full tile of 32 pending sources, keep the (< 32) remainder at the front
         auto drain = [&]() {
@@ -308,7 +326,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
         };
         // append the bodies [bfirst, bfirst+bcount) of a rejected bucket
         auto append_bucket = [&](int bfirst, int bcount) {
-            dir_bodies += bcount;
+            bucket_bodies += bcount;
             for (int b = 0; b < bcount; b += 32) {
                 const int m = min(32, bcount - b);
                 if (lane < m) store_source(slist, ns + lane, __ldg(src_posm + bfirst + b + lane));
@@ -323,12 +341,12 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
             const float4 rcm = __ldg(cell_com + root);
             const int4 rmt = __ldg(cell_meta + root);
             if (accepts(rcm, rmt.z & 0xFF)) {
-                if (lane == 0) store_source(slist, 0, rcm);
-                ns = 1; acc_cells = 1;
+                if (lane == 0) { store_source(slist, 0, rcm); my_cells = 1; }
+                ns = 1;
             } else if ((rmt.z >> 8) & 1) {
                 append_bucket(rmt.x, rmt.y);
             } else {
-                if (lane == 0) W.stack[0] = root;
+                if (lane == 0) W.stack[0] = root_word;
                 sp = 1;
             }
         }
@@ -337,91 +355,92 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
         unsigned guard = 0;
         while (sp > 0) {
             if (++guard > LOOP_GUARD) { if (lane == 0) atomicOr(&sc->err, BH_DERR_LOOP); break; }
-            // wide pop while a full push still fits, single pop (plain DFS) otherwise
-            const int take = (sp <= STACK_CAP - STACK_RESERVE) ? min(sp, 32) : 1;
-            const bool mine = lane < take;
-            const int cell = mine ? W.stack[sp - 1 - lane] : 0;
-            sp -= take;
-            __syncwarp();
-
-            // ---- open: ids, levels and the 128-byte source line of the 8 children ----
-            int e[8] = {BH_CHILD_EMPTY, BH_CHILD_EMPTY, BH_CHILD_EMPTY, BH_CHILD_EMPTY,
-                        BH_CHILD_EMPTY, BH_CHILD_EMPTY, BH_CHILD_EMPTY, BH_CHILD_EMPTY};
-            float4 s[8];
-            unsigned lvlo = 0, lvhi = 0;
-            unsigned src_mask = 0, push_mask = 0, bucket_mask = 0;   // per child slot
-            if (mine) {
-                const int4 lo = __ldg(child4 + 2 * (size_t)cell), hi = __ldg(child4 + 2 * (size_t)cell + 1);
-                const uint2 lv = __ldg(lv2 + cell);
-                lvlo = lv.x; lvhi = lv.y;
-                e[0] = lo.x; e[1] = lo.y; e[2] = lo.z; e[3] = lo.w;
-                e[4] = hi.x; e[5] = hi.y; e[6] = hi.z; e[7] = hi.w;
-                const float4* line = kid_src + (size_t)cell * 8;
+            // ---- pop: the cells on top of the stack whose children number <= ROUND_ITEMS together ----
+            const int avail = min(sp, 32);
+            const bool live = lane < avail;
+            const unsigned ent = live ? W.stack[sp - 1 - lane] : 0u;
+            const unsigned c1 = ent & 7u;                                    // children - 1
+            const unsigned live_m = avail == 32 ? 0xffffffffu : (1u << avail) - 1u;
+            // exclusive prefix of the child counts: three independent ballots instead of a shuffle chain
+            const unsigned b0 = __ballot_sync(0xffffffffu, c1 & 1u), b1 = __ballot_sync(0xffffffffu, c1 & 2u),
+                           b2 = __ballot_sync(0xffffffffu, c1 & 4u);
+            const int excl = __popc(live_m & lt_mask) + __popc(b0 & lt_mask) + 2 * __popc(b1 & lt_mask) + 4 * __popc(b2 & lt_mask);
+            const int limit = (sp <= StackPlan<LEVELS>::WIDE_LIMIT) ? ROUND_ITEMS : 8;
+            const unsigned tk = __ballot_sync(0xffffffffu, live && excl + (int)c1 + 1 <= limit);   // a prefix of the lanes, never empty
+            const int E = __popc(tk);
+            const int T = E + __popc(b0 & tk) + 2 * __popc(b1 & tk) + 4 * __popc(b2 & tk);        // children this round
+            sp -= E;
+            // item k belongs to the cell whose first item number is the last start <= k
+            const bool taken = lane < E;
+            const unsigned base = (ent & ~7u) - (unsigned)excl;             // 8 * cell - first item number
+            unsigned starts[ITEMS];
 #pragma unroll
-                for (int q = 0; q < 8; ++q)
-                    if (e[q] != BH_CHILD_EMPTY) s[q] = __ldg(line + q);
+            for (int j = 0; j < ITEMS; ++j)
+                starts[j] = __reduce_or_sync(0xffffffffu, (taken && (excl >> 5) == j) ? 1u << (excl & 31) : 0u);
+
+            // ---- open: one child per (lane, j): its source and its info word ----
+            float4 s[ITEMS];
+            uint2 w[ITEMS];
+            bool has[ITEMS];
+            int before = 0;
+#pragma unroll
+            for (int j = 0; j < ITEMS; ++j) {
+                const int k = lane + 32 * j;
+                has[j] = k < T;
+                const int owner = before + __popc(starts[j] & le_mask) - 1;
+                before += __popc(starts[j]);
+                const unsigned idx = __shfl_sync(0xffffffffu, base, owner & 31) + (unsigned)k;
+                if (has[j]) {
+                    s[j] = __ldg(kid_src + idx);
+                    w[j] = __ldg(kid_info + idx);
+                }
             }
             // software pipelining: the tiles pending from the previous round are evaluated while the
             // loads above are in flight
             drain();
-            if (mine) {
+            unsigned m_src[ITEMS], m_push[ITEMS], m_bucket = 0;
+            bool is_src[ITEMS], is_push[ITEMS], is_bucket[ITEMS];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    if (e[q] == BH_CHILD_EMPTY) continue;
-                    if (e[q] < 0) { src_mask |= 1u << q; continue; }                 // loose body
-                    const unsigned info = ((q < 4 ? lvlo : lvhi) >> (8 * (q & 3))) & 0xFFu;
-                    if (accepts(s[q], info & 0x7F)) src_mask |= 1u << (q + 8);       // accepted cell
-                    else if (info & 0x80) bucket_mask |= 1u << q;
-                    else push_mask |= 1u << q;
-                }
+            for (int j = 0; j < ITEMS; ++j) {
+                const bool body = has[j] && (w[j].y & BH_KID_BODY);
+                const bool ok = has[j] && (body || accepts(s[j], (int)(w[j].y & BH_KID_LEVEL_MASK)));
+                is_src[j] = ok;
+                is_bucket[j] = has[j] && !ok && (w[j].y & BH_KID_BUCKET);
+                is_push[j] = has[j] && !ok && !(w[j].y & BH_KID_BUCKET);
+                my_bodies += body;
+                my_cells += ok && !body;
+                m_src[j] = __ballot_sync(0xffffffffu, is_src[j]);
+                m_push[j] = __ballot_sync(0xffffffffu, is_push[j]);
+                m_bucket |= __ballot_sync(0xffffffffu, is_bucket[j]);
             }
-            const int n_body = __popc(src_mask & 0xFFu), n_cell = __popc(src_mask >> 8);
-            const int n_push = __popc(push_mask);
-            // one warp prefix sum for both streams: sources in the high half, pushes in the low half
-            const int packed = ((n_body + n_cell) << 16) | n_push;
-            int incl = packed;
+            if (sp + T > STACK_CAP) { if (lane == 0) atomicOr(&sc->err, BH_DERR_STACK); break; }   // unreachable by construction
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, incl, o);
-                if (lane >= o) incl += v;
+            for (int j = 0; j < ITEMS; ++j) {
+                if (is_src[j]) store_source(slist, ns + __popc(m_src[j] & lt_mask), s[j]);
+                if (is_push[j]) W.stack[sp + __popc(m_push[j] & lt_mask)] = w[j].x;
+                ns += __popc(m_src[j]);
+                sp += __popc(m_push[j]);
             }
-            const int total = __shfl_sync(0xffffffffu, incl, 31);
-            if (mine) {
-                int so = sp + ((incl - packed) & 0xFFFF);
-                int di = ns + ((incl - packed) >> 16);
-                const unsigned any_src = (src_mask | (src_mask >> 8)) & 0xFFu;
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    if ((any_src >> q) & 1u) store_source(slist, di++, s[q]);
-                    if ((push_mask >> q) & 1u) W.stack[so++] = e[q];
-                }
-            }
-            // warp totals of the two kinds of sources (interaction statistics)
-            acc_cells += __reduce_add_sync(0xffffffffu, (unsigned)n_cell);
-            dir_bodies += __reduce_add_sync(0xffffffffu, (unsigned)n_body);
-            sp += total & 0xFFFF;
-            ns += total >> 16;
             max_sp = max(max_sp, (unsigned)sp);
             __syncwarp();
 
             // ---- rejected buckets (identical keys): their bodies are a contiguous range ----
-            unsigned bm = __ballot_sync(0xffffffffu, bucket_mask != 0);
-            while (bm) {
-                const int srcl = __ffs(bm) - 1;
-                bm &= bm - 1;
-                unsigned qm = __shfl_sync(0xffffffffu, bucket_mask, srcl);
-                while (qm) {
-                    const int q = __ffs(qm) - 1;
-                    qm &= qm - 1;
-                    int id = 0;
+            if (m_bucket) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) id = (k == q) ? e[k] : id;
-                    id = __shfl_sync(0xffffffffu, id, srcl);
-                    const int4 bmt = __ldg(cell_meta + id);
-                    append_bucket(bmt.x, bmt.y);
+                for (int j = 0; j < ITEMS; ++j) {
+                    unsigned bm = __ballot_sync(0xffffffffu, is_bucket[j]);
+                    while (bm) {
+                        const int srcl = __ffs(bm) - 1;
+                        bm &= bm - 1;
+                        const int id = (int)(__shfl_sync(0xffffffffu, w[j].x, srcl) >> 3);
+                        const int4 bmt = __ldg(cell_meta + id);
+                        append_bucket(bmt.x, bmt.y);
+                    }
                 }
             }
         }
+        const unsigned acc_cells = __reduce_add_sync(0xffffffffu, my_cells);
+        const unsigned dir_bodies = __reduce_add_sync(0xffffffffu, my_bodies) + bucket_bodies;
 
         // ---- what is still pending: full tiles, then the last partial one (zero-mass padding adds 0) ----
         drain();
@@ -509,8 +528,8 @@ int bh_force_prepare() {
 }
 
 int bh_force_launch(const float4* posm, const void* keys, int levels, const int32_t* ids, int64_t n, int64_t first_body,
-                    int64_t body_count, const int4* cell_meta, const int32_t* cell_child, const float4* cell_com,
-                    const float4* kid_src, const uint8_t* kid_lv,
+                    int64_t body_count, const int4* cell_meta, const float4* cell_com,
+                    const float4* kid_src, const uint2* kid_info,
                     float4* acc, BhDevScalars* sc, uint32_t* heavy_list, uint32_t* heavy_flag, int64_t max_chunks,
                     float theta, float softening, float G, float split_alpha, int num_sms, const float4* src_posm,
                     const BhDevScalars* tree_sc, int accumulate, cudaStream_t st) {
@@ -534,12 +553,12 @@ int bh_force_launch(const float4* posm, const void* keys, int levels, const int3
     if (grid > want) grid = want;
     if (levels == 20)
         force_kernel<20><<<(int)grid, FORCE_THREADS, 0, st>>>(posm, (const uint64_t*)keys, ids, first_body, body_count, cell_meta,
-                                                             cell_child, cell_com, kid_src, kid_lv, acc, sc, heavy_list,
+                                                             cell_com, kid_src, kid_info, acc, sc, heavy_list,
                                                              heavy_flag, max_chunks, theta, softening, G, split_alpha, src_posm, tree_sc,
                                                              accumulate);
     else
         force_kernel<10><<<(int)grid, FORCE_THREADS, 0, st>>>(posm, (const uint32_t*)keys, ids, first_body, body_count, cell_meta,
-                                                             cell_child, cell_com, kid_src, kid_lv, acc, sc, heavy_list,
+                                                             cell_com, kid_src, kid_info, acc, sc, heavy_list,
                                                              heavy_flag, max_chunks, theta, softening, G, split_alpha, src_posm, tree_sc,
                                                              accumulate);
     return (int)cudaGetLastError();

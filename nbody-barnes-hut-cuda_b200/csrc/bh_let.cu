@@ -116,10 +116,12 @@ __global__ void __launch_bounds__(LT) let_level_kernel(LetArgs a, const int2* __
         const int4 lo = __ldg(ch), hi = __ldg(ch + 1);
         const uint2 lv = __ldg(reinterpret_cast<const uint2*>(a.kid_lv) + cell);
         const int e[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        int r = 0;   // kid_src lines are dense: the r-th existing child
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
             if (e[q] == BH_CHILD_EMPTY) continue;
-            const float4 s = __ldg(a.kid_src + (size_t)cell * 8 + q);
+            const float4 s = __ldg(a.kid_src + (size_t)cell * 8 + r);
+            ++r;
             if (e[q] < 0) { let_emit(a, peer, s); continue; }
             const unsigned info = ((q < 4 ? lv.x : lv.y) >> (8 * (q & 3))) & 0xFFu;
             if (let_accepts(a, peer, s, (int)(info & 0x7Fu))) let_emit(a, peer, s);

@@ -22,6 +22,13 @@
 //   parent     = the cell owning the tighter of the two pairs that bound the range, lv(l-1) vs
 //                lv(r) — its id is scan[leader(that pair)].
 // Every cell and every loose body then writes itself into its parent's child table.
+//
+// Traversal view of the tree (written by the centre-of-mass pass, read by bh_force.cu / bh_let.cu): per cell one
+// DENSE line of its children in digit order — kid_src[8c + r] = what child r contributes as a source (a loose
+// body's {x,y,z,m}, a child cell's {centre of mass, mass}), kid_info[8c + r] = {stack word of the child cell
+// (id << 3 | its own child count - 1), level | bucket << 7 | body << 8}, r < number of children.  The octree of
+// the reference disk holds 3.2 children per cell: dense lines let the traversal spend its lanes on children that
+// exist.  cell_child stays the canonical digit-indexed table (parity tests, this pass).
 #include "bh_common.cuh"
 
 namespace {
@@ -201,10 +208,10 @@ __global__ void __launch_bounds__(TB) init_cells_kernel(int4* __restrict__ child
 
 // ---- pass E: every cell and every loose body links itself under its parent -------------------
 template <int LEVELS>
-__global__ void __launch_bounds__(TB) link_kernel(const typename BhKey<LEVELS>::type* __restrict__ K, const float4* __restrict__ posm, int n,
+__global__ void __launch_bounds__(TB) link_kernel(const typename BhKey<LEVELS>::type* __restrict__ K, int n,
                                                  const int2* __restrict__ pair_info,
                                                  const int32_t* __restrict__ pair_scan, int4* __restrict__ cell_meta,
-                                                 int32_t* __restrict__ cell_child, float4* __restrict__ kid_src,
+                                                 int32_t* __restrict__ cell_child,
                                                  uint8_t* __restrict__ kid_lv, BhDevScalars* sc) {
     for (int i = blockIdx.x * TB + threadIdx.x; i < n; i += gridDim.x * TB) {
         const typename BhKey<LEVELS>::type ki = __ldg(K + i);
@@ -218,7 +225,6 @@ __global__ void __launch_bounds__(TB) link_kernel(const typename BhKey<LEVELS>::
             const int parent = pair_scan[pair_info[sp].x];
             const int slot = (int)(ki >> (3 * LEVELS - 3 * (Lb + 1))) & 7;
             cell_child[(size_t)parent * 8 + slot] = (int)(0x80000000u | (uint32_t)i);
-            kid_src[(size_t)parent * 8 + slot] = __ldg(posm + i);   // what the traversal reads when it opens `parent`
         }
 
         // (2) pair i, if it leads a cell
@@ -258,25 +264,49 @@ __device__ __forceinline__ void add_body(Moments& s, const float4 p) {
     s.z = __fmaf_rn(p.w, p.z, s.z);
 }
 
-__device__ __forceinline__ void store_cell(float4* __restrict__ mom, float4* __restrict__ com,
-                                           float4* __restrict__ kid_src, int c, const int4 mt, const Moments& s) {
+__device__ __forceinline__ float4 store_cell(float4* __restrict__ mom, float4* __restrict__ com, int c, const Moments& s) {
     __stcg(mom + c, make_float4(s.x, s.y, s.z, s.m));
     const float inv = (s.m > 1e-6f) ? __fdiv_rn(1.0f, s.m) : 0.0f;   // bench:181-183
     const float4 cm = make_float4(__fmul_rn(s.x, inv), __fmul_rn(s.y, inv), __fmul_rn(s.z, inv), s.m);
     com[c] = cm;
-    if (mt.w >= 0) kid_src[(size_t)mt.w * 8 + ((mt.z >> 12) & 7)] = cm;   // the parent's view of this child
+    return cm;
+}
+
+// Sums the children of a cell in slot (digit) order — run-to-run identical, equal to the oracle bit for bit —
+// and writes the dense traversal entries of its loose bodies (child cells write their own entry when they
+// finish, see below).  Returns the number of children.
+__device__ __forceinline__ int sum_children(const int e[8], const float4* __restrict__ posm, const float4* __restrict__ mom,
+                                            int c, float4* __restrict__ kid_src, uint2* __restrict__ kid_info, Moments& t) {
+    int r = 0;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        if (e[q] == BH_CHILD_EMPTY) continue;
+        if (e[q] < 0) {
+            const float4 p = __ldg(posm + (e[q] & 0x7FFFFFFF));
+            add_body(t, p);
+            kid_src[(size_t)c * 8 + r] = p;
+            kid_info[(size_t)c * 8 + r] = make_uint2(0xFFFFFFFFu, BH_KID_BODY);
+        } else {
+            const float4 cm = __ldcg(mom + e[q]);
+            t.m = __fadd_rn(t.m, cm.w); t.x = __fadd_rn(t.x, cm.x);
+            t.y = __fadd_rn(t.y, cm.y); t.z = __fadd_rn(t.z, cm.z);
+        }
+        ++r;
+    }
+    return r;
 }
 
 __global__ void __launch_bounds__(TB) com_kernel(const float4* __restrict__ posm, const int4* __restrict__ cell_meta,
                                                 const int32_t* __restrict__ cell_child, int32_t* __restrict__ arrive,
                                                 float4* __restrict__ mom, float4* __restrict__ com,
-                                                float4* __restrict__ kid_src, const BhDevScalars* __restrict__ sc) {
+                                                float4* __restrict__ kid_src, uint2* __restrict__ kid_info, BhDevScalars* sc) {
     const int M = sc->num_cells;
     const int4* child4 = reinterpret_cast<const int4*>(cell_child);
     for (int c0 = blockIdx.x * TB + threadIdx.x; c0 < M; c0 += gridDim.x * TB) {
         int c = c0;
         int4 mt = __ldg(cell_meta + c);
         Moments s = {0.f, 0.f, 0.f, 0.f};
+        int nkids = 1;   // children of c (buckets are never opened as cells: the field is unused for them)
         if ((mt.z >> 8) & 1) {
             for (int i = mt.x; i < mt.x + mt.y; ++i) add_body(s, __ldg(posm + i));
         } else {
@@ -286,20 +316,26 @@ __global__ void __launch_bounds__(TB) com_kernel(const float4* __restrict__ posm
 #pragma unroll
             for (int q = 0; q < 8; ++q) has_cell |= (e[q] >= 0 && e[q] != BH_CHILD_EMPTY);
             if (has_cell) continue;  // finished later by its last-arriving child cell
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-                if (e[q] < 0) add_body(s, __ldg(posm + (e[q] & 0x7FFFFFFF)));
+            nkids = sum_children(e, posm, mom, c, kid_src, kid_info, s);
         }
-        store_cell(mom, com, kid_src, c, mt, s);
+        float4 cm = store_cell(mom, com, c, s);
         // climb while this thread is the last child cell to arrive
         for (;;) {
             const int p = mt.w;
-            if (p < 0) break;
+            if (p < 0) { sc->root_word = ((unsigned)c << 3) | (unsigned)(nkids - 1); break; }
             const int4 lo = __ldg(child4 + 2 * p), hi = __ldg(child4 + 2 * p + 1);
             const int e[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-            int ncc = 0;
+            const int myslot = (mt.z >> 12) & 7;
+            int ncc = 0, rank = 0;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) ncc += (e[q] >= 0 && e[q] != BH_CHILD_EMPTY);
+            for (int q = 0; q < 8; ++q) {
+                ncc += (e[q] >= 0 && e[q] != BH_CHILD_EMPTY);
+                rank += (q < myslot && e[q] != BH_CHILD_EMPTY);
+            }
+            // the parent's view of this cell: source + the word the traversal pushes to open it later
+            kid_src[(size_t)p * 8 + rank] = cm;
+            kid_info[(size_t)p * 8 + rank] =
+                make_uint2(((unsigned)c << 3) | (unsigned)(nkids - 1), (unsigned)(mt.z & 0xFF) | (((mt.z >> 8) & 1) ? BH_KID_BUCKET : 0u));
             __threadfence();   // publish this cell's moments (st.cg) before announcing arrival
             const int old = atomicAdd(arrive + p, 1);
             if (old + 1 < ncc) break;
@@ -307,19 +343,10 @@ __global__ void __launch_bounds__(TB) com_kernel(const float4* __restrict__ posm
             // ld.cg (L2, the coherence point) below, after the atomic's result is known — the pattern of the
             // CUDA threadFenceReduction sample; no second fence is needed
             Moments t = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {   // slot order => run-to-run identical sums
-                if (e[q] == BH_CHILD_EMPTY) continue;
-                if (e[q] < 0) add_body(t, __ldg(posm + (e[q] & 0x7FFFFFFF)));
-                else {
-                    const float4 cm = __ldcg(mom + e[q]);
-                    t.m = __fadd_rn(t.m, cm.w); t.x = __fadd_rn(t.x, cm.x);
-                    t.y = __fadd_rn(t.y, cm.y); t.z = __fadd_rn(t.z, cm.z);
-                }
-            }
+            nkids = sum_children(e, posm, mom, p, kid_src, kid_info, t);
             c = p;
             mt = __ldg(cell_meta + c);
-            store_cell(mom, com, kid_src, c, mt, t);
+            cm = store_cell(mom, com, c, t);
         }
     }
 }
@@ -335,9 +362,9 @@ inline int capped_grid(int64_t work_items, int per_block) {
 
 // keys: ascending u32 keys of 10 digits (levels == 10, the reference's 30-bit key) or u64 keys of 20 digits
 // (levels == 20, bh_params.key_bits = 60)
-int bh_tree_launch(const void* keys, int levels, const float4* posm, int64_t n64, int2* pair_info, int32_t* pair_scan,
+int bh_tree_launch(const void* keys, int levels, int64_t n64, int2* pair_info, int32_t* pair_scan,
                    int32_t* scan_block_sums, int4* cell_meta, int32_t* cell_child,
-                   int32_t* cell_arrive, float4* kid_src, uint8_t* kid_lv, BhDevScalars* sc, cudaStream_t st) {
+                   int32_t* cell_arrive, uint8_t* kid_lv, BhDevScalars* sc, cudaStream_t st) {
     const int n = (int)n64;
     if (n < 2) return 0;
     const int ntiles = (n - 1 + SCAN_TILE - 1) / SCAN_TILE;
@@ -347,18 +374,18 @@ int bh_tree_launch(const void* keys, int levels, const float4* posm, int64_t n64
     scan_pairs_kernel<<<ntiles, TB, 0, st>>>(pair_info, n, scan_block_sums, pair_scan);
     init_cells_kernel<<<capped_grid(n, TB), TB, 0, st>>>(reinterpret_cast<int4*>(cell_child), cell_arrive, sc);
     if (levels == 20)
-        link_kernel<20><<<capped_grid(n, TB), TB, 0, st>>>((const uint64_t*)keys, posm, n, pair_info, pair_scan, cell_meta, cell_child, kid_src, kid_lv, sc);
+        link_kernel<20><<<capped_grid(n, TB), TB, 0, st>>>((const uint64_t*)keys, n, pair_info, pair_scan, cell_meta, cell_child, kid_lv, sc);
     else
-        link_kernel<10><<<capped_grid(n, TB), TB, 0, st>>>((const uint32_t*)keys, posm, n, pair_info, pair_scan, cell_meta, cell_child, kid_src, kid_lv, sc);
+        link_kernel<10><<<capped_grid(n, TB), TB, 0, st>>>((const uint32_t*)keys, n, pair_info, pair_scan, cell_meta, cell_child, kid_lv, sc);
     return (int)cudaGetLastError();
 }
 
 int bh_com_launch(const float4* posm, int64_t n, const int4* cell_meta, const int32_t* cell_child,
-                  int32_t* cell_arrive, float4* cell_mom, float4* cell_com, float4* kid_src,
+                  int32_t* cell_arrive, float4* cell_mom, float4* cell_com, float4* kid_src, uint2* kid_info,
                   BhDevScalars* sc, cudaStream_t st) {
     if (n < 2) return 0;
     // one thread per possible cell, no grid-stride: a thread that climbs towards the root must not delay
     // the leaf-level cells a strided loop would hand it next
-    com_kernel<<<(int)((n + TB - 1) / TB), TB, 0, st>>>(posm, cell_meta, cell_child, cell_arrive, cell_mom, cell_com, kid_src, sc);
+    com_kernel<<<(int)((n + TB - 1) / TB), TB, 0, st>>>(posm, cell_meta, cell_child, cell_arrive, cell_mom, cell_com, kid_src, kid_info, sc);
     return (int)cudaGetLastError();
 }
