@@ -22,10 +22,11 @@
 #define BH_DERR_TREE        8   // builder found an inconsistent range
 #define BH_DERR_LET_OVERFLOW 16  // locally-essential-tree export ran out of output / queue space
 
-// kid_info[8c + r].y: level of a child cell in the low bits, plus
-#define BH_KID_LEVEL_MASK 0x1Fu
-#define BH_KID_BUCKET     0x80u    // child cell is an identical-key bucket (contiguous body range, never opened)
-#define BH_KID_BODY       0x100u   // child is a loose body (always a source)
+// kid_info[8c + r] = {x: child cell id << 3 | its child count - 1 | BH_KID_BUCKET, y: float bits of the child cell's
+// squared width root_w^2 * 4^-level}; a loose body has x = 0xFFFFFFFF... and y = bits of -1.0f, which passes
+// every acceptance test `w^2 < theta^2 (d^2 + softening)` — bodies are always sources
+#define BH_KID_BUCKET     0x80000000u   // child cell is an identical-key bucket (contiguous body range, never opened)
+#define BH_KID_BODY_W2    0xBF800000u   // -1.0f
 
 struct BhDevScalars {        // one small device struct, zeroed/filled by kernels
     float bounds[6];         // as d_bounds (nbody_v5_bench.cu:149-154)
@@ -119,7 +120,7 @@ int bh_tree_launch(const void* keys, int levels, int64_t n, int2* pair_info, int
                    int32_t* cell_arrive, uint8_t* kid_lv, BhDevScalars* sc, cudaStream_t st);
 // kid_src / kid_info: 8 entries per cell, DENSE (the r-th existing child in digit order sits at 8c + r) — the SOURCE
 // each child contributes when its parent is opened (a loose body's {x,y,z,m}, a child cell's {com,mass}) and
-// {stack word of a child cell = id << 3 | its child count - 1, level | BH_KID_BUCKET | BH_KID_BODY}.
+// {stack word of a child cell = id << 3 | its child count - 1 | BH_KID_BUCKET, squared width as float bits}.
 int bh_com_launch(const float4* posm, int64_t n, const int4* cell_meta, const int32_t* cell_child,
                   int32_t* cell_arrive, float4* cell_mom, float4* cell_com, float4* kid_src, uint2* kid_info,
                   BhDevScalars* sc, cudaStream_t st);

@@ -268,7 +268,7 @@ const char* bh_error_string(int code) {
 }
 
 int bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device) {
-    if (!out || n_max <= 0 || n_max >= ((int64_t)1 << 29)) return BH_E_INVAL;   // traversal stack words are cell id << 3
+    if (!out || n_max <= 0 || n_max >= ((int64_t)1 << 28)) return BH_E_INVAL;   // traversal stack words are cell id << 3 | flag
     *out = nullptr;
     bh_params prm;
     if (params) prm = *params; else bh_default_params(&prm);
@@ -551,7 +551,7 @@ int bh_let_export(bh_ctx* c, const float* boxes_lohi, int npeers, int K, void* o
         int e = bh_let_export_launch(c->cell_meta, c->cell_child, c->cell_com, c->kid_src, c->kid_lv, c->posm_s, c->sc,
                                      c->let_boxes, c->let_boxes + (size_t)npeers * K * 6, npeers, K, (float4*)out, c->let_counts, cap_per_peer, c->let_queue,
                                      c->let_counts + BH_LET_MAX_PEERS, c->let_qcap, c->prm.theta, c->prm.softening,
-                                     h.bounds[3] - h.bounds[0], c->levels, st);
+                                     fmaxf(h.bounds[3] - h.bounds[0], 1.0f), c->levels, st);
         if (e) return e;
         unsigned int hc[BH_LET_MAX_PEERS];
         BH_CUDA_TRY(cudaMemcpyAsync(hc, c->let_counts, sizeof(unsigned int) * npeers, cudaMemcpyDeviceToHost, st));

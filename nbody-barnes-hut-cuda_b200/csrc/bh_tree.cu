@@ -26,7 +26,7 @@
 // Traversal view of the tree (written by the centre-of-mass pass, read by bh_force.cu / bh_let.cu): per cell one
 // DENSE line of its children in digit order — kid_src[8c + r] = what child r contributes as a source (a loose
 // body's {x,y,z,m}, a child cell's {centre of mass, mass}), kid_info[8c + r] = {stack word of the child cell
-// (id << 3 | its own child count - 1), level | bucket << 7 | body << 8}, r < number of children.  The octree of
+// (id << 3 | its own child count - 1 | bucket flag), its squared width as float bits (-1 for a body)}, r < number of children.  The octree of
 // the reference disk holds 3.2 children per cell: dense lines let the traversal spend its lanes on children that
 // exist.  cell_child stays the canonical digit-indexed table (parity tests, this pass).
 #include "bh_common.cuh"
@@ -285,7 +285,7 @@ __device__ __forceinline__ int sum_children(const int e[8], const float4* __rest
             const float4 p = __ldg(posm + (e[q] & 0x7FFFFFFF));
             add_body(t, p);
             kid_src[(size_t)c * 8 + r] = p;
-            kid_info[(size_t)c * 8 + r] = make_uint2(0xFFFFFFFFu, BH_KID_BODY);
+            kid_info[(size_t)c * 8 + r] = make_uint2(0x7FFFFFFFu, BH_KID_BODY_W2);
         } else {
             const float4 cm = __ldcg(mom + e[q]);
             t.m = __fadd_rn(t.m, cm.w); t.x = __fadd_rn(t.x, cm.x);
@@ -302,6 +302,10 @@ __global__ void __launch_bounds__(TB) com_kernel(const float4* __restrict__ posm
                                                 float4* __restrict__ kid_src, uint2* __restrict__ kid_info, BhDevScalars* sc) {
     const int M = sc->num_cells;
     const int4* child4 = reinterpret_cast<const int4*>(cell_child);
+    // squared width of a level-L cell: root_w^2 with 2L taken off the exponent (exact); root_w is the key
+    // grid's size, clamped like bench:52
+    const float root_w = fmaxf(__fsub_rn(sc->bounds[3], sc->bounds[0]), 1.0f);
+    const int root_w2_bits = __float_as_int(__fmul_rn(root_w, root_w));
     for (int c0 = blockIdx.x * TB + threadIdx.x; c0 < M; c0 += gridDim.x * TB) {
         int c = c0;
         int4 mt = __ldg(cell_meta + c);
@@ -335,7 +339,8 @@ __global__ void __launch_bounds__(TB) com_kernel(const float4* __restrict__ posm
             // the parent's view of this cell: source + the word the traversal pushes to open it later
             kid_src[(size_t)p * 8 + rank] = cm;
             kid_info[(size_t)p * 8 + rank] =
-                make_uint2(((unsigned)c << 3) | (unsigned)(nkids - 1), (unsigned)(mt.z & 0xFF) | (((mt.z >> 8) & 1) ? BH_KID_BUCKET : 0u));
+                make_uint2(((unsigned)c << 3) | (unsigned)(nkids - 1) | (((mt.z >> 8) & 1) ? BH_KID_BUCKET : 0u),
+                           (unsigned)(root_w2_bits - ((mt.z & 0xFF) << 24)));
             __threadfence();   // publish this cell's moments (st.cg) before announcing arrival
             const int old = atomicAdd(arrive + p, 1);
             if (old + 1 < ncc) break;

@@ -571,7 +571,7 @@ void orc_force_groups(const float* posm, int64_t n64, const float* bounds,
                       int64_t M64, int32_t root, const int32_t* gstart, int ngroups, float theta, float soft, float G,
                       float* acc, int64_t* counts, int32_t* group_entries) {
     const int n = (int)n64; (void)n;
-    const float root_w = bounds[3] - bounds[0];
+    const float root_w = fmaxf(bounds[3] - bounds[0], 1.0f);   // the key grid's size, clamped like bench:52
     const float theta2 = theta * theta;
     float w2[MAX_LEVELS_ANY + 1];
     for (int L = 0; L <= MAX_LEVELS_ANY; ++L) w2[L] = w2_of_level(root_w, L);
@@ -713,7 +713,7 @@ void orc_force_body(const float* posm, int64_t n64, const float* bounds,
                     int64_t /*M*/, int32_t root, float theta, float soft, float G,
                     float* acc, int64_t* counts) {
     const int n = (int)n64;
-    const float root_w = bounds[3] - bounds[0];
+    const float root_w = fmaxf(bounds[3] - bounds[0], 1.0f);   // the key grid's size, clamped like bench:52
     int64_t ncell = 0, nbody = 0;
 #pragma omp parallel for schedule(dynamic, 256) reduction(+ : ncell, nbody)
     for (int i = 0; i < n; ++i) {

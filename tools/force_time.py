@@ -9,12 +9,13 @@ import nbody_barnes_hut_cuda_b200 as bh  # noqa: E402
 wl = sys.argv[1] if len(sys.argv) > 1 else "refdisk_1m"
 w = bench.WORKLOADS[wl]
 soa = bench.make_ic(bh, w)
-eng = bh.BHEngine(w["n"], flags=2)
+kw = {"group_split": float(os.environ["BH_SPLIT"])} if "BH_SPLIT" in os.environ else {}
+eng = bh.BHEngine(w["n"], flags=2, **kw)
 eng.load_soa(*soa)
 eng.simulation_step(5)
 eng.simulation_step(20)
 ms = eng.phase_ms()
-print(os.environ.get("BH_LIB", "default").split("/")[-1], wl, {k: round(v / 20, 4) for k, v in ms.items()},
+print(os.environ.get("BH_LIB", "default").split("/")[-1], "split", os.environ.get("BH_SPLIT", "-"), wl, {k: round(v / 20, 4) for k, v in ms.items()},
       "int/body", (eng.stat(bh.STAT.INTERACTIONS_CELL) + eng.stat(bh.STAT.INTERACTIONS_BODY)) / w["n"],
       "cell/body", eng.stat(bh.STAT.INTERACTIONS_CELL) / w["n"], "direct/body", eng.stat(bh.STAT.INTERACTIONS_BODY) / w["n"],
       "cells/n", eng.stat(bh.STAT.CELLS) / w["n"])
