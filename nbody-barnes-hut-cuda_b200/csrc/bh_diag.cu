@@ -69,7 +69,9 @@ __global__ void __launch_bounds__(DT) energy_kernel(const float4* __restrict__ p
 __global__ void __launch_bounds__(DT) visuals_kernel(const float4* __restrict__ posm, const float4* __restrict__ vel,
                                                     const int32_t* __restrict__ ids, int64_t n, float* vbo_p, float* vbo_c) {
     for (int64_t i = (int64_t)blockIdx.x * DT + threadIdx.x; i < n; i += (int64_t)gridDim.x * DT) {
-        const int64_t o = 3 * (int64_t)ids[i];
+        const int32_t id = ids[i];
+        if (id < 0 || (int64_t)id >= n) continue;   // ghosts / global ids have no slot in an n-vertex buffer
+        const int64_t o = 3 * (int64_t)id;
         if (vbo_p) {
             const float4 p = __ldg(posm + i);
             vbo_p[o] = p.x; vbo_p[o + 1] = p.y; vbo_p[o + 2] = p.z;

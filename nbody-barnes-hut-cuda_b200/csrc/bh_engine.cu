@@ -546,6 +546,11 @@ int bh_let_export(bh_ctx* c, const float* boxes_lohi, int npeers, int K, void* o
     BH_CUDA_TRY(cudaStreamSynchronize(st));
     BhDevScalars h;
     BH_CUDA_TRY(cudaMemcpy(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost));
+    // overflow is reported per call: a list that did not fit last time must not fail this (larger) attempt
+    if (h.err & BH_DERR_LET_OVERFLOW) {
+        const unsigned int cleared = h.err & ~(unsigned int)BH_DERR_LET_OVERFLOW;
+        BH_CUDA_TRY(cudaMemcpy((char*)c->sc + offsetof(BhDevScalars, err), &cleared, 4, cudaMemcpyHostToDevice));
+    }
     BH_CUDA_TRY(cudaMemcpy(c->let_boxes, boxes.data(), sizeof(float) * boxes.size(), cudaMemcpyHostToDevice));
     if (c->n >= 2) {
         int e = bh_let_export_launch(c->cell_meta, c->cell_child, c->cell_com, c->kid_src, c->kid_lv, c->posm_s, c->sc,
@@ -861,14 +866,17 @@ int bh_momentum(bh_ctx* c, double out[7]) {
 
 // ---- state I/O ----------------------------------------------------------------
 namespace {
-struct CkptHeader {
-    char magic[8];       // "BHB200\0\0"
-    int32_t version;
-    int32_t reserved;
+struct CkptHeader {       // explicit fixed-width fields: the file format does not follow the ABI struct
+    char magic[8];        // "BHB200\0\0"
+    int32_t version;      // 2
+    int32_t header_bytes; // sizeof(CkptHeader)
     int64_t n;
     int64_t steps;
-    bh_params prm;
+    float theta, G, dt, softening, max_speed;
+    int32_t key_bits, leaf_cap;
+    int32_t reserved;
 };
+const int32_t kCkptVersion = 2;
 const char kMagic[8] = {'B', 'H', 'B', '2', '0', '0', 0, 0};
 }  // namespace
 
@@ -906,7 +914,9 @@ int bh_save_checkpoint(bh_ctx* c, const char* path) {
     BH_CUDA_TRY(cudaMemcpy(ids.data(), c->ids, n * 4, cudaMemcpyDeviceToHost));
     CkptHeader h{};
     memcpy(h.magic, kMagic, 8);
-    h.version = 1; h.n = c->n; h.steps = c->steps; h.prm = c->prm;
+    h.version = kCkptVersion; h.header_bytes = (int32_t)sizeof(CkptHeader); h.n = c->n; h.steps = c->steps;
+    h.theta = c->prm.theta; h.G = c->prm.G; h.dt = c->prm.dt; h.softening = c->prm.softening; h.max_speed = c->prm.max_speed;
+    h.key_bits = c->prm.key_bits; h.leaf_cap = c->prm.leaf_cap;
     FILE* f = fopen(path, "wb");
     if (!f) return BH_E_IO;
     bool ok = fwrite(&h, sizeof(h), 1, f) == 1 && fwrite(posm.data(), 16, n, f) == n && fwrite(vel.data(), 16, n, f) == n &&
@@ -920,10 +930,15 @@ int bh_load_checkpoint(bh_ctx* c, const char* path) {
     FILE* f = fopen(path, "rb");
     if (!f) return BH_E_IO;
     CkptHeader h{};
-    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, kMagic, 8) != 0 || h.version != 1 || h.n <= 0 || h.n > c->n_max) {
+    if (fread(&h, sizeof(h), 1, f) != 1 || memcmp(h.magic, kMagic, 8) != 0 || h.version != kCkptVersion ||
+        h.header_bytes != (int32_t)sizeof(CkptHeader) || h.n <= 0 || h.n > c->n_max) {
         fclose(f);
         return BH_E_IO;
     }
+    // the same checks bh_create applies; a different key width or leaf capacity builds a different tree, which
+    // would break the bit-for-bit resume
+    if (!(h.softening > 0.0f) || !(h.theta >= 0.0f) || !(h.max_speed > 0.0f)) { fclose(f); return BH_E_IO; }
+    if (h.key_bits != c->prm.key_bits || h.leaf_cap != c->prm.leaf_cap) { fclose(f); return BH_E_UNSUPPORTED; }
     const size_t n = (size_t)h.n;
     std::vector<float4> posm(n), vel(n);
     std::vector<int32_t> ids(n);
@@ -936,8 +951,8 @@ int bh_load_checkpoint(bh_ctx* c, const char* path) {
     BH_CUDA_TRY(cudaMemcpy(c->vel, vel.data(), n * 16, cudaMemcpyHostToDevice));
     BH_CUDA_TRY(cudaMemcpy(c->ids, ids.data(), n * 4, cudaMemcpyHostToDevice));
     // simulation parameters travel with the state; flags and tuning knobs stay the context's own
-    c->prm.theta = h.prm.theta; c->prm.G = h.prm.G; c->prm.dt = h.prm.dt;
-    c->prm.softening = h.prm.softening; c->prm.max_speed = h.prm.max_speed;
+    c->prm.theta = h.theta; c->prm.G = h.G; c->prm.dt = h.dt;
+    c->prm.softening = h.softening; c->prm.max_speed = h.max_speed;
     c->n = h.n; c->steps = h.steps; c->have_state = true; c->have_sorted = false;
     default_slice(c);
     BH_CUDA_TRY(cudaMemset((char*)c->sc + offsetof(BhDevScalars, epoch), 0, sizeof(BhDevScalars) - offsetof(BhDevScalars, epoch)));

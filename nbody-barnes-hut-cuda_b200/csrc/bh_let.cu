@@ -101,14 +101,15 @@ __global__ void let_seed_kernel(LetArgs a, int npeers, const BhDevScalars* sc, i
     const int4 mt = __ldg(a.cell_meta + root);
     if (let_accepts(a, r, cm, mt.z & 0xFF)) let_emit(a, r, cm);
     else if ((mt.z >> 8) & 1) let_emit_bucket(a, r, mt.x, mt.y);
-    else queue[atomicAdd(qcount, 1u)] = make_int2(root, r);
+    else queue[atomicAdd(qcount, 1u)] = make_int2(root, r);   // <= npeers <= BH_LET_MAX_PEERS entries: always fits
 }
 
 // open every queued cell for its peer; children that are rejected in turn go to the next level's queue
 __global__ void __launch_bounds__(LT) let_level_kernel(LetArgs a, const int2* __restrict__ qin,
                                                       const unsigned int* __restrict__ qin_count, int2* __restrict__ qout,
                                                       unsigned int* qout_count, long long qcap) {
-    const unsigned int nin = *qin_count;
+    // the producer counts past the capacity without storing (and raises BH_DERR_LET_OVERFLOW): never read beyond it
+    const unsigned int nin = (unsigned int)min((long long)*qin_count, qcap);
     for (unsigned int idx = blockIdx.x * LT + threadIdx.x; idx < nin; idx += gridDim.x * LT) {
         const int2 item = qin[idx];
         const int cell = item.x, peer = item.y;

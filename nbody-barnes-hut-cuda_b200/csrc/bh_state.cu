@@ -306,6 +306,10 @@ __global__ void __launch_bounds__(kThreads) export_kernel(const float4* __restri
                                                          float* vy, float* vz, float* ax, float* ay, float* az) {
     for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
         const int32_t o = ids[i];
+        // slot i = body i only holds for ids that are a permutation of [0, n): contexts filled through
+        // bh_import_state / a checkpoint may carry ghosts (-1) or global ids — those slots have no place in
+        // the caller's n-element arrays (bh_direct_sample guards the same way)
+        if (o < 0 || (int64_t)o >= n) continue;
         if (px || py || pz) {
             float4 p = __ldg(posm + i);
             if (px) px[o] = p.x;

@@ -427,6 +427,14 @@ class LetSimulation:
         self.dist.all_to_all_single(recv, send.contiguous(), output_split_sizes=rc, input_split_sizes=sc)
         return recv
 
+    def _agree(self, ok: bool, what: str):
+        """A capacity error seen by ONE rank must be raised by ALL of them, or the others block in the next
+        collective: one MIN all-reduce of the local verdict, then everybody raises (or nobody)."""
+        flag = self.torch.tensor([1 if ok else 0], dtype=self.torch.int32, device=self.device)
+        self.dist.all_reduce(flag, op=self.dist.ReduceOp.MIN)
+        if int(flag.item()) == 0:
+            raise self.rank.bh.BHError(f"{what} (on rank {self.rankno}: {'ok' if ok else 'FAILED'}); every rank stops together")
+
     def step(self, nsteps: int = 1):
         torch, dist, w, me = self.torch, self.dist, self.world, self.rankno
         for _ in range(nsteps):
@@ -459,6 +467,7 @@ class LetSimulation:
                 sc, rc = sc_np.tolist(), recv_counts.cpu().numpy().tolist()
                 migrated = int(sum(sc)) - int(sc[me])
                 v = views if views is not None else (None, None, None)
+                self._agree(int(sum(rc)) <= self.rank.capacity, f"migration: {int(sum(rc))} bodies exceed the context capacity {self.rank.capacity}")
                 tp, tv, ti = self.rank.spare(int(sum(rc)))
                 self._all_to_all_rows(v[0], sc, rc, (4,), torch.float32, out=tp)
                 self._all_to_all_rows(v[1], sc, rc, (4,), torch.float32, out=tv)
@@ -473,7 +482,11 @@ class LetSimulation:
             doms = torch.empty((w, MAX_BOXES, 6), dtype=torch.float32, device=self.device)
             dist.all_gather_into_tensor(doms, dom)
             t = self._mark("domain boxes", t)
-            counts = self.rank.export(compact_boxes(doms.cpu().numpy()), me)
+            try:
+                counts, export_err = self.rank.export(compact_boxes(doms.cpu().numpy()), me), None
+            except self.rank.bh.BHError as e:   # list or queue overflow (cap_per_peer too small)
+                counts, export_err = np.zeros(w, np.int32), e
+            self._agree(export_err is None, f"LET export: {export_err}")
             t = self._mark("export walk", t)
             send_counts = torch.from_numpy(counts.astype(np.int64)).to(self.device)
             recv_counts = torch.empty_like(send_counts)
@@ -481,6 +494,7 @@ class LetSimulation:
             sc, rc = counts.astype(np.int64).tolist(), recv_counts.cpu().numpy().tolist()
             send = torch.cat([self.rank.out[p, : sc[p]] for p in range(w)]) if sum(sc) else None
             n_imp = int(sum(rc))
+            self._agree(n_imp <= self.rank.ghost_cap, f"LET import: {n_imp} points exceed the ghost capacity {self.rank.ghost_cap}")
             self._all_to_all_rows(send, sc, rc, (4,), torch.float32, out=self.rank.ghost_slot(n_imp))
             t = self._mark("exchange", t)
             self.rank.forces_and_update(n_imp)

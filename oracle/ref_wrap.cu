@@ -7,11 +7,39 @@
 // pair bench:355-363) behind extern "C" so Python can drive it.  Used to (1) pin Oracle-L
 // against the real reference on a B200 and (2) time the reference's own sm_100 build
 // (BASELINE.md B1).  Output goes to oracle/_ref/, which is git-ignored.
-#define main reference_main_unused
-#include REF_SRC
-#undef main
-
+//
+// ref_ic() additionally pins the INITIAL CONDITIONS (bench:294-308): it runs the reference's own main() up to its
+// seven host-to-device copies (bench:329-335).  cudaMemcpy is renamed by a macro for the reference's
+// translation unit only; the hook keeps a copy of each host array and leaves main() by an exception after the
+// seventh, so the benchmark loop never starts and no GPU is needed.
+#include <cuda_runtime.h>
 #include <cstdint>
+#include <cstring>
+#include <vector>
+
+namespace refhook {
+struct IcDone {};
+bool capture = false;
+int calls = 0;
+std::vector<float> host[7];   // posX, posY, posZ, velX, velY, velZ, mass in the order of bench:329-335
+inline cudaError_t memcpy_hook(void* dst, const void* src, size_t bytes, cudaMemcpyKind kind) {
+    if (capture && kind == cudaMemcpyHostToDevice) {
+        if (calls < 7) {
+            host[calls].resize(bytes / 4);
+            std::memcpy(host[calls].data(), src, bytes);
+        }
+        if (++calls == 7) throw IcDone{};
+        return cudaSuccess;
+    }
+    return cudaMemcpy(dst, src, bytes, kind);
+}
+}  // namespace refhook
+
+#define main reference_main_unused
+#define cudaMemcpy refhook::memcpy_hook
+#include REF_SRC
+#undef cudaMemcpy
+#undef main
 
 namespace {
 int g_alloc_n = 0;
@@ -19,6 +47,27 @@ template <class T> cudaError_t dalloc(T** p, size_t bytes) { return cudaMalloc((
 }
 
 extern "C" {
+
+// The reference's own initial conditions for n bodies (its main() run up to the uploads).  Host only.
+int ref_ic(int n, float* px, float* py, float* pz, float* vx, float* vy, float* vz, float* mass) {
+    if (n <= 0) return -1;
+    const int saved = N;
+    N = n;
+    refhook::capture = true;
+    refhook::calls = 0;
+    bool done = false;
+    try { reference_main_unused(); } catch (const refhook::IcDone&) { done = true; }
+    refhook::capture = false;
+    N = saved;
+    if (!done) return -2;
+    float* dst[7] = {px, py, pz, vx, vy, vz, mass};
+    for (int k = 0; k < 7; ++k) {
+        if ((int)refhook::host[k].size() != n) return -3;
+        std::memcpy(dst[k], refhook::host[k].data(), (size_t)n * 4);
+        std::vector<float>().swap(refhook::host[k]);
+    }
+    return 0;
+}
 
 void ref_free(void) {
     if (!g_alloc_n) return;

@@ -3,6 +3,8 @@
   python tests/golden/make_golden.py            # CPU: Oracle-I / Oracle-L outputs (oracle_*.npz)
   python tests/golden/make_golden.py reference  # GPU box: outputs of the UNMODIFIED reference
                                                 # (oracle/_ref/libref_step.so) -> gpurun_out/, copied here
+  python tests/golden/make_golden.py reference_ic  # CPU: digests of the reference's own initial conditions
+                                                # (its main() run up to the uploads, oracle/ref_wrap.cu:ref_ic)
 
 The reference ships no fixtures; reference_b200_*.npz are outputs of its own kernels +
 simulationStep() run on a B200, so the CPU-only suite can pin Oracle-L without a GPU.
@@ -49,6 +51,32 @@ def oracle_golden():
     print("wrote oracle golden", N_ORC)
 
 
+IC_SIZES = (1000, 16384, 500_000, 1_000_000)   # 500,000 = the reference default (bench:31), 1,000,000 = configs[1]
+
+
+def reference_ic(n):
+    """The seven host arrays the unmodified reference uploads (bench:294-308, 329-335)."""
+    L = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libref_step.so"))
+    a = [np.zeros(n, np.float32) for _ in range(7)]
+    assert L.ref_ic(n, *[x.ctypes.data_as(C.c_void_p) for x in a]) == 0
+    return a
+
+
+def ic_digest(arrays):
+    return hashlib.sha256(b"".join(np.ascontiguousarray(x, np.float32).tobytes() for x in arrays)).hexdigest()
+
+
+def reference_ic_golden():
+    import json
+
+    out = {str(n): ic_digest(reference_ic(n)) for n in IC_SIZES}
+    head = {str(n): [float(x[0]) for x in reference_ic(n)] for n in IC_SIZES[:1]}
+    with open(os.path.join(HERE, "reference_ic_sha256.json"), "w") as f:
+        json.dump({"what": "sha256 over posX|posY|posZ|velX|velY|velZ|mass (float32) as produced by the unmodified "
+                           "reference main(), nbody_v5_bench.cu:294-308, srand(42)", "sha256": out, "first_body_n1000": head["1000"]}, f, indent=1)
+    print("wrote reference_ic_sha256.json", out)
+
+
 def reference_golden():
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     from test_gpu_reference_pin import run_reference
@@ -65,6 +93,10 @@ def reference_golden():
                         sorted_keys3=r3["keys"], sorted_idx3=r3["idx"])
     print("wrote", out)
 
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "reference_ic":
+    reference_ic_golden()
+    sys.exit(0)
 
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "reference":

@@ -131,3 +131,37 @@ def test_step_halves_equal_a_full_step(bh):
             got = (eng.debug_get(bh.DBG.POSM), eng.debug_get(bh.DBG.VEL), eng.debug_get(bh.DBG.IDS))
             assert got[0].tobytes() == want[0].tobytes() and got[1].tobytes() == want[1].tobytes()
             assert (got[2] == want[2]).all()
+
+
+def test_soa_and_visual_exports_skip_slots_without_a_local_id(bh):
+    """contexts filled through bh_import_state may hold ghosts (id -1) and global ids >= n; the SoA and
+    vertex-buffer exports index the caller's n-element arrays by id and must leave those slots alone."""
+    import torch
+
+    n = 4096
+    soa = bh.ic_uniform_cube(n, 5, 500.0)
+    posm = torch.from_numpy(np.stack([soa[0], soa[1], soa[2], soa[6]], 1)).cuda()
+    vel = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+    ids_np = np.arange(n, dtype=np.int32)
+    ids_np[::7] = -1                       # ghosts
+    ids_np[3::7] = 1_000_000_000           # ids of another rank's numbering
+    ids = torch.from_numpy(ids_np).cuda()
+    with bh.BHEngine(n) as eng:
+        eng.import_state(posm, vel, ids, n)
+        pad = 1024
+        buf = torch.full((9, n + 2 * pad), -777.0, dtype=torch.float32, device="cuda")
+        ptrs = [buf[k, pad:].data_ptr() for k in range(9)]
+        L = bh.lib()
+        import ctypes as C
+
+        assert L.bh_export_soa(eng._ctx, *[C.c_void_p(p) for p in ptrs], None) == 0
+        vbo = torch.full((2, 3 * n + 2 * pad), -777.0, dtype=torch.float32, device="cuda")
+        eng.export_visuals(vbo[0, pad:].data_ptr(), vbo[1, pad:].data_ptr())
+        torch.cuda.synchronize()
+        h = buf.cpu().numpy()
+        assert (h[:, :pad] == -777.0).all() and (h[:, pad + n:] == -777.0).all()      # nothing written outside
+        local = (ids_np >= 0) & (ids_np < n)
+        assert (h[0, pad:pad + n][local] == soa[0][local]).all()
+        assert (h[0, pad:pad + n][~local] == -777.0).all()                            # skipped, not scattered somewhere
+        v = vbo.cpu().numpy()
+        assert (v[:, :pad] == -777.0).all() and (v[:, pad + 3 * n:] == -777.0).all()

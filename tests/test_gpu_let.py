@@ -323,3 +323,33 @@ def test_global_cube_matches_the_reference_bounds(bh):
     halves = [np.arange(5000) < 2000, np.arange(5000) >= 2000]
     boxes = np.array([[soa[a][h].min() for a in range(3)] + [soa[a][h].max() for a in range(3)] for h in halves], f)
     assert global_cube(boxes).tobytes() == b.tobytes()
+
+
+def test_export_overflow_is_reported_per_call_and_never_reads_past_the_queue(bh):
+    """a list that does not fit raises BH_E_DEVICE for THAT call only (the flag used to stick and every
+    later export failed), and the walk never indexes beyond its queue after an overflow."""
+    import torch
+
+    from nbody_barnes_hut_cuda_b200.engine import PHASE
+    from nbody_barnes_hut_cuda_b200.let import EMPTY_BOX
+
+    n = 20000
+    soa = bh.ic_refdisk(n, 3)
+    with bh.BHEngine(n) as eng:
+        eng.load_soa(*soa)
+        for ph in (PHASE.KEYS, PHASE.SORT, PHASE.BUILD, PHASE.COM):
+            eng.run_phase(ph)
+        ps = eng.debug_get(bh.DBG.POSM_SORTED)
+        lo, hi = ps[:, :3].min(0), ps[:, :3].max(0)
+        ext = hi - lo
+        peers = np.tile(EMPTY_BOX, (2, 1, 1))
+        peers[0, 0] = np.concatenate([lo + 0.4 * ext, lo + 0.6 * ext])      # inside the cloud: thousands of points
+        peers[1, 0] = np.concatenate([hi + 40 * ext, hi + 41 * ext])
+        small = torch.empty((2, 64, 4), dtype=torch.float32, device="cuda")
+        with pytest.raises(bh.BHError):
+            eng.let_export(peers, small, 64)                                # 64 points per peer cannot hold it
+        out = torch.empty((2, n, 4), dtype=torch.float32, device="cuda")
+        counts = eng.let_export(peers, out, n)                              # the same context, enough room: fine
+        assert counts[0] > 64 and counts[1] >= 1
+        mass = out[0, : int(counts[0]), 3].double().sum().item()
+        assert abs(mass - soa[6].astype(np.float64).sum()) / soa[6].sum() < 1e-5   # emitted masses add up

@@ -91,6 +91,38 @@ def test_checkpoint_resume_is_bit_exact(bh, tmp_path):
             small.load_checkpoint(path)          # does not fit: refused, not truncated
 
 
+def test_checkpoint_loader_validates_what_bh_create_validates(bh, tmp_path):
+    """parameters from a file get the range checks of bh_create; a different key width is refused."""
+    import struct
+
+    n = 2000
+    soa = bh.ic_refdisk(n, 42)
+    path = str(tmp_path / "ckpt.bin")
+    with bh.BHEngine(n) as eng:
+        eng.load_soa(*soa)
+        eng.simulation_step(1)
+        eng.save_checkpoint(path)
+    raw = bytearray(open(path, "rb").read())
+    magic, version, hbytes, nn, steps, theta, G, dt, soft, vmax, key_bits, leaf_cap, _ = struct.unpack_from("<8siiqqfffffiii", raw, 0)
+    assert magic == b"BHB200\0\0" and version == 2 and nn == n and steps == 1 and key_bits == 30 and leaf_cap == 1
+    assert (theta, G, dt, soft, vmax) == (0.5, 0.5, struct.unpack("<f", struct.pack("<f", 0.02))[0], 50.0, 500.0)
+    bad = str(tmp_path / "bad.bin")
+    off_soft = 8 + 4 + 4 + 8 + 8 + 3 * 4
+    for patch in (struct.pack("<f", 0.0), struct.pack("<f", -1.0), struct.pack("<f", float("nan"))):
+        b2 = bytearray(raw)
+        b2[off_soft:off_soft + 4] = patch
+        open(bad, "wb").write(b2)
+        with bh.BHEngine(n) as eng, pytest.raises(bh.BHError):
+            eng.load_checkpoint(bad)                     # softening <= 0 would make the self term NaN
+    with bh.BHEngine(n, key_bits=60) as eng, pytest.raises(bh.BHError):
+        eng.load_checkpoint(path)                        # 30-bit file, 60-bit context: a different tree
+    b2 = bytearray(raw)
+    b2[8:12] = struct.pack("<i", 1)                      # the round-1 layout embedded the ABI struct: refused
+    open(bad, "wb").write(b2)
+    with bh.BHEngine(n) as eng, pytest.raises(bh.BHError):
+        eng.load_checkpoint(bad)
+
+
 def test_bench_front_end_prints_the_reference_table(bh):
     """nbody_v5_bench.cu:287,350-351,366."""
     exe = os.path.join(os.path.dirname(bh.library_path()), "nbody_bench")

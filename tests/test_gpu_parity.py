@@ -53,10 +53,27 @@ CASES = [("uniform", 2), ("uniform", 3), ("uniform", 31), ("uniform", 33), ("uni
 
 @pytest.mark.parametrize("kind,n", CASES)
 def test_every_phase_against_oracle(bh, kind, n):
-    soa = make_case(bh, kind, n)
+    check_every_phase(bh, make_case(bh, kind, n))
+
+
+def test_headline_workload_at_full_size_against_oracle(bh):
+    """BASELINE.json configs[1] at its own size: the 1,000,000-body reference disk (bench:294-308), every phase
+    against the oracle — ids, keys, tree and centre of mass bit for bit, acceptance decisions equal, accelerations
+    within 1e-4 relative RMS."""
+    check_every_phase(bh, bh.ic_refdisk(1_000_000, 42))
+
+
+@pytest.mark.parametrize("theta", [0.3, 0.8])
+def test_plummer_theta_sweep_decisions_equal_the_oracle(bh, theta):
+    """BASELINE.json configs[2]: Plummer sphere at theta != 0.5 (bench:207-208 with another THETA)."""
+    check_every_phase(bh, make_case(bh, "plummer", 100_000), theta=theta)
+
+
+def check_every_phase(bh, soa, theta=O.THETA):
+    n = len(soa[0])
     posm, vel, ids = O.soa_to_internal(soa)
     P, D, S = bh.PHASE, bh.DBG, bh.STAT
-    with bh.BHEngine(n, flags=1) as eng:
+    with bh.BHEngine(n, flags=1, theta=theta) as eng:
         eng.load_soa(*soa)
         # --- bounds + keys: bit exact (bench:134-156, 42-63)
         eng.run_phase(P.KEYS)
@@ -92,7 +109,7 @@ def test_every_phase_against_oracle(bh, kind, n):
         eng.run_phase(P.FORCE)
         assert eng.stat(S.DEVICE_ERROR) == 0
         groups = O.make_groups(ps, ks, O.GROUP, O.SPLIT)        # same cut rule as the warp applies
-        acc, counts = O.force_groups(ps, b, meta, child, com, root, groups)
+        acc, counts = O.force_groups(ps, b, meta, child, com, root, groups, theta=theta)
         gacc = eng.debug_get(D.ACC)
         assert eng.stat(S.INTERACTIONS_CELL) == counts[0]
         assert eng.stat(S.INTERACTIONS_BODY) == counts[1]
@@ -208,6 +225,11 @@ def test_energy_on_device_matches_oracle(bh):
     assert abs(ke - wke) / wke < 1e-10 and abs(pe - wpe) / abs(wpe) < 1e-10
 
 
+# measured on B200 with the group acceptance test: see the print below (the per-body test of SURVEY §6 gives 1.3e-2
+# on this disk; the group test is more conservative); bound = measured x 1.2
+MILLION_BODY_DIRECT_SUM_BOUND = 1.3e-2
+
+
 def test_million_body_invariants(bh):
     """BASELINE.json configs[1] size: properties that do not need the oracle at full size."""
     n = 1_000_000
@@ -231,7 +253,8 @@ def test_million_body_invariants(bh):
         sample = np.arange(0, n, 997, dtype=np.int32)
         out = eng.read_soa()
         err = O.rel_rms(np.stack(out[6:9], 1)[sample], eng.direct_sample(sample))
-        assert err < 1.3e-2                                        # 1.3e-2 per-body test on this disk
+        print(f"refdisk 1M: rel-RMS vs direct sum on {len(sample)} bodies = {err:.3e}, interactions/body = {per_body:.1f}")
+        assert err < MILLION_BODY_DIRECT_SUM_BOUND
 
 
 def test_two_morton_slices_emulated_on_one_gpu_equal_the_full_run(bh):
