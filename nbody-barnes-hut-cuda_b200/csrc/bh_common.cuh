@@ -90,18 +90,26 @@ __device__ __forceinline__ int bh_shared_digits_t<20>(uint64_t a, uint64_t b) {
 struct BhSortPlan {
     int64_t n;
     int num_tiles;
-    size_t hist_bytes;      // passes * 256 counters
-    size_t lookback_bytes;  // passes * tiles * 256 status words
+    size_t hist_bytes;      // passes * RADIX counters
+    size_t lookback_bytes;  // passes * tiles * RADIX status words
     size_t ticket_bytes;    // passes tickets
     size_t total_bytes;
 };
 BhSortPlan bh_sort_plan(int64_t n);
+int bh_sort_passes(int bits);   // radix passes a `bits`-wide key takes (the result lands in q iff even)
 // Pass 0 reads (keys_src, vals_src) -> (p); then p -> q -> p ...; result in q iff the pass count
 // is even (*result_in_q).  keys_q may alias keys_src.  tmp holds histogram + look-back + tickets
 // (bh_sort_plan(n).total_bytes).  If vals_in_is_iota pass 0 generates value = index.
 int bh_sort_pairs_launch(const uint32_t* keys_src, const uint32_t* vals_src, uint32_t* keys_p, uint32_t* vals_p,
                          uint32_t* keys_q, uint32_t* vals_q, int64_t n, int begin_bit, int end_bit, void* tmp,
                          bool vals_in_is_iota, unsigned int* err_flag, int* result_in_q, cudaStream_t st);
+
+// same, and the last pass also reorders the bodies (out[i] = in[sorted value i]) — the step's Morton reorder
+int bh_sort_pairs_move_launch(const uint32_t* keys_src, const uint32_t* vals_src, uint32_t* keys_p, uint32_t* vals_p,
+                              uint32_t* keys_q, uint32_t* vals_q, int64_t n, int begin_bit, int end_bit, void* tmp,
+                              bool vals_in_is_iota, unsigned int* err_flag, int* result_in_q, const float4* posm_in,
+                              const float4* vel_in, const int32_t* ids_in, float4* posm_out, float4* vel_out,
+                              int32_t* ids_out, cudaStream_t st);
 
 int bh_keys_launch(const float4* posm, int64_t n, BhDevScalars* sc, uint32_t* keys, cudaStream_t st);
 // 60-bit keys: hi = the reference key, lo = ten more bits per axis from the fractional part of the same float
@@ -110,7 +118,8 @@ int bh_gather_u32_launch(const uint32_t* src, const uint32_t* perm, uint32_t* ds
 // keys64[i] = hi_sorted[i] << 30 | lo_unsorted[perm[i]]
 int bh_combine_keys_launch(const uint32_t* hi_sorted, const uint32_t* lo_unsorted, const uint32_t* perm, uint64_t* keys64,
                            int64_t n, cudaStream_t st);
-int bh_bounds_launch(const float4* posm, int64_t n, BhDevScalars* sc, cudaStream_t st);
+int bh_bounds_enc_launch(const float4* posm, int64_t n, BhDevScalars* sc, cudaStream_t st);   // positions -> min/max images
+int bh_bounds_finish_launch(BhDevScalars* sc, cudaStream_t st);                                 // images -> cube (consumes them)
 int bh_reorder_launch(const float4* posm_in, const float4* vel_in, const int32_t* ids_in,
                       const uint32_t* perm, float4* posm_out, float4* vel_out, int32_t* ids_out,
                       int64_t n, cudaStream_t st);
@@ -137,7 +146,8 @@ int bh_force_launch(const float4* posm, const void* keys, int levels, const int3
 int bh_force_prepare();
 int bh_integrate_launch(const float4* posm_s, const float4* vel_s, const int32_t* ids_s, const float4* acc,
                         float4* posm, float4* vel, int32_t* ids, int64_t first_body, int64_t body_count,
-                        float dt, float max_speed, cudaStream_t st);
+                        float dt, float max_speed, BhDevScalars* sc /* min/max of the new positions accumulate here */,
+                        cudaStream_t st);
 int bh_import_launch(const float* px, const float* py, const float* pz, const float* vx,
                      const float* vy, const float* vz, const float* m, int64_t n, float4* posm,
                      float4* vel, int32_t* ids, cudaStream_t st);

@@ -28,6 +28,10 @@ struct bh_ctx {
     int64_t n_max = 0, n_alloc = 0, n = 0;
     int64_t steps = 0;
     bool have_state = false, have_sorted = false;
+    // sc->bbox_enc holds the min/max of the CURRENT positions (left there by the integrator of a full step, or by
+    // bh_bounds_enc_launch); the keys phase consumes it.  False => the positions are reduced before the keys phase.
+    bool bbox_fresh = false;
+    bool external_writers = false;   // bh_state_ptrs handed the position array out: never trust bbox_fresh again
     // slice (multi-GPU Morton ranges); default = everything
     int rank = 0, world = 1;
     int64_t slice_first = 0, slice_count = 0;
@@ -35,6 +39,11 @@ struct bh_ctx {
     float4 *posm = nullptr, *vel = nullptr, *posm_s = nullptr, *vel_s = nullptr, *acc = nullptr;
     int32_t *ids = nullptr, *ids_s = nullptr;
     uint32_t *keys0 = nullptr, *keys1 = nullptr, *vals0 = nullptr, *vals1 = nullptr;
+    uint32_t* perm = nullptr;            // where the step's sort leaves the permutation (depends on key width / pass parity)
+    // 30-bit sort: pass 0 reads `keys_unsorted` and the passes ping-pong so that the sorted keys land in keys0 and the
+    // permutation in vals0 — an odd pass count starts from keys1, an even one from keys0 (dead after pass 0)
+    uint32_t* keys_unsorted = nullptr;
+    bool keys_sorted = false;            // what BH_DBG_KEYS shows: the unsorted keys after the keys phase, the sorted ones later
     // key_bits = 60 only: unsorted low words, a sort ping-pong buffer, the sorted 60-bit keys
     uint32_t *klo = nullptr, *kaux = nullptr;
     uint64_t* keys64 = nullptr;
@@ -103,54 +112,81 @@ void default_slice(bh_ctx* c) {
 }
 
 // ---- the phases ---------------------------------------------------------------------------
+// Not part of a captured graph (whether it is needed changes from step to step): reduce the positions to the
+// min/max images unless the integrator of the previous full step already left them behind.
+int pre_keys(bh_ctx* c, cudaStream_t st) {
+    if (c->fixed_bounds_set || c->bbox_fresh) return 0;
+    int e = bh_bounds_enc_launch(c->posm, c->n, c->sc, st);
+    if (e) return e;
+    c->bbox_fresh = true;
+    return 0;
+}
+
+// after the update phase: the images describe the new positions iff every body was integrated here
+void post_update(bh_ctx* c) { c->bbox_fresh = !c->external_writers && c->slice_first == 0 && c->slice_count == c->n; }
+
 int phase_keys(bh_ctx* c, cudaStream_t st) {
     int e = 0;
     if (c->fixed_bounds_set) {   // LET mode: the cube was agreed with the other ranks
         BH_CUDA_TRY(cudaMemcpyAsync((char*)c->sc + offsetof(BhDevScalars, bounds), c->fixed_bounds, sizeof(c->fixed_bounds),
                                     cudaMemcpyHostToDevice, st));
     } else {
-        e = bh_bounds_launch(c->posm, c->n, c->sc, st);
+        e = bh_bounds_finish_launch(c->sc, st);   // consumes the min/max images (pre_keys / the last integrator)
     }
     if (e) return e;
     if (c->levels == 20) return bh_keys60_launch(c->posm, c->n, c->sc, c->keys0, c->klo, st);
-    return bh_keys_launch(c->posm, c->n, c->sc, c->keys0, st);
+    return bh_keys_launch(c->posm, c->n, c->sc, c->keys_unsorted, st);
 }
 
-// key_bits = 60: LSD over the two 30-bit words with the same u32 sorter — low word first (values = iota),
-// then the high word carried along in that order (stable), then the sorted 60-bit keys are assembled.
+// key_bits = 60: LSD over the two 30-bit words with the same u32 sorter — low word first (values = iota), then the
+// high word carried along in that order (stable), then the sorted 60-bit keys are assembled.  Buffer roles depend
+// on the parity of the pass count (the result of a sort lands in its q pair iff the count is even).
 int sort_keys60(bh_ctx* c, cudaStream_t st) {
     unsigned int* err = (unsigned int*)((char*)c->sc + offsetof(BhDevScalars, err));
-    int in_q = 0;
-    int e = bh_sort_pairs_launch(c->klo, nullptr, c->keys1, c->vals1, c->kaux, c->vals0, c->n, 0, BH_KEY_BITS, c->sort_tmp, true,
-                                 err, &in_q, st);                                   // -> order by low word in vals0
+    const bool even = (bh_sort_passes(BH_KEY_BITS) & 1) == 0;
+    int in_q = 0, e = 0;
+    // 1) order by low word -> vals0
+    if (even) e = bh_sort_pairs_launch(c->klo, nullptr, c->keys1, c->vals1, c->kaux, c->vals0, c->n, 0, BH_KEY_BITS, c->sort_tmp, true, err, &in_q, st);
+    else e = bh_sort_pairs_launch(c->klo, nullptr, c->kaux, c->vals0, c->keys1, c->vals1, c->n, 0, BH_KEY_BITS, c->sort_tmp, true, err, &in_q, st);
     if (e) return e;
-    if (!in_q) return BH_E_UNSUPPORTED;
+    if ((in_q != 0) != even) return BH_E_UNSUPPORTED;
     e = bh_gather_u32_launch(c->keys0, c->vals0, c->keys1, c->n, st);               // high words in that order
     if (e) return e;
-    e = bh_sort_pairs_launch(c->keys1, c->vals0, c->kaux, c->vals1, c->keys0, c->vals0, c->n, 0, BH_KEY_BITS, c->sort_tmp, false,
-                             err, &in_q, st);                                       // -> sorted high words in keys0, final order in vals0
+    // 2) stable sort by high word, carrying that order -> sorted high words in keys0, final order in c->perm
+    if (even) e = bh_sort_pairs_launch(c->keys1, c->vals0, c->kaux, c->vals1, c->keys0, c->vals0, c->n, 0, BH_KEY_BITS, c->sort_tmp, false, err, &in_q, st);
+    else e = bh_sort_pairs_launch(c->keys1, c->vals0, c->keys0, c->vals1, c->kaux, c->vals0, c->n, 0, BH_KEY_BITS, c->sort_tmp, false, err, &in_q, st);
     if (e) return e;
-    if (!in_q) return BH_E_UNSUPPORTED;
-    return bh_combine_keys_launch(c->keys0, c->klo, c->vals0, c->keys64, c->n, st);
+    if ((in_q != 0) != even) return BH_E_UNSUPPORTED;
+    return bh_combine_keys_launch(c->keys0, c->klo, c->perm, c->keys64, c->n, st);
+}
+
+// the 30-bit sort of the unsorted keys; with_bodies: the last pass also writes posm_s / vel_s / ids_s
+int sort_keys30(bh_ctx* c, bool with_bodies, cudaStream_t st) {
+    int in_q = 0, e = 0;
+    unsigned int* err = (unsigned int*)((char*)c->sc + offsetof(BhDevScalars, err));
+    const float4* pin = with_bodies ? c->posm : nullptr;
+    if (c->keys_unsorted == c->keys0)   // even pass count: keys0 -> keys1 -> keys0 ...
+        e = bh_sort_pairs_move_launch(c->keys0, nullptr, c->keys1, c->vals1, c->keys0, c->vals0, c->n, 0, BH_KEY_BITS, c->sort_tmp,
+                                      true, err, &in_q, pin, c->vel, c->ids, c->posm_s, c->vel_s, c->ids_s, st);
+    else                                // odd: keys1 -> keys0 -> keys1 -> keys0
+        e = bh_sort_pairs_move_launch(c->keys1, nullptr, c->keys0, c->vals0, c->keys1, c->vals1, c->n, 0, BH_KEY_BITS, c->sort_tmp,
+                                      true, err, &in_q, pin, c->vel, c->ids, c->posm_s, c->vel_s, c->ids_s, st);
+    if (e) return e;
+    return ((in_q != 0) == (c->keys_unsorted == c->keys0)) ? 0 : BH_E_UNSUPPORTED;   // sorted keys in keys0, permutation in vals0
 }
 
 int sort_keys_only(bh_ctx* c, cudaStream_t st) {
     if (c->levels == 20) return sort_keys60(c, st);
-    int in_q = 0;
-    // pass 0 reads keys0 (+ implicit iota values) -> keys1/vals1 -> keys0/vals0 -> ...; 4 passes end in keys0/vals0
-    int e = bh_sort_pairs_launch(c->keys0, nullptr, c->keys1, c->vals1, c->keys0, c->vals0, c->n, 0, BH_KEY_BITS,
-                                 c->sort_tmp, true, (unsigned int*)((char*)c->sc + offsetof(BhDevScalars, err)), &in_q, st);
-    if (e) return e;
-    if (!in_q) return BH_E_UNSUPPORTED;  // 30 bits = 4 passes: always even
-    return 0;
+    return sort_keys30(c, false, st);
 }
 
 int reorder_only(bh_ctx* c, cudaStream_t st) {
-    return bh_reorder_launch(c->posm, c->vel, c->ids, c->vals0, c->posm_s, c->vel_s, c->ids_s, c->n, st);
+    return bh_reorder_launch(c->posm, c->vel, c->ids, c->perm, c->posm_s, c->vel_s, c->ids_s, c->n, st);
 }
 
 int phase_sort(bh_ctx* c, cudaStream_t st) {
-    int e = sort_keys_only(c, st);
+    if (c->levels != 20) return sort_keys30(c, true, st);   // the last radix pass moves the bodies itself
+    int e = sort_keys60(c, st);
     if (e) return e;
     return reorder_only(c, st);
 }
@@ -172,7 +208,7 @@ int phase_force(bh_ctx* c, cudaStream_t st) {
 
 int phase_update(bh_ctx* c, cudaStream_t st) {
     return bh_integrate_launch(c->posm_s, c->vel_s, c->ids_s, c->acc, c->posm, c->vel, c->ids, c->slice_first,
-                               c->slice_count, c->prm.dt, c->prm.max_speed, st);
+                               c->slice_count, c->prm.dt, c->prm.max_speed, c->sc, st);
 }
 
 typedef int (*phase_fn)(bh_ctx*, cudaStream_t);
@@ -293,6 +329,11 @@ int bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device) 
     TRYA(dev_alloc(&c->vel_s, na)); TRYA(dev_alloc(&c->acc, na)); TRYA(dev_alloc(&c->ids, na)); TRYA(dev_alloc(&c->ids_s, na));
     TRYA(dev_alloc(&c->keys0, na)); TRYA(dev_alloc(&c->keys1, na)); TRYA(dev_alloc(&c->vals0, na)); TRYA(dev_alloc(&c->vals1, na));
     TRYA(cudaMalloc(&c->sort_tmp, plan.total_bytes));
+    {
+        const bool even = (bh_sort_passes(BH_KEY_BITS) & 1) == 0;
+        c->keys_unsorted = even ? c->keys0 : c->keys1;
+        c->perm = (c->levels == 20 && !even) ? c->vals1 : c->vals0;
+    }
     if (c->levels == 20) { TRYA(dev_alloc(&c->klo, na)); TRYA(dev_alloc(&c->kaux, na)); TRYA(dev_alloc(&c->keys64, na)); }
     TRYA(dev_alloc(&c->pair_info, na)); TRYA(dev_alloc(&c->pair_scan, na)); TRYA(dev_alloc(&c->tile_sums, na / 2048 + 16));
     TRYA(dev_alloc(&c->cell_meta, na)); TRYA(dev_alloc(&c->cell_child, na * 8)); TRYA(dev_alloc(&c->cell_arrive, na));
@@ -324,7 +365,7 @@ int bh_import_soa(bh_ctx* c, const float* px, const float* py, const float* pz, 
                   const float* vz, const float* mass, int64_t n, void* stream) {
     if (!c || !px || !py || !pz || !vx || !vy || !vz || !mass || n <= 0 || n > c->n_max) return BH_E_INVAL;
     BH_CUDA_TRY(cudaSetDevice(c->device));
-    c->n = n; c->steps = 0; c->have_sorted = false;
+    c->n = n; c->steps = 0; c->have_sorted = false; c->bbox_fresh = false;
     default_slice(c);
     // scheduling history of the previous body set is meaningless now
     BH_CUDA_TRY(cudaMemsetAsync((char*)c->sc + offsetof(BhDevScalars, epoch), 0,
@@ -378,8 +419,9 @@ int bh_local_bounds(bh_ctx* c, float lohi[6]) {
     if (!c->have_state) return BH_E_STATE;
     BH_CUDA_TRY(cudaSetDevice(c->device));
     BH_CUDA_TRY(cudaDeviceSynchronize());
-    int e = bh_bounds_launch(c->posm, c->n, c->sc, 0);
+    int e = bh_bounds_enc_launch(c->posm, c->n, c->sc, 0);
     if (e) return e;
+    c->bbox_fresh = true;   // the images now describe the current positions: the next keys phase may use them
     BhDevScalars h;
     BH_CUDA_TRY(cudaMemcpy(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost));
     for (int k = 0; k < 6; ++k) {   // undo the order-preserving integer image (bh_f2ord)
@@ -394,7 +436,7 @@ int bh_import_state(bh_ctx* c, const void* posm, const void* vel, const int32_t*
     if (!c || !posm || !vel || !ids || n <= 0 || n > c->n_max) return BH_E_INVAL;
     BH_CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
-    c->n = n; c->steps = 0; c->have_sorted = false;
+    c->n = n; c->steps = 0; c->have_sorted = false; c->bbox_fresh = false;
     default_slice(c);
     BH_CUDA_TRY(cudaMemsetAsync((char*)c->sc + offsetof(BhDevScalars, epoch), 0,
                                 sizeof(BhDevScalars) - offsetof(BhDevScalars, epoch), st));
@@ -458,18 +500,16 @@ int bh_sort_coarse(bh_ctx* c, void* stream) {
         BH_CUDA_TRY(cudaMemcpyAsync((char*)c->sc + offsetof(BhDevScalars, bounds), c->fixed_bounds, sizeof(c->fixed_bounds),
                                     cudaMemcpyHostToDevice, st));
     } else {
-        e = bh_bounds_launch(c->posm, c->n, c->sc, st);
+        e = pre_keys(c, st);
+        if (!e) e = bh_bounds_finish_launch(c->sc, st);
         if (e) return e;
+        c->bbox_fresh = false;
     }
-    e = bh_keys_launch(c->posm, c->n, c->sc, c->keys0, st);
+    e = bh_keys_launch(c->posm, c->n, c->sc, c->keys_unsorted, st);
     if (e) return e;
-    int in_q = 0;
-    e = bh_sort_pairs_launch(c->keys0, nullptr, c->keys1, c->vals1, c->keys0, c->vals0, c->n, 0, BH_KEY_BITS, c->sort_tmp, true,
-                             (unsigned int*)((char*)c->sc + offsetof(BhDevScalars, err)), &in_q, st);
+    e = sort_keys30(c, true, st);   // sorted 30-bit keys in keys0, bodies in posm_s / vel_s / ids_s
     if (e) return e;
-    if (!in_q) return BH_E_UNSUPPORTED;
-    e = reorder_only(c, st);
-    if (e) return e;
+    c->keys_sorted = true;
     c->have_sorted = true;
     return 0;
 }
@@ -578,6 +618,7 @@ int bh_let_export(bh_ctx* c, const float* boxes_lohi, int npeers, int K, void* o
 int bh_set_slice(bh_ctx* c, int rank, int world) {
     if (!c || world < 1 || rank < 0 || rank >= world) return BH_E_INVAL;
     c->rank = rank; c->world = world;
+    c->bbox_fresh = false;
     if (c->have_state) {
         default_slice(c);
         BH_CUDA_TRY(cudaSetDevice(c->device));
@@ -591,7 +632,7 @@ int bh_set_slice(bh_ctx* c, int rank, int world) {
 
 int bh_state_ptrs(bh_ctx* c, void** posm, void** vel, void** ids, int64_t* n, int64_t* slice_first, int64_t* slice_count) {
     if (!c) return BH_E_INVAL;
-    if (posm) *posm = c->posm;
+    if (posm) { *posm = c->posm; c->external_writers = true; c->bbox_fresh = false; }
     if (vel) *vel = c->vel;
     if (ids) *ids = c->ids;
     if (n) *n = c->n;
@@ -613,6 +654,8 @@ int bh_step(bh_ctx* c, int nsteps, void* stream) {
         if (e) return e;
     }
     for (int s = 0; s < nsteps; ++s) {
+        if (timer) BH_CUDA_TRY(cudaEventRecord(c->ev[0], st));
+        { int e = pre_keys(c, st); if (e) return e; }   // only when the last integrator did not cover every body
         if (!direct) {
             BH_CUDA_TRY(cudaGraphLaunch(c->graph_exec, st));
         } else if (!timer) {
@@ -620,7 +663,7 @@ int bh_step(bh_ctx* c, int nsteps, void* stream) {
             if (e) return e;
         } else {
             for (int p = 0; p < BH_PHASE_TOTAL; ++p) {
-                BH_CUDA_TRY(cudaEventRecord(c->ev[p], st));
+                if (p > 0) BH_CUDA_TRY(cudaEventRecord(c->ev[p], st));
                 int e = kPhases[p](c, st);
                 if (e) return e;
             }
@@ -633,8 +676,9 @@ int bh_step(bh_ctx* c, int nsteps, void* stream) {
                 c->phase_ms[BH_PHASE_TOTAL] += ms;
             }
         }
+        post_update(c);
     }
-    if (nsteps > 0) { c->steps += nsteps; c->have_sorted = true; }
+    if (nsteps > 0) { c->steps += nsteps; c->have_sorted = true; c->keys_sorted = true; }
     return 0;
 }
 
@@ -642,6 +686,7 @@ int bh_step_half(bh_ctx* c, int half, void* stream) {
     if (!c || half < 0 || half > 1) return BH_E_INVAL;
     if (!c->have_state) return BH_E_STATE;
     BH_CUDA_TRY(cudaSetDevice(c->device));
+    if (half == 0) { int e = pre_keys(c, (cudaStream_t)stream); if (e) return e; }
     if (c->prm.flags & (BH_FLAG_NO_GRAPH | BH_FLAG_PHASE_TIMER)) {
         int e = launch_half(c, half, (cudaStream_t)stream);
         if (e) return e;
@@ -650,7 +695,8 @@ int bh_step_half(bh_ctx* c, int half, void* stream) {
         if (e) return e;
         BH_CUDA_TRY(cudaGraphLaunch(c->half_exec[half], (cudaStream_t)stream));
     }
-    if (half == 1) { c->steps += 1; c->have_sorted = true; }
+    if (half == 0) { c->bbox_fresh = false; c->keys_sorted = true; }   // images consumed by the keys phase; keys sorted
+    if (half == 1) { c->steps += 1; c->have_sorted = true; post_update(c); }
     return 0;
 }
 
@@ -658,8 +704,12 @@ int bh_run_phase(bh_ctx* c, int phase, void* stream) {
     if (!c || phase < 0 || phase >= BH_PHASE_TOTAL) return BH_E_INVAL;
     if (!c->have_state) return BH_E_STATE;
     BH_CUDA_TRY(cudaSetDevice(c->device));
+    if (phase == BH_PHASE_KEYS) { int e0 = pre_keys(c, (cudaStream_t)stream); if (e0) return e0; }
     int e = kPhases[phase](c, (cudaStream_t)stream);
     if (e) return e;
+    if (phase == BH_PHASE_KEYS) { c->bbox_fresh = false; c->keys_sorted = false; }   // images consumed; keys unsorted
+    if (phase == BH_PHASE_SORT) c->keys_sorted = true;
+    if (phase == BH_PHASE_UPDATE) post_update(c);
     if (phase >= BH_PHASE_SORT) c->have_sorted = true;
     return 0;
 }
@@ -737,11 +787,11 @@ static int dbg_locate(bh_ctx* c, int what, void** ptr, size_t* bytes) {
     const size_t n = (size_t)c->n;
     switch (what) {
         case BH_DBG_BOUNDS: *ptr = (char*)c->sc + offsetof(BhDevScalars, bounds); *bytes = 24; break;
-        case BH_DBG_KEYS: *ptr = c->keys0; *bytes = n * 4; break;
+        case BH_DBG_KEYS: *ptr = (c->levels == 20 || c->keys_sorted) ? c->keys0 : c->keys_unsorted; *bytes = n * 4; break;
         case BH_DBG_KEYS64:
             if (c->levels != 20) return BH_E_UNSUPPORTED;
             *ptr = c->keys64; *bytes = n * 8; break;
-        case BH_DBG_PERM: *ptr = c->vals0; *bytes = n * 4; break;
+        case BH_DBG_PERM: *ptr = c->perm; *bytes = n * 4; break;
         case BH_DBG_IDS: *ptr = c->ids; *bytes = n * 4; break;
         case BH_DBG_POSM: *ptr = c->posm; *bytes = n * 16; break;
         case BH_DBG_VEL: *ptr = c->vel; *bytes = n * 16; break;
@@ -780,6 +830,7 @@ int bh_debug_set(bh_ctx* c, int what, const void* src, size_t bytes) {
     if (e) return e;
     if (bytes != want) return BH_E_INVAL;
     if (bytes == 0) return 0;
+    c->bbox_fresh = false;   // the caller may have moved bodies
     return (int)cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice);
 }
 
@@ -816,7 +867,7 @@ int bh_sort_pairs_u32(const uint32_t* keys_in, const uint32_t* vals_in, uint32_t
     uint32_t* tv = (uint32_t*)(base + plan_bytes + arr);
     unsigned int* err = (unsigned int*)(base + plan_bytes + 2 * arr);
     BH_CUDA_TRY(cudaMemsetAsync(err, 0, 4, (cudaStream_t)stream));
-    const int passes = (end_bit - begin_bit + 7) / 8;
+    const int passes = bh_sort_passes(end_bit - begin_bit);
     int in_q = 0;
     // make the final pass land in (keys_out, vals_out)
     if (passes & 1)
@@ -953,7 +1004,7 @@ int bh_load_checkpoint(bh_ctx* c, const char* path) {
     // simulation parameters travel with the state; flags and tuning knobs stay the context's own
     c->prm.theta = h.theta; c->prm.G = h.G; c->prm.dt = h.dt;
     c->prm.softening = h.softening; c->prm.max_speed = h.max_speed;
-    c->n = h.n; c->steps = h.steps; c->have_state = true; c->have_sorted = false;
+    c->n = h.n; c->steps = h.steps; c->have_state = true; c->have_sorted = false; c->bbox_fresh = false;
     default_slice(c);
     BH_CUDA_TRY(cudaMemset((char*)c->sc + offsetof(BhDevScalars, epoch), 0, sizeof(BhDevScalars) - offsetof(BhDevScalars, epoch)));
     BH_CUDA_TRY(cudaMemset(c->heavy_flag, 0, 8 * (size_t)c->max_chunks));

@@ -3,26 +3,42 @@
 // Replaces thrust::sort_by_key(d_keys, d_keys + N, d_vals)  nbody_v5_bench.cu:262-264
 // (stable ascending; ties keep ascending input position).
 //
-// Structure (8-bit digits):
+// Structure (RADIX_BITS-bit digits.  8 bits = four passes over the reference's 30-bit key.  Three passes of 10
+// bits — 52 instead of 68 B/pair, SURVEY §8d — were built and measured in round 2: 0.125 vs 0.098 ms at 1M and
+// 0.91 vs 0.71 ms at 16M random keys; with 1,024 bins a 4,096-key tile leaves 4-key (16-byte) runs to write, the
+// look-back touches four times as many status words and the kernel spills at 80 registers.  The code stays
+// generic in RADIX_BITS — `make EXTRA_NVFLAGS=-DBH_RADIX_BITS=10` rebuilds that variant):
 //   1. one histogram kernel counts every pass's digits in a single read of the keys
 //      (shared-memory histograms, one global atomic per bin per CTA);
-//   2. a 256-thread kernel turns each pass's histogram into exclusive bucket bases;
+//   2. a RADIX-thread kernel turns each pass's histogram into exclusive bucket bases;
 //   3. one "onesweep" kernel per digit: a CTA takes a tile ticket, ranks its 4096 keys with
 //      warp-level match/ballot digit histograms (stable), publishes its per-digit counts,
-//      resolves the cross-tile prefix by decoupled look-back on packed status words, stages
-//      the tile digit-ordered in shared memory and writes runs out coalesced.
-// Algorithmic traffic: 4 B (histogram) + 16 B per pass per pair (SURVEY §8d).
+//      resolves the cross-tile prefix by decoupled look-back on packed status words (RADIX / 256 digits
+//      per thread, their look-back chains interleaved), stages the tile digit-ordered in shared memory and
+//      writes runs out coalesced.
+//   4. the LAST pass of the step's sort also moves the bodies: it knows every pair's final slot, so it
+//      gathers posm / vel / ids by the carried index and writes them in sorted order itself — no separate
+//      reorder launch, the permutation is not re-read from HBM.
+// Algorithmic traffic: 4 B (histogram) + 16 B per pass per pair.
 #include "bh_common.cuh"
 
 namespace {
 
-constexpr int RADIX_BITS = 8;
+#ifndef BH_RADIX_BITS
+#define BH_RADIX_BITS 8
+#endif
+constexpr int RADIX_BITS = BH_RADIX_BITS;
 constexpr int RADIX = 1 << RADIX_BITS;
 constexpr int SORT_THREADS = 256;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
-constexpr int ITEMS = 16;
+#ifndef BH_SORT_ITEMS
+#define BH_SORT_ITEMS 16
+#endif
+constexpr int ITEMS = BH_SORT_ITEMS;
 constexpr int TILE = SORT_THREADS * ITEMS;  // 4096 pairs per CTA
-constexpr int MAX_PASSES = 4;
+constexpr int MAX_PASSES = 4;                // 32 key bits = 4 x 8 (or 10 + 10 + 10 + 2)
+constexpr int DPT = RADIX / SORT_THREADS;    // digits per thread in the per-digit part of a pass
+static_assert(DPT * SORT_THREADS == RADIX && 32 * ITEMS < 65536, "digit ownership / 16-bit warp counters");
 
 constexpr uint32_t ST_MASK = 0x3FFFFFFFu;
 constexpr uint32_t ST_LOCAL = 0x40000000u;  // tile's own count is published
@@ -101,16 +117,22 @@ __global__ void __launch_bounds__(RADIX) scan_hist_kernel(uint32_t* hist, int pa
     }
 }
 
-template <bool IOTA>
+// what the last pass of the step's sort moves besides the pairs
+struct BodyMove {
+    const float4* posm_in; const float4* vel_in; const int32_t* ids_in;
+    float4* posm_out; float4* vel_out; int32_t* ids_out;
+};
+
+template <bool IOTA, bool MOVE>
 __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_t* __restrict__ keys_in,
                                                                const uint32_t* __restrict__ vals_in,
                                                                uint32_t* __restrict__ keys_out,
                                                                uint32_t* __restrict__ vals_out, int64_t n, int shift,
                                                                uint32_t mask, const uint32_t* __restrict__ bucket_base,
                                                                volatile uint32_t* lookback, unsigned int* ticket,
-                                                               unsigned int* err_flag) {
+                                                               unsigned int* err_flag, BodyMove mv) {
     __shared__ uint32_t s_buf[TILE];
-    __shared__ uint32_t s_whist[SORT_WARPS][RADIX];
+    __shared__ uint16_t s_whist[SORT_WARPS][RADIX];   // a warp holds 32 * ITEMS = 512 keys: counts fit 16 bits
     __shared__ uint32_t s_tile_excl[RADIX];
     __shared__ uint32_t s_global_off[RADIX];   // n < 2^30: 32-bit wrap-around arithmetic is exact
     __shared__ uint32_t s_scan[SORT_WARPS];
@@ -118,7 +140,7 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_
 
     const int lane = bh_lane(), warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = threadIdx.x; i < SORT_WARPS * RADIX; i += SORT_THREADS) (&s_whist[0][0])[i] = 0;
+    for (int i = threadIdx.x; i < SORT_WARPS * RADIX / 2; i += SORT_THREADS) reinterpret_cast<uint32_t*>(&s_whist[0][0])[i] = 0;
     __syncthreads();
     const unsigned tile = s_tile;
     const int64_t tile_base = (int64_t)tile * TILE;
@@ -144,14 +166,14 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_
 
     // ---- stable in-warp ranking with match-any digit groups --------------------------------
     uint32_t rank[ITEMS];
-    uint32_t* my_hist = s_whist[warp];
+    uint16_t* my_hist = s_whist[warp];
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) {
         const uint32_t d = (key[k] >> shift) & mask;
         const unsigned peers = __match_any_sync(0xffffffffu, d);
         const int leader = __ffs(peers) - 1;
         uint32_t base = 0;
-        if (lane == leader) { base = my_hist[d]; my_hist[d] = base + (uint32_t)__popc(peers); }
+        if (lane == leader) { base = my_hist[d]; my_hist[d] = (uint16_t)(base + (uint32_t)__popc(peers)); }
         base = __shfl_sync(0xffffffffu, base, leader);
         rank[k] = base + (uint32_t)__popc(peers & ((1u << lane) - 1u));
         __syncwarp();
@@ -160,19 +182,26 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_
 
     // ---- per-digit: warp offsets, tile count, publish, look-back --------------------------
     {
-        const int d = threadIdx.x;  // SORT_THREADS == RADIX
-        uint32_t running = 0;
+        const int d0 = threadIdx.x * DPT;   // this thread owns digits d0 .. d0 + DPT - 1
+        uint32_t running[DPT];
 #pragma unroll
-        for (int w = 0; w < SORT_WARPS; ++w) {
-            uint32_t c = s_whist[w][d];
-            s_whist[w][d] = running;
-            running += c;
+        for (int q = 0; q < DPT; ++q) {
+            uint32_t r = 0;
+#pragma unroll
+            for (int w = 0; w < SORT_WARPS; ++w) {
+                const uint32_t c = s_whist[w][d0 + q];
+                s_whist[w][d0 + q] = (uint16_t)r;
+                r += c;
+            }
+            running[q] = r;
+            lookback[(size_t)tile * RADIX + d0 + q] = (tile == 0 ? ST_INCL : ST_LOCAL) | r;
         }
-        volatile uint32_t* my_status = lookback + (size_t)tile * RADIX + d;
-        *my_status = (tile == 0 ? ST_INCL : ST_LOCAL) | running;
 
-        // exclusive scan of the tile's digit counts across the 256 threads
-        uint32_t inc = running;
+        // exclusive scan of the tile's digit counts across the threads (DPT consecutive digits each)
+        uint32_t mine = 0;
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) mine += running[q];
+        uint32_t inc = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
             uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
@@ -180,38 +209,57 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_
         }
         if (lane == 31) s_scan[warp] = inc;
         __syncthreads();
-        uint32_t wbase = 0;
-        for (int w = 0; w < warp; ++w) wbase += s_scan[w];
-        const uint32_t excl_in_tile = wbase + inc - running;
-        s_tile_excl[d] = excl_in_tile;
+        uint32_t excl = inc - mine;
+        for (int w = 0; w < warp; ++w) excl += s_scan[w];
+        uint32_t excl_in_tile[DPT];
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) { excl_in_tile[q] = excl; s_tile_excl[d0 + q] = excl; excl += running[q]; }
 
-        uint32_t prior = 0;
+        uint32_t prior[DPT];
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) prior[q] = 0;
         if (tile > 0) {
-            // Decoupled look-back, LB_WIDE predecessors per round trip: the statuses of tiles p, p-1, ...
-            // are fetched together (independent loads) and consumed in order.  The chain of dependent L2
-            // round trips, which bounds the first wave when hundreds of tiles start together, shrinks by
-            // the same factor.
-            constexpr int LB_WIDE = 8;
-            int p = (int)tile - 1;
+            // Decoupled look-back, LB_WIDE predecessors per round trip and the DPT digit chains of this thread
+            // interleaved: the statuses of tiles p, p-1, ... are fetched together (independent loads) and
+            // consumed in order.  The chain of dependent L2 round trips, which bounds the first wave when
+            // hundreds of tiles start together, shrinks by the same factor.
+            constexpr int LB_WIDE = DPT == 1 ? 8 : 4;
+            int p[DPT];
+            bool done[DPT];
+#pragma unroll
+            for (int q = 0; q < DPT; ++q) { p[q] = (int)tile - 1; done[q] = false; }
             unsigned spins = 0;
-            bool done = false;
-            while (!done) {
-                uint32_t st[LB_WIDE];
+            bool all_done = false;
+            while (!all_done) {
+                uint32_t st[DPT][LB_WIDE];
 #pragma unroll
-                for (int j = 0; j < LB_WIDE; ++j) st[j] = (p - j >= 0) ? lookback[(size_t)(p - j) * RADIX + d] : 0x80000000u;
+                for (int q = 0; q < DPT; ++q)
 #pragma unroll
-                for (int j = 0; j < LB_WIDE; ++j) {
-                    if (done) break;
-                    const uint32_t sv = st[j];
-                    if (sv & ST_INCL) { prior += sv & ST_MASK; done = true; }
-                    else if (sv & ST_LOCAL) { prior += sv & ST_MASK; --p; spins = 0; }
-                    else break;   // not published yet: poll again from this tile
+                    for (int j = 0; j < LB_WIDE; ++j)
+                        st[q][j] = (!done[q] && p[q] - j >= 0) ? lookback[(size_t)(p[q] - j) * RADIX + d0 + q] : 0x80000000u;
+                all_done = true;
+                bool progress = false;
+#pragma unroll
+                for (int q = 0; q < DPT; ++q) {
+                    if (done[q]) continue;
+#pragma unroll
+                    for (int j = 0; j < LB_WIDE; ++j) {
+                        if (done[q]) break;
+                        const uint32_t sv = st[q][j];
+                        if (sv & ST_INCL) { prior[q] += sv & ST_MASK; done[q] = true; progress = true; }
+                        else if (sv & ST_LOCAL) { prior[q] += sv & ST_MASK; --p[q]; progress = true; }
+                        else break;   // not published yet: poll again from this tile
+                    }
+                    all_done = all_done && done[q];
                 }
-                if (!done && ++spins > SPIN_LIMIT) { atomicOr(err_flag, BH_DERR_SORT_SPIN); break; }
+                spins = progress ? 0 : spins + 1;
+                if (!all_done && spins > SPIN_LIMIT) { atomicOr(err_flag, BH_DERR_SORT_SPIN); break; }
             }
-            *my_status = ST_INCL | (prior + running);
+#pragma unroll
+            for (int q = 0; q < DPT; ++q) lookback[(size_t)tile * RADIX + d0 + q] = ST_INCL | (prior[q] + running[q]);
         }
-        s_global_off[d] = bucket_base[d] + prior - excl_in_tile;
+#pragma unroll
+        for (int q = 0; q < DPT; ++q) s_global_off[d0 + q] = bucket_base[d0 + q] + prior[q] - excl_in_tile[q];
     }
     __syncthreads();
 
@@ -237,10 +285,36 @@ __global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_
 #pragma unroll
     for (int k = 0; k < ITEMS; ++k) s_buf[pos[k]] = val[k];
     __syncthreads();
+    if (!MOVE) {
 #pragma unroll
-    for (int k = 0; k < ITEMS; ++k) {
-        const int p = threadIdx.x + k * SORT_THREADS;
-        if (p < tile_valid) vals_out[dst[k]] = s_buf[p];
+        for (int k = 0; k < ITEMS; ++k) {
+            const int p = threadIdx.x + k * SORT_THREADS;
+            if (p < tile_valid) vals_out[dst[k]] = s_buf[p];
+        }
+    } else {
+        // the carried value is the body's slot in the unsorted state: gather it, write it at its final slot
+        // (consecutive threads write consecutive slots within a digit run)
+#pragma unroll
+        for (int k0 = 0; k0 < ITEMS; k0 += 4) {
+            uint32_t j[4];
+            float4 pp[4], vv[4];
+            int32_t id[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int p = threadIdx.x + (k0 + k) * SORT_THREADS;
+                j[k] = s_buf[p];
+                if (p < tile_valid) { pp[k] = __ldg(mv.posm_in + j[k]); vv[k] = __ldg(mv.vel_in + j[k]); id[k] = __ldg(mv.ids_in + j[k]); }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int p = threadIdx.x + (k0 + k) * SORT_THREADS;
+                if (p < tile_valid) {
+                    const uint32_t o = dst[k0 + k];
+                    vals_out[o] = j[k];
+                    mv.posm_out[o] = pp[k]; mv.vel_out[o] = vv[k]; mv.ids_out[o] = id[k];
+                }
+            }
+        }
     }
 }
 
@@ -259,6 +333,8 @@ PassDesc make_passes(int begin_bit, int end_bit) {
 
 }  // namespace
 
+int bh_sort_passes(int bits) { return (bits + RADIX_BITS - 1) / RADIX_BITS; }
+
 BhSortPlan bh_sort_plan(int64_t n) {
     BhSortPlan p{};
     p.n = n;
@@ -274,9 +350,12 @@ BhSortPlan bh_sort_plan(int64_t n) {
 // Pass 0 reads (keys_src, vals_src) and writes (keys_p, vals_p); later passes ping-pong p -> q -> p ...
 // The sorted pairs end in p when the pass count is odd and in q when it is even (*result_in_q).
 // keys_q may alias keys_src (the source is dead after pass 0).
-int bh_sort_pairs_launch(const uint32_t* keys_src, const uint32_t* vals_src, uint32_t* keys_p, uint32_t* vals_p,
-                         uint32_t* keys_q, uint32_t* vals_q, int64_t n, int begin_bit, int end_bit, void* tmp,
-                         bool vals_in_is_iota, unsigned int* err_flag, int* result_in_q, cudaStream_t st) {
+// With posm_in != nullptr the last pass also reorders the bodies: out[i] = in[sorted value i].
+int bh_sort_pairs_move_launch(const uint32_t* keys_src, const uint32_t* vals_src, uint32_t* keys_p, uint32_t* vals_p,
+                              uint32_t* keys_q, uint32_t* vals_q, int64_t n, int begin_bit, int end_bit, void* tmp,
+                              bool vals_in_is_iota, unsigned int* err_flag, int* result_in_q, const float4* posm_in,
+                              const float4* vel_in, const int32_t* ids_in, float4* posm_out, float4* vel_out,
+                              int32_t* ids_out, cudaStream_t st) {
     if (n < 0 || begin_bit < 0 || end_bit > 32 || begin_bit >= end_bit) return BH_E_INVAL;
     if (end_bit - begin_bit > MAX_PASSES * RADIX_BITS) return BH_E_INVAL;
     if (n >= (int64_t)ST_MASK) return BH_E_UNSUPPORTED;
@@ -294,18 +373,29 @@ int bh_sort_pairs_launch(const uint32_t* keys_src, const uint32_t* vals_src, uin
     histogram_kernel<<<hblocks, SORT_THREADS, 0, st>>>(keys_src, n, pd, hist);
     scan_hist_kernel<<<1, RADIX, 0, st>>>(hist, pd.passes);
     const uint32_t *kin = keys_src, *vin = vals_src;
+    const BodyMove none{nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    const BodyMove move{posm_in, vel_in, ids_in, posm_out, vel_out, ids_out};
     for (int p = 0; p < pd.passes; ++p) {
         uint32_t* kout = (p & 1) ? keys_q : keys_p;
         uint32_t* vout = (p & 1) ? vals_q : vals_p;
         volatile uint32_t* lb = lookback + (size_t)p * plan.num_tiles * RADIX;
-        if (p == 0 && vals_in_is_iota)
-            onesweep_kernel<true><<<plan.num_tiles, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, n, pd.shift[p], pd.mask[p],
-                                                                          hist + p * RADIX, lb, tickets + p, err_flag);
-        else
-            onesweep_kernel<false><<<plan.num_tiles, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, n, pd.shift[p], pd.mask[p],
-                                                                           hist + p * RADIX, lb, tickets + p, err_flag);
+        const bool iota = p == 0 && vals_in_is_iota, last = posm_in != nullptr && p == pd.passes - 1;
+#define BH_SWEEP(I, M, mvarg) onesweep_kernel<I, M><<<plan.num_tiles, SORT_THREADS, 0, st>>>(kin, vin, kout, vout, n, pd.shift[p], pd.mask[p], hist + p * RADIX, lb, tickets + p, err_flag, mvarg)
+        if (iota && last) BH_SWEEP(true, true, move);
+        else if (iota) BH_SWEEP(true, false, none);
+        else if (last) BH_SWEEP(false, true, move);
+        else BH_SWEEP(false, false, none);
+#undef BH_SWEEP
         kin = kout;
         vin = vout;
     }
     return (int)cudaGetLastError();
+}
+
+int bh_sort_pairs_launch(const uint32_t* keys_src, const uint32_t* vals_src, uint32_t* keys_p, uint32_t* vals_p,
+                         uint32_t* keys_q, uint32_t* vals_q, int64_t n, int begin_bit, int end_bit, void* tmp,
+                         bool vals_in_is_iota, unsigned int* err_flag, int* result_in_q, cudaStream_t st) {
+    return bh_sort_pairs_move_launch(keys_src, vals_src, keys_p, vals_p, keys_q, vals_q, n, begin_bit, end_bit, tmp,
+                                     vals_in_is_iota, err_flag, result_in_q, nullptr, nullptr, nullptr, nullptr, nullptr,
+                                     nullptr, st);
 }

@@ -31,14 +31,8 @@ __global__ void reset_step_scalars(BhDevScalars* sc) {
     }
 }
 
-__global__ void __launch_bounds__(kThreads) bounds_kernel(const float4* __restrict__ posm, int64_t n,
-                                                         BhDevScalars* sc) {
-    float lo[3] = {1e10f, 1e10f, 1e10f}, hi[3] = {-1e10f, -1e10f, -1e10f};
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
-        float4 p = __ldg(posm + i);
-        lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
-        hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
-    }
+// CTA-wide min/max of per-thread partial boxes -> six ordered-integer atomics on sc->bbox_enc
+__device__ __forceinline__ void block_minmax_to_enc(float lo[3], float hi[3], BhDevScalars* sc) {
 #pragma unroll
     for (int a = 0; a < 3; ++a)
 #pragma unroll
@@ -59,6 +53,17 @@ __global__ void __launch_bounds__(kThreads) bounds_kernel(const float4* __restri
     }
 }
 
+__global__ void __launch_bounds__(kThreads) bounds_kernel(const float4* __restrict__ posm, int64_t n,
+                                                         BhDevScalars* sc) {
+    float lo[3] = {1e10f, 1e10f, 1e10f}, hi[3] = {-1e10f, -1e10f, -1e10f};
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        float4 p = __ldg(posm + i);
+        lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+        hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
+    }
+    block_minmax_to_enc(lo, hi, sc);
+}
+
 // bench:148-154: size = largest extent; cube anchored at the min corner.
 __device__ __forceinline__ void cube_from_enc(const BhDevScalars* sc, float b[6]) {
     float minX = bh_ord2f(sc->bbox_enc[0]), minY = bh_ord2f(sc->bbox_enc[1]), minZ = bh_ord2f(sc->bbox_enc[2]);
@@ -68,11 +73,15 @@ __device__ __forceinline__ void cube_from_enc(const BhDevScalars* sc, float b[6]
     b[3] = __fadd_rn(minX, size); b[4] = __fadd_rn(minY, size); b[5] = __fadd_rn(minZ, size);
 }
 
+// The min/max images are CONSUMED here: the cube is formed and the images go back to the reference's +-1e10f
+// start values (bench:138), ready for the integrator of this step to accumulate the next step's box.
 __global__ void finish_bounds_kernel(BhDevScalars* sc) {
     if (threadIdx.x == 0) {
         float b[6];
         cube_from_enc(sc, b);
         for (int k = 0; k < 6; ++k) sc->bounds[k] = b[k];
+        sc->bbox_enc[0] = sc->bbox_enc[1] = sc->bbox_enc[2] = bh_f2ord(1e10f);
+        sc->bbox_enc[3] = sc->bbox_enc[4] = sc->bbox_enc[5] = bh_f2ord(-1e10f);
     }
 }
 
@@ -163,13 +172,17 @@ __global__ void __launch_bounds__(kThreads) reorder_kernel(const float4* __restr
 //   v = fma(a,DT,v); s = fma(vz,vz,fma(vx,vx,vy*vy)); if s > MAX^2: v *= MAX/sqrt(s); p = fma(v,DT,p)
 // Out of place: reads the Morton-sorted scratch copy the force phase used, writes the context's
 // current state, so a captured CUDA graph sees the same pointers every step.
+// The min/max of the NEW positions is reduced on the way out (bench:134-156 for the next step): the next
+// step forms its cube from six atomics' worth of data instead of re-reading every position.
 __global__ void __launch_bounds__(kThreads) integrate_kernel(const float4* __restrict__ posm_s,
                                                             const float4* __restrict__ vel_s,
                                                             const int32_t* __restrict__ ids_s,
                                                             const float4* __restrict__ acc, float4* __restrict__ posm,
                                                             float4* __restrict__ vel, int32_t* __restrict__ ids,
-                                                            int64_t first, int64_t count, float dt, float max_speed) {
+                                                            int64_t first, int64_t count, float dt, float max_speed,
+                                                            BhDevScalars* sc) {
     const float vmax2 = __fmul_rn(max_speed, max_speed);
+    float lo[3] = {1e10f, 1e10f, 1e10f}, hi[3] = {-1e10f, -1e10f, -1e10f};
     for (int64_t t = (int64_t)blockIdx.x * kThreads + threadIdx.x; t < count; t += (int64_t)gridDim.x * kThreads) {
         const int64_t i = first + t;
         float4 p = __ldg(posm_s + i), v = __ldg(vel_s + i);
@@ -183,7 +196,10 @@ __global__ void __launch_bounds__(kThreads) integrate_kernel(const float4* __res
         v.x = x; v.y = y; v.z = z;
         p.x = __fmaf_rn(x, dt, p.x); p.y = __fmaf_rn(y, dt, p.y); p.z = __fmaf_rn(z, dt, p.z);
         vel[i] = v; posm[i] = p; ids[i] = __ldg(ids_s + i);
+        lo[0] = fminf(lo[0], p.x); lo[1] = fminf(lo[1], p.y); lo[2] = fminf(lo[2], p.z);
+        hi[0] = fmaxf(hi[0], p.x); hi[1] = fmaxf(hi[1], p.y); hi[2] = fmaxf(hi[2], p.z);
     }
+    block_minmax_to_enc(lo, hi, sc);
 }
 
 // ---- drop the ghosts (locally-essential-tree mode) ------------------------------------------
@@ -333,9 +349,15 @@ __global__ void __launch_bounds__(kThreads) export_kernel(const float4* __restri
 
 }  // namespace
 
-int bh_bounds_launch(const float4* posm, int64_t n, BhDevScalars* sc, cudaStream_t st) {
+// min/max images of all positions -> sc->bbox_enc (what the integrator leaves behind after a full step)
+int bh_bounds_enc_launch(const float4* posm, int64_t n, BhDevScalars* sc, cudaStream_t st) {
     reset_step_scalars<<<1, 32, 0, st>>>(sc);
     bounds_kernel<<<grid_for(n, 4), kThreads, 0, st>>>(posm, n, sc);
+    return (int)cudaGetLastError();
+}
+
+// bbox_enc -> sc->bounds (bench:148-154); consumes the images
+int bh_bounds_finish_launch(BhDevScalars* sc, cudaStream_t st) {
     finish_bounds_kernel<<<1, 32, 0, st>>>(sc);
     return (int)cudaGetLastError();
 }
@@ -370,10 +392,10 @@ int bh_reorder_launch(const float4* posm_in, const float4* vel_in, const int32_t
 
 int bh_integrate_launch(const float4* posm_s, const float4* vel_s, const int32_t* ids_s, const float4* acc,
                         float4* posm, float4* vel, int32_t* ids, int64_t first_body, int64_t body_count,
-                        float dt, float max_speed, cudaStream_t st) {
+                        float dt, float max_speed, BhDevScalars* sc, cudaStream_t st) {
     if (body_count <= 0) return 0;
     integrate_kernel<<<grid_for(body_count, 2), kThreads, 0, st>>>(posm_s, vel_s, ids_s, acc, posm, vel, ids, first_body,
-                                                                  body_count, dt, max_speed);
+                                                                  body_count, dt, max_speed, sc);
     return (int)cudaGetLastError();
 }
 

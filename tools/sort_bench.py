@@ -14,6 +14,7 @@ import nbody_barnes_hut_cuda_b200 as bh  # noqa: E402
 cub = C.CDLL(os.path.join(ROOT, "oracle", "libcub_sort_baseline.so"))
 dev = torch.device("cuda:0")
 out = {}
+tag = os.environ.get('BH_LIB', 'default').split('/')[-1]
 for n in (1_000_000, 16_000_000):
     rng = np.random.default_rng(1)
     keys = torch.from_numpy(rng.integers(0, 1 << 30, n, dtype=np.uint32).view(np.int32)).to(dev)
@@ -21,7 +22,7 @@ for n in (1_000_000, 16_000_000):
     ko, vo = torch.empty_like(keys), torch.empty_like(vals)
     tmp = torch.empty(bh.sort_pairs_u32(None, None, None, None, n, 0, 30), dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    for end_bit in (30, 32):
+    for end_bit in (30,):
         for _ in range(3):
             bh.sort_pairs_u32(keys, vals, ko, vo, n, 0, end_bit, tmp)
         ts = []
@@ -48,4 +49,5 @@ for n in (1_000_000, 16_000_000):
         gb = (4 + 16 * 4) * n / 1e9
         out[f"n={n},bits={end_bit}"] = {"onesweep_ms_l2_flushed": mine, "onesweep_ms_back_to_back": mine_b2b, "cub_ms_back_to_back": ms.value,
                                         "onesweep_GBps_alg": gb / (mine * 1e-3), "cub_GBps_alg": gb / (ms.value * 1e-3)}
+out['lib'] = tag
 print(json.dumps(out, indent=1))
