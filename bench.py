@@ -20,7 +20,8 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-LAUNCHES_PER_STEP = 20   # bounds 3, keys 1, sort 6, reorder 1, tree 5, com 1, force 2, integrate 1
+LAUNCHES_PER_STEP = 17   # cube+keys 2, sort 6 (the last pass moves the bodies), tree 5, com 1, force 2, integrate 1 (it also
+                         # reduces the next step's bounding box); +2 (reset, bounds) on the first step after an import
 FLOP_PER_INTERACTION = 20  # SURVEY §8d (GPU-Gems convention; bench:205-213 op count)
 
 WORKLOADS = {
@@ -34,8 +35,40 @@ WORKLOADS = {
 }
 
 
-def make_ic(bh, w):
+def workload_config(args, w):
+    """`config` of the JSON line: the WORKLOAD only, identical for both arms (engine knobs live in `engine`)."""
+    return {"workload": args.workload, "desc": w["desc"], "n_bodies": w["n"], "theta": 0.5, "G": 0.5, "dt": 0.02,
+            "softening": 50.0, "max_speed": 500.0}
+
+
+def reference_ic(n):
+    """The reference disk from the reference's OWN generator (its main() run up to the uploads,
+    oracle/ref_wrap.cu:ref_ic) — the reference arm makes its input without touching the engine's libraries."""
+    import ctypes as C
+
+    import numpy as np
+
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_step.so")
+    if not os.path.exists(path):
+        return None
+    L = C.CDLL(path)
+    a = [np.zeros(n, np.float32) for _ in range(7)]
+    fd = os.dup(1)                      # main() prints its banner: keep it off our stdout
+    os.dup2(2, 1)
+    try:
+        rc = L.ref_ic(n, *[x.ctypes.data_as(C.c_void_p) for x in a])
+    finally:
+        os.dup2(fd, 1)
+        os.close(fd)
+    return a if rc == 0 else None
+
+
+def make_ic(bh, w, reference_generator=False):
     if w["ic"] == "refdisk":
+        if reference_generator:
+            a = reference_ic(w["n"])
+            if a is not None:
+                return a
         return bh.ic_refdisk(w["n"], 42)
     if w["ic"] == "uniform":
         return bh.ic_uniform_cube(w["n"], 42, 1000.0)
@@ -99,20 +132,22 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_baseline(w, budget_steps=None):
+def cpu_baseline(w, budget_steps=None, reference_generator=False):
     """Oracle-L (OpenMP transliteration of the reference kernels, contract baseline (a)) on the host cores."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
-    import nbody_barnes_hut_cuda_b200 as bh
+    import nbody_barnes_hut_cuda_b200 as bh   # only its host-side IC library (libbh_ic.so) is loaded here
     import oracle_lib as O
 
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    O.lib().orc_set_num_threads(cores)        # torchrun exports OMP_NUM_THREADS=1: ask for the cores we report
     n = min(w["n"], 1_000_000)
-    soa = make_ic(bh, dict(w, n=n))
+    soa = make_ic(bh, dict(w, n=n), reference_generator)
     steps = budget_steps or (10 if n <= 100_000 else 4)
     O.reference_step(soa, 1, fixed=0)  # warm the allocator / page cache
     t0 = time.perf_counter()
     r = O.reference_step(soa, steps, fixed=0)
     dt = time.perf_counter() - t0
-    return {"value": n * steps / dt, "unit": "body-steps/s", "cores": O.num_threads(), "kind": "port",
+    return {"value": n * steps / dt, "unit": "body-steps/s", "cores": O.num_threads(), "omp_num_threads_set": cores, "kind": "port",
             "sample": f"Oracle-L (literal OpenMP transliteration, 1.00 interactions/body) {steps} steps at N={n} of the {w['ic']} input",
             "phase_ms_per_step": {k: round(v / steps, 3) for k, v in zip(("keys", "sort", "insert", "com", "force", "integrate"), r["phase_ms"])}}
 
@@ -129,7 +164,7 @@ def run_reference_arm(args, w):
         return None
     import nbody_barnes_hut_cuda_b200 as bh
 
-    cpu = cpu_baseline(w)
+    cpu = cpu_baseline(w, reference_generator=True)
     path = os.path.join(ROOT, "oracle", "_ref", "libref_step.so")
     have_gpu = False
     try:
@@ -140,10 +175,12 @@ def run_reference_arm(args, w):
         pass
     line = {"impl": "reference", "metric": "body-steps/s", "unit": "body-steps/s", "n_gpus": 1, "steps": args.steps,
             "warmup": args.warmup, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic", "config": {"workload": args.workload, "desc": w["desc"], "n_bodies": w["n"], "theta": 0.5}}
+            "data": "synthetic", "config": workload_config(args, w)}
     if have_gpu and os.path.exists(path):
         L = C.CDLL(path)
-        soa = make_ic(bh, w)
+        soa = make_ic(bh, w, reference_generator=True)
+        line["input"] = ("the reference's own main() run up to its uploads (oracle/ref_wrap.cu:ref_ic)" if w["ic"] == "refdisk"
+                         else "libbh_ic.so (host-only IC generators; the reference has no such input of its own)")
         p = lambda a: a.ctypes.data_as(C.c_void_p)
         rc = L.ref_init(w["n"], *[p(np.ascontiguousarray(a, np.float32)) for a in soa])
         assert rc == 0, f"ref_init {rc}"
@@ -295,8 +332,8 @@ def run_ours(args, w):
         "metric": "body-steps/s", "value": value, "unit": "body-steps/s", "n_gpus": 1, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": w["desc"], "n_bodies": n, "theta": 0.5, "G": 0.5, "dt": 0.02,
-                   "softening": 50.0, "max_speed": 500.0, "group": 32, "key_bits": key_bits,
+        "config": workload_config(args, w),
+        "engine": {"group": 32, "key_bits": key_bits, "launches_per_step": LAUNCHES_PER_STEP,
                    "l2": "flushed between timed steps (256 MiB fill, untimed); value_l2_warm is the back-to-back loop"},
         "interactions_per_body": inter / n, "interactions_per_s": inter * args.steps / (total_ms * 1e-3),
         "value_l2_warm": n * args.steps / (warm_ms * 1e-3), "ms_per_step_l2_warm": warm_ms / args.steps,
@@ -304,6 +341,8 @@ def run_ours(args, w):
         "phase_ms": {k: round(v, 4) for k, v in phases.items()},
         "roofline": {"bound": "fp32", "kernel": "force_kernel", "achieved": force_tflops, "peak": fp32_peak,
                      "unit": "TFLOP/s", "frac": force_tflops / fp32_peak if fp32_peak else None, "traffic": traffic,
+                     "traffic_source": "STATIC: dram bytes read+write of one force_kernel launch from the committed ncu --set full "
+                                       "capture (profiles/force_traffic.json names the report); not measured in this run",
                      "peak_source": "bh_probe_fp32_tflops (FMA issue-rate probe run in this process)",
                      "flop_per_interaction": FLOP_PER_INTERACTION,
                      "hbm_frac_streaming_phases": {k: round(v, 4) for k, v in hbm_frac.items()},

@@ -14,6 +14,7 @@ from .engine import (  # noqa: F401
     PHASE,
     STAT,
     build_library,
+    ic_lib,
     ic_plummer,
     ic_refdisk,
     ic_two_disks,

@@ -14,7 +14,9 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.environ.get("BH_LIB") or os.path.join(_HERE, "libbh.so")  # BH_LIB: tuning variants only
+_IC_LIB_PATH = os.path.join(_HERE, "libbh_ic.so")   # host-only build of csrc/bh_ic.cpp (same bh_ic_* symbols as libbh.so)
 _lib: Optional[C.CDLL] = None
+_ic_lib: Optional[C.CDLL] = None
 
 
 class BHError(RuntimeError):
@@ -151,10 +153,34 @@ def lib() -> C.CDLL:
     return L
 
 
+def ic_lib() -> C.CDLL:
+    """The initial-condition generators (host C++).  A library of their own, so that callers which must not touch
+    the engine — bench.py's reference arm, the CPU baseline — can make inputs without mapping libbh.so."""
+    global _ic_lib
+    if _ic_lib is not None:
+        return _ic_lib
+    if not os.path.exists(_IC_LIB_PATH):
+        raise BHError(f"{_IC_LIB_PATH} is missing: run __graft_entry__.build()")
+    L = C.CDLL(_IC_LIB_PATH)
+    vp, i64, f32 = C.c_void_p, C.c_int64, C.c_float
+    L.bh_ic_refdisk.argtypes = [i64, C.c_uint] + [vp] * 7
+    L.bh_ic_uniform_cube.argtypes = [i64, C.c_uint64, f32] + [vp] * 7
+    L.bh_ic_two_disks.argtypes = [i64, C.c_uint64, f32, f32, f32] + [vp] * 7
+    L.bh_ic_two_disks_range.argtypes = [i64, i64, C.c_uint64, f32, f32, f32] + [vp] * 7
+    L.bh_ic_plummer.argtypes = [i64, C.c_uint64, f32, f32, f32, f32] + [vp] * 7
+    _ic_lib = L
+    return L
+
+
 def _check(code: int, what: str) -> None:
     if code != 0:
         msg = lib().bh_error_string(code).decode()
         raise BHError(f"{what} failed: {code} ({msg})")
+
+
+def _check_ic(code: int, what: str) -> None:
+    if code != 0:
+        raise BHError(f"{what} failed: {code}")   # no bh_error_string here: the IC path never loads libbh.so
 
 
 # ---- initial conditions (host) ------------------------------------------------------------
@@ -165,34 +191,34 @@ def _soa(n: int):
 def ic_refdisk(n: int, seed: int = 42):
     """main()'s disk, nbody_v5_bench.cu:294-308 (glibc rand)."""
     a = _soa(n)
-    _check(lib().bh_ic_refdisk(n, seed, *[_vp(x) for x in a]), "bh_ic_refdisk")
+    _check_ic(ic_lib().bh_ic_refdisk(n, seed, *[_vp(x) for x in a]), "bh_ic_refdisk")
     return a
 
 
 def ic_uniform_cube(n: int, seed: int = 42, half_edge: float = 1000.0):
     a = _soa(n)
-    _check(lib().bh_ic_uniform_cube(n, seed, half_edge, *[_vp(x) for x in a]), "bh_ic_uniform_cube")
+    _check_ic(ic_lib().bh_ic_uniform_cube(n, seed, half_edge, *[_vp(x) for x in a]), "bh_ic_uniform_cube")
     return a
 
 
 def ic_plummer(n: int, seed: int = 42, scale_a: float = 200.0, rcut_in_a: float = 10.0,
                body_mass: float = 4.5, G: float = 0.5):
     a = _soa(n)
-    _check(lib().bh_ic_plummer(n, seed, scale_a, rcut_in_a, body_mass, G, *[_vp(x) for x in a]), "bh_ic_plummer")
+    _check_ic(ic_lib().bh_ic_plummer(n, seed, scale_a, rcut_in_a, body_mass, G, *[_vp(x) for x in a]), "bh_ic_plummer")
     return a
 
 
 def ic_two_disks(n: int, seed: int = 42, sep: float = 4000.0, vx: float = 20.0, vy: float = 8.0):
     """BASELINE.json configs[4]: two reference-style discs on a collision course."""
     a = _soa(n)
-    _check(lib().bh_ic_two_disks(n, seed, sep, vx, vy, *[_vp(x) for x in a]), "bh_ic_two_disks")
+    _check_ic(ic_lib().bh_ic_two_disks(n, seed, sep, vx, vy, *[_vp(x) for x in a]), "bh_ic_two_disks")
     return a
 
 
 def ic_two_disks_range(first: int, n: int, seed: int = 42, sep: float = 4000.0, vx: float = 20.0, vy: float = 8.0):
     """Bodies [first, first+n) of ic_two_disks: each rank of a multi-GPU run generates only its share."""
     a = _soa(n)
-    _check(lib().bh_ic_two_disks_range(first, n, seed, sep, vx, vy, *[_vp(x) for x in a]), "bh_ic_two_disks_range")
+    _check_ic(ic_lib().bh_ic_two_disks_range(first, n, seed, sep, vx, vy, *[_vp(x) for x in a]), "bh_ic_two_disks_range")
     return a
 
 

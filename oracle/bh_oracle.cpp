@@ -63,6 +63,15 @@ inline uint32_t quantise(float p, float lo, float size) {
 
 extern "C" {
 
+// torchrun exports OMP_NUM_THREADS=1 to its workers; the CPU baseline asks for the cores it reports
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int orc_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();
