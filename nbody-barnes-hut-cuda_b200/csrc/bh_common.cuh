@@ -126,13 +126,17 @@ int bh_reorder_launch(const float4* posm_in, const float4* vel_in, const int32_t
 // kid_lv: 8 bytes per cell, digit-indexed like cell_child — level | bucket<<7 of child cells.
 int bh_tree_launch(const void* keys, int levels, int64_t n, int2* pair_info, int32_t* pair_scan,
                    int32_t* scan_block_sums, int4* cell_meta, int32_t* cell_child,
-                   int32_t* cell_arrive, uint8_t* kid_lv, BhDevScalars* sc, cudaStream_t st);
+                   uint8_t* kid_lv, BhDevScalars* sc, cudaStream_t st);
 // kid_src / kid_info: 8 entries per cell, DENSE (the r-th existing child in digit order sits at 8c + r) — the SOURCE
 // each child contributes when its parent is opened (a loose body's {x,y,z,m}, a child cell's {com,mass}) and
 // {stack word of a child cell = id << 3 | its child count - 1 | BH_KID_BUCKET, squared width as float bits}.
-int bh_com_launch(const float4* posm, int64_t n, const int4* cell_meta, const int32_t* cell_child,
-                  int32_t* cell_arrive, float4* cell_mom, float4* cell_com, float4* kid_src, uint2* kid_info,
-                  BhDevScalars* sc, cudaStream_t st);
+size_t bh_com_scratch_bytes(int64_t n);
+// the two halves of bh_com_launch: prefix sums over the sorted bodies (independent of the tree), then one thread per cell
+int bh_com_prefix_launch(const float4* posm, int64_t n, void* com_scratch, cudaStream_t st);
+int bh_com_cells_launch(const float4* posm, int64_t n, const int4* cell_meta, const int32_t* cell_child, void* com_scratch,
+                        float4* cell_com, float4* kid_src, uint2* kid_info, BhDevScalars* sc, cudaStream_t st);
+int bh_com_launch(const float4* posm, int64_t n, const int4* cell_meta, const int32_t* cell_child, void* com_scratch,
+                  float4* cell_com, float4* kid_src, uint2* kid_info, BhDevScalars* sc, cudaStream_t st);
 // heavy_list, heavy_flag: 2 * max_chunks u32 each (see BhDevScalars::epoch)
 // ids: nullptr, or per-body ids where id < 0 marks a ghost (a source whose own acceleration is not wanted)
 int bh_force_launch(const float4* posm, const void* keys, int levels, const int32_t* ids, int64_t n, int64_t first_body,

@@ -53,8 +53,9 @@ struct bh_ctx {
     int2* pair_info = nullptr;
     int32_t *pair_scan = nullptr, *tile_sums = nullptr;
     int4* cell_meta = nullptr;
-    int32_t *cell_child = nullptr, *cell_arrive = nullptr;
-    float4 *cell_mom = nullptr, *cell_com = nullptr;
+    int32_t* cell_child = nullptr;
+    float4* cell_com = nullptr;
+    void* com_scratch = nullptr;   // prefix sums of the centre-of-mass pass (bh_com_scratch_bytes)
     float4* kid_src = nullptr;   // 8 per cell
     uint8_t* kid_lv = nullptr;   // 8 per cell (digit-indexed)
     uint2* kid_info = nullptr;   // 8 per cell (dense, pairs with kid_src)
@@ -78,6 +79,8 @@ struct bh_ctx {
     cudaGraphExec_t half_exec[2] = {nullptr, nullptr};   // head / tail of the step (bh_step_half)
     int64_t graph_half_n = -1, graph_half_first = -1, graph_half_count = -1;
     cudaStream_t own_stream = nullptr;
+    cudaStream_t aux_stream = nullptr;       // second branch of the step: the centre-of-mass prefix sums run beside the tree build
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev[BH_PHASE_COUNT + 1] = {};
     float phase_ms[BH_PHASE_COUNT] = {};
 };
@@ -94,9 +97,12 @@ void free_all(bh_ctx* c) {
     for (auto& g : c->half_exec) if (g) cudaGraphExecDestroy(g);
     for (auto& e : c->ev) if (e) cudaEventDestroy(e);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     void* ptrs[] = {c->posm, c->vel, c->posm_s, c->vel_s, c->acc, c->ids, c->ids_s, c->keys0, c->keys1, c->vals0,
                     c->vals1, c->sort_tmp, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
-                    c->cell_arrive, c->cell_mom, c->cell_com, c->sc, c->stage, c->d_scratch, c->heavy_list, c->heavy_flag, c->kid_src, c->kid_lv, c->kid_info, c->let_boxes, c->let_counts, c->let_queue, c->klo, c->kaux, c->keys64};
+                    c->com_scratch, c->cell_com, c->sc, c->stage, c->d_scratch, c->heavy_list, c->heavy_flag, c->kid_src, c->kid_lv, c->kid_info, c->let_boxes, c->let_counts, c->let_queue, c->klo, c->kaux, c->keys64};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -193,11 +199,11 @@ int phase_sort(bh_ctx* c, cudaStream_t st) {
 
 int phase_build(bh_ctx* c, cudaStream_t st) {
     return bh_tree_launch(c->levels == 20 ? (const void*)c->keys64 : (const void*)c->keys0, c->levels, c->n, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
-                          c->cell_arrive, c->kid_lv, c->sc, st);
+                          c->kid_lv, c->sc, st);
 }
 
 int phase_com(bh_ctx* c, cudaStream_t st) {
-    return bh_com_launch(c->posm_s, c->n, c->cell_meta, c->cell_child, c->cell_arrive, c->cell_mom, c->cell_com, c->kid_src, c->kid_info, c->sc, st);
+    return bh_com_launch(c->posm_s, c->n, c->cell_meta, c->cell_child, c->com_scratch, c->cell_com, c->kid_src, c->kid_info, c->sc, st);
 }
 
 int phase_force(bh_ctx* c, cudaStream_t st) {
@@ -214,12 +220,28 @@ int phase_update(bh_ctx* c, cudaStream_t st) {
 typedef int (*phase_fn)(bh_ctx*, cudaStream_t);
 const phase_fn kPhases[BH_PHASE_TOTAL] = {phase_keys, phase_sort, phase_build, phase_com, phase_force, phase_update};
 
+// build -> centre of mass -> force -> update, with the centre-of-mass prefix sums (which need the sorted bodies only)
+// on a second stream beside the tree construction: fork after the sort, join before the per-cell kernel.  Captured
+// into the step graph the two branches become parallel graph nodes.
+int launch_tail_overlapped(bh_ctx* c, cudaStream_t st) {
+    BH_CUDA_TRY(cudaEventRecord(c->ev_fork, st));
+    BH_CUDA_TRY(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+    int e = bh_com_prefix_launch(c->posm_s, c->n, c->com_scratch, c->aux_stream);
+    if (!e) e = phase_build(c, st);
+    BH_CUDA_TRY(cudaEventRecord(c->ev_join, c->aux_stream));   // always join, also on error (an open fork breaks a capture)
+    BH_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));
+    if (e) return e;
+    e = bh_com_cells_launch(c->posm_s, c->n, c->cell_meta, c->cell_child, c->com_scratch, c->cell_com, c->kid_src, c->kid_info, c->sc, st);
+    if (!e) e = phase_force(c, st);
+    if (!e) e = phase_update(c, st);
+    return e;
+}
+
 int launch_all_phases(bh_ctx* c, cudaStream_t st) {
-    for (int p = 0; p < BH_PHASE_TOTAL; ++p) {
-        int e = kPhases[p](c, st);
-        if (e) return e;
-    }
-    return 0;
+    int e = phase_keys(c, st);
+    if (!e) e = phase_sort(c, st);
+    if (!e) e = launch_tail_overlapped(c, st);
+    return e;
 }
 
 // The step in two halves for multi-GPU overlap: the HEAD (bounds, keys, radix sort) reads positions only, so
@@ -231,7 +253,7 @@ int launch_half(bh_ctx* c, int half, cudaStream_t st) {
         return sort_keys_only(c, st);
     }
     int e = reorder_only(c, st);
-    for (int p = BH_PHASE_BUILD; !e && p < BH_PHASE_TOTAL; ++p) e = kPhases[p](c, st);
+    if (!e) e = launch_tail_overlapped(c, st);
     return e;
 }
 
@@ -336,13 +358,16 @@ int bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device) 
     }
     if (c->levels == 20) { TRYA(dev_alloc(&c->klo, na)); TRYA(dev_alloc(&c->kaux, na)); TRYA(dev_alloc(&c->keys64, na)); }
     TRYA(dev_alloc(&c->pair_info, na)); TRYA(dev_alloc(&c->pair_scan, na)); TRYA(dev_alloc(&c->tile_sums, na / 2048 + 16));
-    TRYA(dev_alloc(&c->cell_meta, na)); TRYA(dev_alloc(&c->cell_child, na * 8)); TRYA(dev_alloc(&c->cell_arrive, na));
-    TRYA(dev_alloc(&c->cell_mom, na)); TRYA(dev_alloc(&c->cell_com, na));
+    TRYA(dev_alloc(&c->cell_meta, na)); TRYA(dev_alloc(&c->cell_child, na * 8));
+    TRYA(dev_alloc(&c->cell_com, na)); TRYA(cudaMalloc(&c->com_scratch, bh_com_scratch_bytes(c->n_alloc)));
     TRYA(dev_alloc(&c->kid_src, na * 8)); TRYA(dev_alloc(&c->kid_lv, na * 8)); TRYA(dev_alloc(&c->kid_info, na * 8));
     TRYA(dev_alloc(&c->sc, 1)); TRYA(dev_alloc(&c->d_scratch, 8));
     c->max_chunks = (int64_t)(na / BH_GROUP + 1);
     TRYA(dev_alloc(&c->heavy_list, 2 * (size_t)c->max_chunks)); TRYA(dev_alloc(&c->heavy_flag, 2 * (size_t)c->max_chunks));
     TRYA(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    TRYA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+    TRYA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+    TRYA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     for (auto& ev : c->ev) TRYA(cudaEventCreate(&ev));
 #undef TRYA
     if (e == cudaSuccess) e = cudaMemset(c->sc, 0, sizeof(BhDevScalars));

@@ -5,7 +5,7 @@
 //   cudaMemset + initRootKernel      nbody_v5_bench.cu:266-267, 65-81
 //   insertParticlesKernel x N/1024   nbody_v5_bench.cu:83-132, 269-275
 //   cudaMemcpy(&hCount ...)          nbody_v5_bench.cu:277-278   (no host round trip here)
-//   computeCOMKernel/finalizeCOM     nbody_v5_bench.cu:158-189   (no float atomics here)
+//   computeCOMKernel/finalizeCOM     nbody_v5_bench.cu:158-189   (no atomics at all here: prefix sums)
 //
 // Canonical tree (DESIGN.md §"Tree"): a CELL is a maximal run of >= 2 sorted bodies whose keys
 // share exactly L leading 3-bit digits (L = level, 0..10).  L == 10 means identical keys: a
@@ -195,14 +195,12 @@ __global__ void __launch_bounds__(TB) scan_pairs_kernel(const int2* __restrict__
 }
 
 // ---- pass D: clear the child tables / arrival counters of the cells that exist --------------
-__global__ void __launch_bounds__(TB) init_cells_kernel(int4* __restrict__ child4, int32_t* __restrict__ arrive,
-                                                       const BhDevScalars* __restrict__ sc) {
+__global__ void __launch_bounds__(TB) init_cells_kernel(int4* __restrict__ child4, const BhDevScalars* __restrict__ sc) {
     const int M = sc->num_cells;
     const int4 empty = make_int4(BH_CHILD_EMPTY, BH_CHILD_EMPTY, BH_CHILD_EMPTY, BH_CHILD_EMPTY);
     for (int c = blockIdx.x * TB + threadIdx.x; c < M; c += gridDim.x * TB) {
         child4[2 * c] = empty;
         child4[2 * c + 1] = empty;
-        arrive[c] = 0;
     }
 }
 
@@ -254,105 +252,161 @@ __global__ void __launch_bounds__(TB) link_kernel(const typename BhKey<LEVELS>::
     }
 }
 
-// ---- centre of mass: bottom-up with per-cell arrival counters --------------------------------
-struct Moments { float m, x, y, z; };
+// ---- centre of mass: prefix sums over the sorted bodies ------------------------------------------
+// A cell is a contiguous range [first, first + count) of the Morton-sorted bodies (that is what the construction
+// above emits), so its moments are a DIFFERENCE OF PREFIX SUMS of {m, m x, m y, m z} — no walk up the tree, no
+// arrival counters, no float atomics (bench:158-189 adds 4 N floats per level with atomicAdd, which also makes the
+// reference's sums depend on the schedule).  Three flat kernels:
+//   com_scan_kernel   per block of 4,096 bodies: exclusive LOCAL prefix (restarts at 0 in every block) + block total;
+//   com_base_kernel   exclusive prefix of the block totals (one CTA);
+//   com_cells_kernel  one thread per cell: moments = (base[b2] - base[b1]) + (local[e] - local[first]), centre of
+//                     mass as bench:181-186, and the cell's entries in the dense traversal lines.
+// Sums are double: m x is exact in double (24 x 24 bits), a small cell lies inside one block, so its difference
+// involves at most 4,096 terms and is far more accurate than any float32 summation order.  Every addition happens
+// in a fixed order (16 bodies per thread in sequence, Hillis-Steele across a warp, warps / chunks in sequence), which
+// oracle/bh_oracle.cpp:orc_tree_com reproduces operation for operation: the results are equal bit for bit.
+constexpr int CPT = 16;           // consecutive bodies per thread (summed in sequence)
+constexpr int CT = 256;           // threads per scan block
+constexpr int CB = CT * CPT;      // 4,096 bodies per scan block
 
-__device__ __forceinline__ void add_body(Moments& s, const float4 p) {
-    s.m = __fadd_rn(s.m, p.w);
-    s.x = __fmaf_rn(p.w, p.x, s.x);
-    s.y = __fmaf_rn(p.w, p.y, s.y);
-    s.z = __fmaf_rn(p.w, p.z, s.z);
+struct __align__(32) D4 { double m, x, y, z; };
+
+__device__ __forceinline__ D4 d4_zero() { return D4{0.0, 0.0, 0.0, 0.0}; }
+__device__ __forceinline__ D4 d4_add(const D4 a, const D4 b) {
+    return D4{__dadd_rn(a.m, b.m), __dadd_rn(a.x, b.x), __dadd_rn(a.y, b.y), __dadd_rn(a.z, b.z)};
 }
-
-__device__ __forceinline__ float4 store_cell(float4* __restrict__ mom, float4* __restrict__ com, int c, const Moments& s) {
-    __stcg(mom + c, make_float4(s.x, s.y, s.z, s.m));
-    const float inv = (s.m > 1e-6f) ? __fdiv_rn(1.0f, s.m) : 0.0f;   // bench:181-183
-    const float4 cm = make_float4(__fmul_rn(s.x, inv), __fmul_rn(s.y, inv), __fmul_rn(s.z, inv), s.m);
-    com[c] = cm;
-    return cm;
+__device__ __forceinline__ D4 d4_sub(const D4 a, const D4 b) {
+    return D4{__dsub_rn(a.m, b.m), __dsub_rn(a.x, b.x), __dsub_rn(a.y, b.y), __dsub_rn(a.z, b.z)};
 }
-
-// Sums the children of a cell in slot (digit) order — run-to-run identical, equal to the oracle bit for bit —
-// and writes the dense traversal entries of its loose bodies (child cells write their own entry when they
-// finish, see below).  Returns the number of children.
-__device__ __forceinline__ int sum_children(const int e[8], const float4* __restrict__ posm, const float4* __restrict__ mom,
-                                            int c, float4* __restrict__ kid_src, uint2* __restrict__ kid_info, Moments& t) {
-    int r = 0;
+__device__ __forceinline__ D4 d4_term(const float4 p) {   // exact products
+    const double m = (double)p.w;
+    return D4{m, __dmul_rn(m, (double)p.x), __dmul_rn(m, (double)p.y), __dmul_rn(m, (double)p.z)};
+}
+__device__ __forceinline__ D4 d4_shfl_up(const D4 v, int o) {
+    return D4{__shfl_up_sync(0xffffffffu, v.m, o), __shfl_up_sync(0xffffffffu, v.x, o), __shfl_up_sync(0xffffffffu, v.y, o),
+              __shfl_up_sync(0xffffffffu, v.z, o)};
+}
+// inclusive Hillis-Steele scan over the lanes of a warp: at distance o, lane i adds the value lane i-o held
+// BEFORE this step (the oracle mirrors exactly this)
+__device__ __forceinline__ D4 d4_warp_inclusive(D4 v) {
+    const int lane = bh_lane();
 #pragma unroll
-    for (int q = 0; q < 8; ++q) {
-        if (e[q] == BH_CHILD_EMPTY) continue;
-        if (e[q] < 0) {
-            const float4 p = __ldg(posm + (e[q] & 0x7FFFFFFF));
-            add_body(t, p);
-            kid_src[(size_t)c * 8 + r] = p;
-            kid_info[(size_t)c * 8 + r] = make_uint2(0x7FFFFFFFu, BH_KID_BODY_W2);
-        } else {
-            const float4 cm = __ldcg(mom + e[q]);
-            t.m = __fadd_rn(t.m, cm.w); t.x = __fadd_rn(t.x, cm.x);
-            t.y = __fadd_rn(t.y, cm.y); t.z = __fadd_rn(t.z, cm.z);
-        }
-        ++r;
+    for (int o = 1; o < 32; o <<= 1) {
+        const D4 u = d4_shfl_up(v, o);
+        if (lane >= o) v = d4_add(v, u);
     }
-    return r;
+    return v;
 }
 
-__global__ void __launch_bounds__(TB) com_kernel(const float4* __restrict__ posm, const int4* __restrict__ cell_meta,
-                                                const int32_t* __restrict__ cell_child, int32_t* __restrict__ arrive,
-                                                float4* __restrict__ mom, float4* __restrict__ com,
-                                                float4* __restrict__ kid_src, uint2* __restrict__ kid_info, BhDevScalars* sc) {
+// exclusive prefix over one CTA of NW warps given each thread's value; returns the thread's exclusive prefix and,
+// through `total`, the CTA total (valid in every thread)
+template <int NW>
+__device__ __forceinline__ D4 d4_block_exclusive(const D4 v, D4* s_w /*NW*/, D4& total) {
+    const int lane = bh_lane(), warp = threadIdx.x >> 5;
+    const D4 incl = d4_warp_inclusive(v);
+    D4 prev = d4_shfl_up(incl, 1);
+    if (lane == 0) prev = d4_zero();
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    D4 before = d4_zero(), all = d4_zero();   // warps in sequence: ((W0 + W1) + W2) ...
+#pragma unroll 1
+    for (int w = 0; w < NW; ++w) {
+        if (w == warp) before = all;
+        all = d4_add(all, s_w[w]);
+    }
+    total = all;
+    __syncthreads();
+    return d4_add(before, prev);
+}
+
+__global__ void __launch_bounds__(CT) com_scan_kernel(const float4* __restrict__ posm, int n, D4* __restrict__ local,
+                                                     D4* __restrict__ totals) {
+    __shared__ D4 s_w[CT / 32];
+    const int i0 = blockIdx.x * CB + threadIdx.x * CPT;
+    D4 sum = d4_zero();   // this thread's bodies, in sequence
+#pragma unroll 4
+    for (int k = 0; k < CPT; ++k)
+        if (i0 + k < n) sum = d4_add(sum, d4_term(__ldg(posm + i0 + k)));
+    D4 total;
+    const D4 pre = d4_block_exclusive<CT / 32>(sum, s_w, total);
+    // local[i] = sum of the bodies of this block before i; entry n (one past the last body) is written too.
+    // Second read of the thread's 256 bytes (L1/L2) instead of 16 live partial sums in registers.
+    D4 run = pre;
+#pragma unroll 4
+    for (int k = 0; k < CPT; ++k) {
+        if (i0 + k <= n) local[i0 + k] = run;
+        if (i0 + k < n) run = d4_add(run, d4_term(__ldg(posm + i0 + k)));
+    }
+    if (threadIdx.x == 0) totals[blockIdx.x] = total;
+    if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1 && (blockIdx.x + 1) * CB == n) local[n] = d4_zero();   // n on a block boundary
+}
+
+__global__ void __launch_bounds__(1024) com_base_kernel(const D4* __restrict__ totals, int nblocks, D4* __restrict__ base) {
+    __shared__ D4 s_w[32];
+    __shared__ D4 s_carry;
+    if (threadIdx.x == 0) s_carry = d4_zero();
+    __syncthreads();
+    for (int c0 = 0; c0 < nblocks; c0 += 1024) {
+        const int b = c0 + threadIdx.x;
+        const D4 v = b < nblocks ? totals[b] : d4_zero();
+        D4 total;
+        const D4 pre = d4_block_exclusive<32>(v, s_w, total);
+        const D4 carry = s_carry;
+        if (b < nblocks) base[b] = d4_add(carry, pre);
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = d4_add(carry, total);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) base[nblocks] = s_carry;
+}
+
+__global__ void __launch_bounds__(TB) com_cells_kernel(const float4* __restrict__ posm, const int4* __restrict__ cell_meta,
+                                                      const int32_t* __restrict__ cell_child, const D4* __restrict__ local,
+                                                      const D4* __restrict__ base, float4* __restrict__ com,
+                                                      float4* __restrict__ kid_src, uint2* __restrict__ kid_info, BhDevScalars* sc) {
     const int M = sc->num_cells;
     const int4* child4 = reinterpret_cast<const int4*>(cell_child);
     // squared width of a level-L cell: root_w^2 with 2L taken off the exponent (exact); root_w is the key
     // grid's size, clamped like bench:52
     const float root_w = fmaxf(__fsub_rn(sc->bounds[3], sc->bounds[0]), 1.0f);
     const int root_w2_bits = __float_as_int(__fmul_rn(root_w, root_w));
-    for (int c0 = blockIdx.x * TB + threadIdx.x; c0 < M; c0 += gridDim.x * TB) {
-        int c = c0;
-        int4 mt = __ldg(cell_meta + c);
-        Moments s = {0.f, 0.f, 0.f, 0.f};
-        int nkids = 1;   // children of c (buckets are never opened as cells: the field is unused for them)
-        if ((mt.z >> 8) & 1) {
-            for (int i = mt.x; i < mt.x + mt.y; ++i) add_body(s, __ldg(posm + i));
-        } else {
+    for (int c = blockIdx.x * TB + threadIdx.x; c < M; c += gridDim.x * TB) {
+        const int4 mt = __ldg(cell_meta + c);
+        const int first = mt.x, end = mt.x + mt.y;
+        const D4 s = d4_add(d4_sub(base[end / CB], base[first / CB]), d4_sub(local[end], local[first]));
+        const float m = (float)s.m, sx = (float)s.x, sy = (float)s.y, sz = (float)s.z;
+        const float inv = (m > 1e-6f) ? __fdiv_rn(1.0f, m) : 0.0f;   // bench:181-183
+        const float4 cm = make_float4(__fmul_rn(sx, inv), __fmul_rn(sy, inv), __fmul_rn(sz, inv), m);
+        com[c] = cm;
+        const bool bucket = (mt.z >> 8) & 1;
+        int nkids = 1;   // buckets are never opened as cells: the field is unused for them
+        if (!bucket) {   // the loose bodies of this cell: their entries in its dense line
             const int4 lo = __ldg(child4 + 2 * c), hi = __ldg(child4 + 2 * c + 1);
             const int e[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-            bool has_cell = false;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) has_cell |= (e[q] >= 0 && e[q] != BH_CHILD_EMPTY);
-            if (has_cell) continue;  // finished later by its last-arriving child cell
-            nkids = sum_children(e, posm, mom, c, kid_src, kid_info, s);
-        }
-        float4 cm = store_cell(mom, com, c, s);
-        // climb while this thread is the last child cell to arrive
-        for (;;) {
-            const int p = mt.w;
-            if (p < 0) { sc->root_word = ((unsigned)c << 3) | (unsigned)(nkids - 1); break; }
-            const int4 lo = __ldg(child4 + 2 * p), hi = __ldg(child4 + 2 * p + 1);
-            const int e[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
-            const int myslot = (mt.z >> 12) & 7;
-            int ncc = 0, rank = 0;
+            int r = 0;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                ncc += (e[q] >= 0 && e[q] != BH_CHILD_EMPTY);
-                rank += (q < myslot && e[q] != BH_CHILD_EMPTY);
+                if (e[q] == BH_CHILD_EMPTY) continue;
+                if (e[q] < 0) {
+                    kid_src[(size_t)c * 8 + r] = __ldg(posm + (e[q] & 0x7FFFFFFF));
+                    kid_info[(size_t)c * 8 + r] = make_uint2(0x7FFFFFFFu, BH_KID_BODY_W2);
+                }
+                ++r;
             }
-            // the parent's view of this cell: source + the word the traversal pushes to open it later
-            kid_src[(size_t)p * 8 + rank] = cm;
-            kid_info[(size_t)p * 8 + rank] =
-                make_uint2(((unsigned)c << 3) | (unsigned)(nkids - 1) | (((mt.z >> 8) & 1) ? BH_KID_BUCKET : 0u),
-                           (unsigned)(root_w2_bits - ((mt.z & 0xFF) << 24)));
-            __threadfence();   // publish this cell's moments (st.cg) before announcing arrival
-            const int old = atomicAdd(arrive + p, 1);
-            if (old + 1 < ncc) break;
-            // last arrival: the siblings' moments were fenced before their own atomics and are read with
-            // ld.cg (L2, the coherence point) below, after the atomic's result is known — the pattern of the
-            // CUDA threadFenceReduction sample; no second fence is needed
-            Moments t = {0.f, 0.f, 0.f, 0.f};
-            nkids = sum_children(e, posm, mom, p, kid_src, kid_info, t);
-            c = p;
-            mt = __ldg(cell_meta + c);
-            cm = store_cell(mom, com, c, t);
+            nkids = r;
         }
+        const unsigned word = ((unsigned)c << 3) | (unsigned)(nkids - 1);
+        const int p = mt.w;
+        if (p < 0) { sc->root_word = word; continue; }
+        // the parent's view of this cell: source + the word the traversal pushes to open it later
+        const int4 lo = __ldg(child4 + 2 * p), hi = __ldg(child4 + 2 * p + 1);
+        const int e[8] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+        const int myslot = (mt.z >> 12) & 7;
+        int rank = 0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) rank += (q < myslot && e[q] != BH_CHILD_EMPTY);
+        kid_src[(size_t)p * 8 + rank] = cm;
+        kid_info[(size_t)p * 8 + rank] = make_uint2(word | (bucket ? BH_KID_BUCKET : 0u), (unsigned)(root_w2_bits - ((mt.z & 0xFF) << 24)));
     }
 }
 
@@ -369,7 +423,7 @@ inline int capped_grid(int64_t work_items, int per_block) {
 // (levels == 20, bh_params.key_bits = 60)
 int bh_tree_launch(const void* keys, int levels, int64_t n64, int2* pair_info, int32_t* pair_scan,
                    int32_t* scan_block_sums, int4* cell_meta, int32_t* cell_child,
-                   int32_t* cell_arrive, uint8_t* kid_lv, BhDevScalars* sc, cudaStream_t st) {
+                   uint8_t* kid_lv, BhDevScalars* sc, cudaStream_t st) {
     const int n = (int)n64;
     if (n < 2) return 0;
     const int ntiles = (n - 1 + SCAN_TILE - 1) / SCAN_TILE;
@@ -377,7 +431,7 @@ int bh_tree_launch(const void* keys, int levels, int64_t n64, int2* pair_info, i
     else pair_kernel<10><<<ntiles, TB, 0, st>>>((const uint32_t*)keys, n, pair_info, scan_block_sums);
     scan_tiles_kernel<<<1, 1024, 0, st>>>(scan_block_sums, ntiles, sc);
     scan_pairs_kernel<<<ntiles, TB, 0, st>>>(pair_info, n, scan_block_sums, pair_scan);
-    init_cells_kernel<<<capped_grid(n, TB), TB, 0, st>>>(reinterpret_cast<int4*>(cell_child), cell_arrive, sc);
+    init_cells_kernel<<<capped_grid(n, TB), TB, 0, st>>>(reinterpret_cast<int4*>(cell_child), sc);
     if (levels == 20)
         link_kernel<20><<<capped_grid(n, TB), TB, 0, st>>>((const uint64_t*)keys, n, pair_info, pair_scan, cell_meta, cell_child, kid_lv, sc);
     else
@@ -385,12 +439,40 @@ int bh_tree_launch(const void* keys, int levels, int64_t n64, int2* pair_info, i
     return (int)cudaGetLastError();
 }
 
-int bh_com_launch(const float4* posm, int64_t n, const int4* cell_meta, const int32_t* cell_child,
-                  int32_t* cell_arrive, float4* cell_mom, float4* cell_com, float4* kid_src, uint2* kid_info,
-                  BhDevScalars* sc, cudaStream_t st) {
+// com_scratch: 32-byte aligned, bh_com_scratch_bytes(n) bytes — local prefixes (n + 1), block totals, block bases
+size_t bh_com_scratch_bytes(int64_t n) {
+    const size_t nblocks = (size_t)((n + CB - 1) / CB) + 1;
+    return sizeof(D4) * ((size_t)n + 1 + 2 * nblocks + 4);
+}
+
+// The prefix sums need the sorted bodies only: they can run beside the tree construction (bh_com_prefix_launch on
+// another stream); bh_com_cells_launch needs both the tree and the sums.
+int bh_com_prefix_launch(const float4* posm, int64_t n64, void* com_scratch, cudaStream_t st) {
+    const int n = (int)n64;
     if (n < 2) return 0;
-    // one thread per possible cell, no grid-stride: a thread that climbs towards the root must not delay
-    // the leaf-level cells a strided loop would hand it next
-    com_kernel<<<(int)((n + TB - 1) / TB), TB, 0, st>>>(posm, cell_meta, cell_child, cell_arrive, cell_mom, cell_com, kid_src, kid_info, sc);
+    const int nblocks = (n + CB - 1) / CB;
+    D4* local = reinterpret_cast<D4*>(com_scratch);
+    D4* totals = local + (size_t)n + 1;
+    D4* base = totals + nblocks + 1;
+    com_scan_kernel<<<nblocks, CT, 0, st>>>(posm, n, local, totals);
+    com_base_kernel<<<1, 1024, 0, st>>>(totals, nblocks, base);
     return (int)cudaGetLastError();
+}
+
+int bh_com_cells_launch(const float4* posm, int64_t n64, const int4* cell_meta, const int32_t* cell_child, void* com_scratch,
+                        float4* cell_com, float4* kid_src, uint2* kid_info, BhDevScalars* sc, cudaStream_t st) {
+    const int n = (int)n64;
+    if (n < 2) return 0;
+    const int nblocks = (n + CB - 1) / CB;
+    const D4* local = reinterpret_cast<const D4*>(com_scratch);
+    const D4* base = local + (size_t)n + 1 + nblocks + 1;
+    com_cells_kernel<<<capped_grid(n, TB), TB, 0, st>>>(posm, cell_meta, cell_child, local, base, cell_com, kid_src, kid_info, sc);
+    return (int)cudaGetLastError();
+}
+
+int bh_com_launch(const float4* posm, int64_t n64, const int4* cell_meta, const int32_t* cell_child, void* com_scratch,
+                  float4* cell_com, float4* kid_src, uint2* kid_info, BhDevScalars* sc, cudaStream_t st) {
+    int e = bh_com_prefix_launch(posm, n64, com_scratch, st);
+    if (e) return e;
+    return bh_com_cells_launch(posm, n64, cell_meta, cell_child, com_scratch, cell_com, kid_src, kid_info, sc, st);
 }

@@ -493,58 +493,95 @@ int orc_tree_build64(const uint64_t* sorted_keys, int64_t n64, int levels, int32
     return M;
 }
 
-// Slot-ordered moment sums (engine: bh_com.cu).  posm = float4 per body in sorted order.
-// Bodies add with fmaf(m, x, acc); child cells add their moment vectors with plain adds;
-// com = moment * (1/m) as bench:183-186 (m > 1e-6f guard, bench:181).
-void orc_tree_com(const float* posm, int64_t /*n*/, const int32_t* meta, const int32_t* child,
-                  int64_t M64, int32_t root, float* mom, float* com) {
-    const int M = (int)M64;
+// Centre of mass from prefix sums (engine: bh_tree.cu "centre of mass").  A cell is a contiguous range of the
+// sorted bodies, so its moments {m, m x, m y, m z} are a difference of prefix sums, taken in double (m x is exact
+// in double).  The reference adds the same terms up the parent chain with float atomics in schedule order
+// (bench:158-176); any order is "the reference's", this one is fixed and more accurate than all of them.
+// The order of every addition mirrors the kernels: blocks of 4,096 bodies; 16 consecutive bodies per thread in
+// sequence; Hillis-Steele across the 32 lanes of a warp; warps, and chunks of 1,024 block totals, in sequence.
+// com = moment * (1/m) on the float-rounded sums as bench:181-186 (m > 1e-6f guard).
+namespace {
+struct D4 { double m, x, y, z; };
+inline D4 d4_add(const D4& a, const D4& b) { return D4{a.m + b.m, a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline D4 d4_sub(const D4& a, const D4& b) { return D4{a.m - b.m, a.x - b.x, a.y - b.y, a.z - b.z}; }
+const D4 kZero{0.0, 0.0, 0.0, 0.0};
+
+// vals: nw * 32 thread values -> exclusive prefix of every thread and the total (d4_block_exclusive in bh_tree.cu)
+void block_exclusive(const D4* vals, int nw, D4* excl, D4& total) {
+    std::vector<D4> incl(vals, vals + (size_t)nw * 32), tmp(32);
+    for (int w = 0; w < nw; ++w) {
+        D4* v = incl.data() + 32 * w;
+        for (int o = 1; o < 32; o <<= 1) {
+            std::copy(v, v + 32, tmp.begin());
+            for (int i = o; i < 32; ++i) v[i] = d4_add(tmp[i], tmp[i - o]);
+        }
+    }
+    D4 all = kZero;
+    for (int w = 0; w < nw; ++w) {
+        const D4 before = all;
+        for (int l = 0; l < 32; ++l) excl[32 * w + l] = d4_add(before, l == 0 ? kZero : incl[32 * w + l - 1]);
+        all = d4_add(all, incl[32 * w + 31]);
+    }
+    total = all;
+}
+}  // namespace
+
+extern "C" void orc_tree_com(const float* posm, int64_t n64, const int32_t* meta, const int32_t* child,
+                             int64_t M64, int32_t root, float* mom, float* com) {
+    (void)child;
+    const int M = (int)M64, n = (int)n64;
     if (M == 0 || root < 0) return;
-    std::vector<char> done(M, 0);
-    std::vector<int> stack;
-    stack.push_back(root);
-    while (!stack.empty()) {
-        int c = stack.back();
-        const int32_t* mt = meta + 4 * c;
-        const int32_t* ch = child + 8 * c;
-        bool bucket = (mt[2] >> 8) & 1;
-        if (!bucket) {
-            bool pending = false;
-            for (int q = 0; q < 8; ++q) {
-                int e = ch[q];
-                if (e != CHILD_EMPTY && e >= 0 && !done[e]) { stack.push_back(e); pending = true; }
-            }
-            if (pending) continue;
+    constexpr int CT = 256, CPT = 16, CB = CT * CPT;   // 4,096 bodies per block, 16 consecutive bodies per thread
+    const int nblocks = (n + CB - 1) / CB;
+    std::vector<D4> local((size_t)n + 1, kZero), totals((size_t)nblocks, kZero), base((size_t)nblocks + 1, kZero);
+    auto term = [&](int i) {
+        const float* q = posm + 4 * (int64_t)i;
+        const double m = (double)q[3];
+        return D4{m, m * (double)q[0], m * (double)q[1], m * (double)q[2]};
+    };
+#pragma omp parallel for schedule(static)
+    for (int b = 0; b < nblocks; ++b) {
+        D4 v[CT], pre[CT];
+        for (int t = 0; t < CT; ++t) {
+            const int i0 = b * CB + CPT * t;
+            D4 sum = kZero;
+            for (int k = 0; k < CPT; ++k)
+                if (i0 + k < n) sum = d4_add(sum, term(i0 + k));
+            v[t] = sum;
         }
-        stack.pop_back();
-        if (done[c]) continue;
-        float m = 0.f, sx = 0.f, sy = 0.f, sz = 0.f;
-        if (bucket) {
-            for (int i = mt[0]; i < mt[0] + mt[1]; ++i) {
-                const float* p = posm + 4 * (int64_t)i;
-                m = m + p[3];
-                sx = fmaf(p[3], p[0], sx); sy = fmaf(p[3], p[1], sy); sz = fmaf(p[3], p[2], sz);
-            }
-        } else {
-            for (int q = 0; q < 8; ++q) {
-                int e = ch[q];
-                if (e == CHILD_EMPTY) continue;
-                if (e < 0) {
-                    const float* p = posm + 4 * (int64_t)(e & 0x7FFFFFFF);
-                    m = m + p[3];
-                    sx = fmaf(p[3], p[0], sx); sy = fmaf(p[3], p[1], sy); sz = fmaf(p[3], p[2], sz);
-                } else {
-                    const float* s = mom + 4 * (int64_t)e;
-                    m = m + s[3]; sx = sx + s[0]; sy = sy + s[1]; sz = sz + s[2];
-                }
+        D4 total;
+        block_exclusive(v, CT / 32, pre, total);
+        for (int t = 0; t < CT; ++t) {
+            const int i0 = b * CB + CPT * t;
+            D4 run = pre[t];
+            for (int k = 0; k < CPT; ++k) {
+                if (i0 + k <= n) local[i0 + k] = run;
+                if (i0 + k < n) run = d4_add(run, term(i0 + k));
             }
         }
+        totals[b] = total;
+    }
+    if (nblocks * CB == n) local[n] = kZero;
+    D4 carry = kZero;
+    for (int c0 = 0; c0 < nblocks; c0 += 1024) {
+        D4 v[1024], pre[1024], total;
+        for (int t = 0; t < 1024; ++t) v[t] = c0 + t < nblocks ? totals[c0 + t] : kZero;
+        block_exclusive(v, 32, pre, total);
+        for (int t = 0; t < 1024 && c0 + t < nblocks; ++t) base[c0 + t] = d4_add(carry, pre[t]);
+        carry = d4_add(carry, total);
+    }
+    base[nblocks] = carry;
+#pragma omp parallel for schedule(static)
+    for (int c = 0; c < M; ++c) {
+        const int32_t* mt = meta + 4 * (int64_t)c;
+        const int first = mt[0], end = mt[0] + mt[1];
+        const D4 s = d4_add(d4_sub(base[end / CB], base[first / CB]), d4_sub(local[end], local[first]));
+        const float m = (float)s.m, sx = (float)s.x, sy = (float)s.y, sz = (float)s.z;
         float* o = mom + 4 * (int64_t)c;
         o[0] = sx; o[1] = sy; o[2] = sz; o[3] = m;
-        float inv = (m > 1e-6f) ? 1.0f / m : 0.0f;
+        const float inv = (m > 1e-6f) ? 1.0f / m : 0.0f;
         float* cc = com + 4 * (int64_t)c;
         cc[0] = sx * inv; cc[1] = sy * inv; cc[2] = sz * inv; cc[3] = m;
-        done[c] = 1;
     }
 }
 
