@@ -196,6 +196,25 @@ int  bh_step_half(bh_ctx* ctx, int half, void* stream);
 int  bh_state_ptrs(bh_ctx* ctx, void** posm, void** vel, void** ids,
                    int64_t* n, int64_t* slice_first, int64_t* slice_count);
 
+/* The host driver of this mode (csrc/bh_mg.cu): one PROCESS per GPU, every process creates its context with
+ * bh_create, loads the FULL state (bh_import_soa*), then
+ *   rank 0:  bh_mg_unique_id(id)  ->  the 128 bytes reach the other processes by whatever the host has
+ *            (a file, MPI, torch.distributed — plumbing)
+ *   all:     bh_mg_create(&mg, ctx, id, rank, world, device)     NCCL communicator + bh_set_slice
+ *            bh_mg_step(mg, nsteps, stream)                        ≙ the frame loop nbody_v5_bench.cu:353-367
+ *            bh_mg_finish(mg, stream)                              `stream` waits for the gathers still in flight
+ * bh_mg_step never blocks the host: the in-place NCCL all-gathers of the updated slices run on an internal
+ * stream and the next step's keys + radix sort (positions only) start while velocities and ids are still
+ * crossing NVLink.  Results are bit-identical to bh_step on one GPU.  NCCL is dlopen'ed on first use.     */
+#define BH_MG_ID_BYTES 128
+typedef struct bh_mg bh_mg;
+int  bh_mg_unique_id(void* id128);
+int  bh_mg_create(bh_mg** out, bh_ctx* ctx, const void* id128, int rank, int world, int device);
+int  bh_mg_step(bh_mg* mg, int nsteps, void* stream);
+int  bh_mg_finish(bh_mg* mg, void* stream);
+int  bh_mg_info(bh_mg* mg, int* rank, int* world, int64_t* slice_first, int64_t* slice_count, int64_t* padded_per_rank);
+void bh_mg_destroy(bh_mg* mg);
+
 /* ---- multi-GPU: locally-essential-tree exchange (north_star) -----
  * For body counts that are not replicated on every GPU.  A rank owns the bodies of one Morton-key range;
  *   every few steps it

@@ -10,6 +10,8 @@ from .engine import (  # noqa: F401
     BHEngine,
     BHError,
     BHParams,
+    MultiGpu,
+    mg_unique_id,
     DBG,
     PHASE,
     STAT,

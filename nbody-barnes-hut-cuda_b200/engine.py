@@ -146,6 +146,13 @@ def lib() -> C.CDLL:
     L.bh_ic_two_disks_range.argtypes = [i64, i64, C.c_uint64, f32, f32, f32] + [vp] * 7
     L.bh_set_flags.argtypes = [vp, i32]
     L.bh_ic_plummer.argtypes = [i64, C.c_uint64, f32, f32, f32, f32] + [vp] * 7
+    L.bh_mg_unique_id.argtypes = [vp]
+    L.bh_mg_create.argtypes = [C.POINTER(vp), vp, vp, i32, i32, i32]
+    L.bh_mg_step.argtypes = [vp, i32, vp]
+    L.bh_mg_finish.argtypes = [vp, vp]
+    L.bh_mg_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i64), C.POINTER(i64), C.POINTER(i64)]
+    L.bh_mg_destroy.argtypes = [vp]
+    L.bh_mg_destroy.restype = None
     L.bh_probe_fp32_tflops.argtypes = [i32, C.POINTER(f32)]
     L.bh_probe_hbm_gbs.argtypes = [i32, C.POINTER(f32)]
     L.bh_probe_fp32x2_tflops.argtypes = [i32, C.POINTER(f32)]
@@ -220,6 +227,44 @@ def ic_two_disks_range(first: int, n: int, seed: int = 42, sep: float = 4000.0, 
     a = _soa(n)
     _check_ic(ic_lib().bh_ic_two_disks_range(first, n, seed, sep, vx, vy, *[_vp(x) for x in a]), "bh_ic_two_disks_range")
     return a
+
+
+MG_ID_BYTES = 128
+
+
+def mg_unique_id() -> bytes:
+    """Rank 0: the 128-byte NCCL id the other ranks need for MultiGpu (send it with whatever the host has)."""
+    buf = C.create_string_buffer(MG_ID_BYTES)
+    _check(lib().bh_mg_unique_id(buf), "bh_mg_unique_id")
+    return buf.raw
+
+
+class MultiGpu:
+    """bh_mg_* — the C++/NCCL driver of the Morton-slice mode (csrc/bh_mg.cu).  One per process/GPU; the engine must
+    hold the FULL state.  step() is asynchronous; finish() makes `stream` wait for the gathers in flight."""
+
+    def __init__(self, engine: "BHEngine", unique_id: bytes, rank: int, world: int, device: int):
+        assert len(unique_id) == MG_ID_BYTES
+        self._mg = C.c_void_p()
+        self._id = C.create_string_buffer(unique_id, MG_ID_BYTES)
+        _check(lib().bh_mg_create(C.byref(self._mg), engine._ctx, self._id, rank, world, device), "bh_mg_create")
+
+    def step(self, nsteps: int = 1, stream: int = 0):
+        _check(lib().bh_mg_step(self._mg, nsteps, C.c_void_p(stream)), "bh_mg_step")
+
+    def finish(self, stream: int = 0):
+        _check(lib().bh_mg_finish(self._mg, C.c_void_p(stream)), "bh_mg_finish")
+
+    def info(self) -> dict:
+        r, w = C.c_int(), C.c_int()
+        first, count, per = C.c_int64(), C.c_int64(), C.c_int64()
+        _check(lib().bh_mg_info(self._mg, C.byref(r), C.byref(w), C.byref(first), C.byref(count), C.byref(per)), "bh_mg_info")
+        return {"rank": r.value, "world": w.value, "first": first.value, "count": count.value, "per": per.value}
+
+    def close(self):
+        if self._mg:
+            lib().bh_mg_destroy(self._mg)
+            self._mg = C.c_void_p()
 
 
 def probe_fp32_tflops(device: int = 0) -> float:

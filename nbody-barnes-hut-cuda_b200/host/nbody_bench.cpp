@@ -7,8 +7,14 @@
 // reference's edit-and-recompile knobs (N is a global at bench:31, 1000 frames at bench:353).
 //
 //   nbody_bench [--n N] [--frames F] [--ic refdisk|uniform|plummer|twodisk] [--theta T] [--key-bits 30|60]
-//               [--quiet] [--phases] [--dump out.txt] [--save ckpt.bin] [--resume ckpt.bin]
+//               [--quiet] [--phases] [--dump out.txt] [--save ckpt.bin] [--resume ckpt.bin] [--gpus G]
+//
+// --gpus G (Morton-slice mode, include/bh.h bh_mg_*): one PROCESS per GPU.  The process started by the user is
+// rank 0; it re-executes itself G-1 times (--mg-rank r --mg-id FILE), writes the 128-byte NCCL id to FILE and
+// every rank then runs the same frame loop on bh_mg_step; rank 0 prints the table.  No MPI, no Python.
 #include <cuda_runtime.h>
+#include <sys/wait.h>
+#include <unistd.h>
 
 #include <cstdio>
 #include <cstdlib>
@@ -26,9 +32,9 @@ static void die(const char* what, int code) {
 
 int main(int argc, char** argv) {
     long long n = 1000000;   // README.md:23 (the code's global says 500000, bench:31)
-    int frames = 100, quiet = 0, phases = 0, key_bits = 30;
+    int frames = 100, quiet = 0, phases = 0, key_bits = 30, gpus = 1, mg_rank = 0;
     float theta = 0.5f;
-    std::string ic = "refdisk", dump, save, resume;
+    std::string ic = "refdisk", dump, save, resume, mg_id_file;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         auto next = [&]() -> const char* { if (i + 1 >= argc) { fprintf(stderr, "missing value for %s\n", a.c_str()); exit(2); } return argv[++i]; };
@@ -42,9 +48,54 @@ int main(int argc, char** argv) {
         else if (a == "--dump") dump = next();
         else if (a == "--save") save = next();
         else if (a == "--resume") resume = next();
+        else if (a == "--gpus") gpus = atoi(next());
+        else if (a == "--mg-rank") mg_rank = atoi(next());      // internal: a worker started by rank 0
+        else if (a == "--mg-id") mg_id_file = next();           // internal
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
-    printf("Pokretanje Benchmarka za N = %lld...\n", n);   // bench:287
+    if (gpus < 1 || gpus > 64 || mg_rank < 0 || mg_rank >= gpus) { fprintf(stderr, "bad --gpus / --mg-rank\n"); return 2; }
+    // ---- multi-GPU: rank 0 starts the other ranks as processes of their own BEFORE touching CUDA
+    std::vector<pid_t> workers;
+    unsigned char mg_id[BH_MG_ID_BYTES];
+    if (gpus > 1 && mg_rank == 0) {
+        char tmpl[] = "/tmp/nbody_bench_mgid_XXXXXX";
+        const int fd = mkstemp(tmpl);
+        if (fd < 0) { perror("mkstemp"); return 1; }
+        close(fd);
+        mg_id_file = tmpl;
+        for (int r = 1; r < gpus; ++r) {
+            const pid_t pid = fork();
+            if (pid < 0) { perror("fork"); return 1; }
+            if (pid == 0) {
+                std::vector<std::string> args(argv, argv + argc);
+                args.push_back("--mg-rank"); args.push_back(std::to_string(r));
+                args.push_back("--mg-id"); args.push_back(mg_id_file);
+                args.push_back("--quiet");
+                std::vector<char*> cargs;
+                for (auto& x : args) cargs.push_back(const_cast<char*>(x.c_str()));
+                cargs.push_back(nullptr);
+                execv("/proc/self/exe", cargs.data());
+                perror("execv");
+                _exit(127);
+            }
+            workers.push_back(pid);
+        }
+        CHECK(bh_mg_unique_id(mg_id));
+        FILE* f = fopen((mg_id_file + ".tmp").c_str(), "wb");
+        if (!f || fwrite(mg_id, 1, BH_MG_ID_BYTES, f) != BH_MG_ID_BYTES || fclose(f) != 0) { fprintf(stderr, "cannot write the NCCL id\n"); return 1; }
+        rename((mg_id_file + ".tmp").c_str(), mg_id_file.c_str());   // atomic: a reader sees all 128 bytes or nothing
+    } else if (gpus > 1) {
+        for (int tries = 0;; ++tries) {   // wait for rank 0's id
+            FILE* f = fopen(mg_id_file.c_str(), "rb");
+            size_t got = f ? fread(mg_id, 1, BH_MG_ID_BYTES, f) : 0;
+            if (f) fclose(f);
+            if (got == BH_MG_ID_BYTES) break;
+            if (tries > 6000) { fprintf(stderr, "rank %d: no NCCL id from rank 0\n", mg_rank); return 1; }
+            usleep(10000);
+        }
+    }
+    const bool lead = mg_rank == 0;
+    if (lead) printf("Pokretanje Benchmarka za N = %lld...\n", n);   // bench:287
 
     bh_params p;
     bh_default_params(&p);
@@ -52,7 +103,9 @@ int main(int argc, char** argv) {
     p.key_bits = key_bits;   // 60: the reference key + 10 more bits per axis (deep trees for > 10^7 bodies)
     if (phases) p.flags |= BH_FLAG_PHASE_TIMER;
     bh_ctx* ctx = nullptr;
-    CHECK(bh_create(&ctx, n, &p, 0));
+    const int device = gpus > 1 ? mg_rank : 0;
+    CHECK(bh_create(&ctx, n, &p, device));
+    cudaSetDevice(device);
 
     cudaEvent_t start, stop;
     cudaEventCreate(&start);
@@ -75,12 +128,17 @@ int main(int argc, char** argv) {
         cudaEventElapsedTime(&h2d_ms, start, stop);
     }
 
-    printf("------------------------------------------\n");                       // bench:350
-    printf("\n%-10s | %-15s | %-10s\n", "Frame", "Trajanje (ms)", "FPS");         // bench:351
+    bh_mg* mg = nullptr;
+    if (gpus > 1) CHECK(bh_mg_create(&mg, ctx, mg_id, mg_rank, gpus, device));     // NCCL communicator + this rank's Morton slice
+    if (lead) {
+        printf("------------------------------------------\n");                   // bench:350
+        printf("\n%-10s | %-15s | %-10s\n", "Frame", "Trajanje (ms)", "FPS");     // bench:351
+    }
     double total_ms = 0.0, phase_sum[BH_PHASE_COUNT] = {0};
     for (int frame = 0; frame < frames; ++frame) {                                // bench:353-367
         cudaEventRecord(start);
-        CHECK(bh_step(ctx, 1, nullptr));                                          // simulationStep()
+        if (mg) { CHECK(bh_mg_step(mg, 1, nullptr)); CHECK(bh_mg_finish(mg, nullptr)); }   // sliced simulationStep() + gathers
+        else CHECK(bh_step(ctx, 1, nullptr));                                     // simulationStep()
         cudaEventRecord(stop);
         cudaEventSynchronize(stop);
         float ms = 0.f;
@@ -95,10 +153,17 @@ int main(int argc, char** argv) {
     }
     long long err = bh_stat(ctx, BH_STAT_DEVICE_ERROR);
     if (err) { fprintf(stderr, "device error flag %lld\n", err); return 1; }
+    if (!lead) {   // workers: done (the state is replicated; rank 0 reports and writes the files)
+        bh_mg_destroy(mg);
+        bh_destroy(ctx);
+        return 0;
+    }
 
     // README.md:56-60 — the per-section metrics
-    const double inter = (double)bh_stat(ctx, BH_STAT_INTERACTIONS_CELL) + (double)bh_stat(ctx, BH_STAT_INTERACTIONS_BODY);
+    const double inter = ((double)bh_stat(ctx, BH_STAT_INTERACTIONS_CELL) + (double)bh_stat(ctx, BH_STAT_INTERACTIONS_BODY)) *
+                         (mg ? (double)gpus : 1.0);   // a rank counts its own slice; slices hold equal body counts
     printf("------------------------------------------\n");
+    if (mg) printf("%d GPUs, one process each: replicated sort + tree, Morton-slice traversal, in-place NCCL all-gather\n", gpus);
     printf("frames %d  mean %.3f ms  %.1f FPS  %.1f M body-steps/s  %.1f G interactions/s (%.1f per body)\n", frames,
            total_ms / frames, 1000.0 * frames / total_ms, n * 1e-3 * frames / total_ms, inter * 1e-6 * frames / total_ms, inter / n);
     if (phases) {
@@ -114,6 +179,13 @@ int main(int argc, char** argv) {
     printf("  transfers: host->device %.3f ms (28 B/body), device->host %.3f ms (24 B/body)\n", h2d_ms, d2h_ms);
     if (!dump.empty()) CHECK(bh_dump_text(ctx, dump.c_str()));
     if (!save.empty()) CHECK(bh_save_checkpoint(ctx, save.c_str()));
+    bh_mg_destroy(mg);
     bh_destroy(ctx);
-    return 0;
+    int rc = 0;
+    for (pid_t pid : workers) {
+        int status = 0;
+        if (waitpid(pid, &status, 0) < 0 || !WIFEXITED(status) || WEXITSTATUS(status) != 0) rc = 1;
+    }
+    if (!mg_id_file.empty() && lead) unlink(mg_id_file.c_str());
+    return rc;
 }

@@ -9,7 +9,11 @@ One process per GPU (torchrun).  Every rank holds the full state; each step ever
 Slices are whole 32-body chunks, so chunk boundaries — and therefore every acceptance decision and
 every float — are identical to the single-GPU run.
 
-torch / torch.distributed are plumbing only (device views of the context's buffers + the collective).
+The step loop itself — slice bookkeeping, the in-place NCCL all-gathers on their own stream, the overlap of the
+next step's keys + sort with the gathers of velocities and ids — is C++ behind the C ABI (bh_mg_*, csrc/bh_mg.cu).
+This module is the test / bench harness around it: torch.distributed only carries the 128-byte NCCL id to the
+other ranks and reduces the timings; `step(overlap=False)` keeps a torch all-gather loop as an independent
+cross-check of the C++ driver.
 """
 from __future__ import annotations
 
@@ -72,6 +76,14 @@ class SlicedSimulation:
         st = self.eng.state_ptrs()
         assert (st["first"], st["count"]) == (self.first, self.count), "slice arithmetic differs from the C side"
         self.views = device_views(torch, st, self.per, world, self.device)
+        # the C++/NCCL driver: rank 0 makes the id, torch.distributed only carries it to the others
+        idt = torch.zeros(128, dtype=torch.uint8, device=self.device)   # BH_MG_ID_BYTES
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(bh.mg_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        self.mg = bh.MultiGpu(self.eng, bytes(idt.cpu().numpy().tobytes()), rank, world, local)
+        info = self.mg.info()
+        assert (info["first"], info["count"], info["per"]) == (self.first, self.count, self.per)
 
     def step(self, nsteps: int = 1, overlap: bool = True):
         """nsteps sliced steps.  With overlap the three all-gathers are issued asynchronously in the order
@@ -83,25 +95,11 @@ class SlicedSimulation:
                 self.eng.simulation_step(1, stream)
                 allgather_slices(self.dist, self.views, self.rank, self.per)
             return
-        lo, hi = self.rank * self.per, (self.rank + 1) * self.per
-        for _ in range(nsteps):
-            pending = getattr(self, "_pending", None)
-            if pending:
-                pending[0].wait()               # positions of the previous step are complete
-            self.eng.step_half(0, stream)
-            if pending:
-                pending[1].wait()
-                pending[2].wait()
-            self.eng.step_half(1, stream)
-            self._pending = [self.dist.all_gather_into_tensor(full, full[lo:hi], async_op=True) for full in self.views]
+        self.mg.step(nsteps, stream)   # bh_mg_step: asynchronous, the gathers of the last step stay in flight
 
     def finish(self):
-        """Complete the all-gathers a previous step(overlap=True) left in flight."""
-        pending = getattr(self, "_pending", None)
-        if pending:
-            for h in pending:
-                h.wait()
-            self._pending = None
+        """The current stream waits for the all-gathers a previous step(overlap=True) left in flight."""
+        self.mg.finish(self.torch.cuda.current_stream().cuda_stream)
 
     def step_host(self, host_in, host_out, nsteps: int = 1):
         """End-to-end step with HOST state, sharded over the ranks' PCIe links: every rank uploads 1/world of
@@ -134,6 +132,7 @@ class SlicedSimulation:
     def close(self):
         self.finish()
         self.torch.cuda.synchronize()
+        self.mg.close()
         self.eng.close()
 
 
@@ -217,21 +216,42 @@ def run_sliced_bench(args, w, bh, dist, rank, world, local):
     cells = sim.eng.stat(bh.STAT.CELLS)
     sim.close()
     total_ms = float(ms.item())
+    # the SAME workload on ONE GPU (rank 0, 10 graph-replayed steps): the strong-scaling curve reads off this line alone
+    same1 = None
+    if rank == 0:
+        with bh.BHEngine(n, device=local) as one:
+            one.load_soa(*soa)
+            stream1 = torch.cuda.current_stream().cuda_stream
+            one.simulation_step(3, stream1)
+            torch.cuda.synchronize()
+            a1, b1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a1.record()
+            one.simulation_step(10, stream1)
+            b1.record()
+            torch.cuda.synchronize()
+            one.check_device_error()
+            ms1 = a1.elapsed_time(b1) / 10
+            same1 = {"workload": args.workload, "n_bodies": n, "ms_per_step": ms1, "value": n / (ms1 * 1e-3), "unit": "body-steps/s",
+                     "steps": 10, "warmup": 3, "note": "bh_step on rank 0's GPU alone, same input, measured in this run"}
+    dist.barrier()
     roofline = bench.force_roofline(bh, local, float(inter.item()) / world, max(force_per_rank))
     line = {
         "metric": "body-steps/s", "value": n * args.steps / (total_ms * 1e-3), "unit": "body-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": w["desc"], "n_bodies": n, "theta": 0.5, "G": 0.5, "dt": 0.02,
-                   "softening": 50.0, "max_speed": 500.0, "group": 32,
+        "config": bench.workload_config(args, w),
+        "engine": {"group": 32, "key_bits": 30, "launches_per_step": bench.LAUNCHES_PER_STEP + 2,
                    "parallelism": f"morton-slices x{world}: replicated sort+tree, sliced traversal, in-place NCCL all-gather of 36 B/body",
+                   "driver": "bh_mg_step (C++/NCCL behind the C ABI, csrc/bh_mg.cu); torch.distributed carries the NCCL id and reduces the timings",
                    "l2": "state far larger than L2 (>= 5 GB context at 16M bodies); no flush between steps"},
+        "same_workload_1gpu": same1,
+        "efficiency_same_workload": (same1["ms_per_step"] / (world * total_ms / args.steps)) if same1 else None,
         "interactions_per_body": float(inter.item()) / n,
         "interactions_per_s": float(inter.item()) * args.steps / (total_ms * 1e-3),
         "phase_ms_rank0": {k: round(v, 4) for k, v in acc.items()}, "force_ms_per_rank": force_per_rank,
         "allgather_ms": allgather_ms,
         "cells": cells, "e2e": e2e, "roofline": roofline,
-        "gpu_launches": bench.LAUNCHES_PER_STEP * args.steps * world, "clocks": ck,
+        "gpu_launches": (bench.LAUNCHES_PER_STEP + 2) * args.steps * world, "clocks": ck,
     }
     dist.destroy_process_group()
     return line if rank == 0 else None
