@@ -155,6 +155,9 @@ int bh_integrate_launch(const float4* posm_s, const float4* vel_s, const int32_t
 int bh_import_launch(const float* px, const float* py, const float* pz, const float* vx,
                      const float* vy, const float* vz, const float* m, int64_t n, float4* posm,
                      float4* vel, int32_t* ids, cudaStream_t st);
+int bh_import_pos_launch(const float* px, const float* py, const float* pz, int64_t n, float4* posm, cudaStream_t st);
+int bh_import_rest_launch(const float* vx, const float* vy, const float* vz, const float* m, int64_t n, float4* posm,
+                          float4* vel, int32_t* ids, cudaStream_t st);
 int bh_export_launch(const float4* posm, const float4* vel, const float4* acc, const int32_t* ids,
                      int64_t n, float* px, float* py, float* pz, float* vx, float* vy, float* vz,
                      float* ax, float* ay, float* az, cudaStream_t st);

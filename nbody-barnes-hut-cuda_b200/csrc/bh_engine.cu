@@ -81,6 +81,8 @@ struct bh_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t aux_stream = nullptr;       // second branch of the step: the centre-of-mass prefix sums run beside the tree build
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaStream_t copy_stream = nullptr;      // host uploads of bh_step_host (its events must not be the ones a capture re-records)
+    cudaEvent_t ev_h2d_pos = nullptr, ev_h2d_rest = nullptr;
     cudaEvent_t ev[BH_PHASE_COUNT + 1] = {};
     float phase_ms[BH_PHASE_COUNT] = {};
 };
@@ -100,6 +102,9 @@ void free_all(bh_ctx* c) {
     if (c->aux_stream) cudaStreamDestroy(c->aux_stream);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+    if (c->ev_h2d_pos) cudaEventDestroy(c->ev_h2d_pos);
+    if (c->ev_h2d_rest) cudaEventDestroy(c->ev_h2d_rest);
     void* ptrs[] = {c->posm, c->vel, c->posm_s, c->vel_s, c->acc, c->ids, c->ids_s, c->keys0, c->keys1, c->vals0,
                     c->vals1, c->sort_tmp, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
                     c->com_scratch, c->cell_com, c->sc, c->stage, c->d_scratch, c->heavy_list, c->heavy_flag, c->kid_src, c->kid_lv, c->kid_info, c->let_boxes, c->let_counts, c->let_queue, c->klo, c->kaux, c->keys64};
@@ -368,6 +373,9 @@ int bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device) 
     TRYA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
     TRYA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
     TRYA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    TRYA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+    TRYA(cudaEventCreateWithFlags(&c->ev_h2d_pos, cudaEventDisableTiming));
+    TRYA(cudaEventCreateWithFlags(&c->ev_h2d_rest, cudaEventDisableTiming));
     for (auto& ev : c->ev) TRYA(cudaEventCreate(&ev));
 #undef TRYA
     if (e == cudaSuccess) e = cudaMemset(c->sc, 0, sizeof(BhDevScalars));
@@ -781,24 +789,55 @@ int bh_export_soa_host(bh_ctx* c, float* px, float* py, float* pz, float* vx, fl
     return 0;
 }
 
+// Host state in -> nsteps -> host state out, every copy inside the call.  The uploads are ordered so that compute
+// starts early: positions first; bounds, keys and the radix sort (they read positions only) run while masses and
+// velocities are still crossing PCIe on the copy stream — the trick bh_mg_step plays for NVLink.
 int bh_step_host(bh_ctx* c, float* px, float* py, float* pz, float* vx, float* vy, float* vz, const float* mass,
                  int64_t n, int nsteps) {
-    int e = import_host_impl(c, px, py, pz, vx, vy, vz, mass, n, false);
+    if (!c || !px || !py || !pz || !vx || !vy || !vz || !mass || n <= 0 || n > c->n_max || nsteps < 0) return BH_E_INVAL;
+    BH_CUDA_TRY(cudaSetDevice(c->device));
+    int e = ensure_stage(c);
     if (e) return e;
-    e = bh_step(c, nsteps, c->own_stream);
-    if (e) return e;
-    // export on the same stream: no device-wide sync needed
-    e = ensure_stage(c);
-    if (e) return e;
-    const size_t na = (size_t)c->n_alloc;
+    const size_t na = (size_t)c->n_alloc, bytes = (size_t)n * 4;
     float* s = c->stage;
+    cudaStream_t cs = c->own_stream, xs = c->copy_stream;   // compute / copies
+    if (nsteps == 0 || (c->prm.flags & BH_FLAG_PHASE_TIMER)) {   // nothing to overlap with / phases are timed one by one
+        e = import_host_impl(c, px, py, pz, vx, vy, vz, mass, n, false);
+        if (!e) e = bh_step(c, nsteps, cs);
+        if (e) return e;
+    } else {
+        const float* first[3] = {px, py, pz};
+        const float* rest[4] = {vx, vy, vz, mass};
+        for (int k = 0; k < 3; ++k) BH_CUDA_TRY(cudaMemcpyAsync(s + (size_t)k * na, first[k], bytes, cudaMemcpyHostToDevice, xs));
+        BH_CUDA_TRY(cudaEventRecord(c->ev_h2d_pos, xs));
+        for (int k = 0; k < 4; ++k) BH_CUDA_TRY(cudaMemcpyAsync(s + (size_t)(3 + k) * na, rest[k], bytes, cudaMemcpyHostToDevice, xs));
+        BH_CUDA_TRY(cudaEventRecord(c->ev_h2d_rest, xs));
+        // what bh_import_soa does, in two parts
+        c->n = n; c->steps = 0; c->have_sorted = false; c->bbox_fresh = false;
+        default_slice(c);
+        BH_CUDA_TRY(cudaMemsetAsync((char*)c->sc + offsetof(BhDevScalars, epoch), 0, sizeof(BhDevScalars) - offsetof(BhDevScalars, epoch), cs));
+        BH_CUDA_TRY(cudaMemsetAsync(c->heavy_flag, 0, 8 * (size_t)c->max_chunks, cs));
+        BH_CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_h2d_pos, 0));
+        e = bh_import_pos_launch(s, s + na, s + 2 * na, n, c->posm, cs);
+        if (e) return e;
+        c->have_state = true;
+        e = bh_step_half(c, 0, cs);                       // bounds, keys, radix sort: positions only
+        if (e) return e;
+        BH_CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_h2d_rest, 0));
+        e = bh_import_rest_launch(s + 3 * na, s + 4 * na, s + 5 * na, s + 6 * na, n, c->posm, c->vel, c->ids, cs);
+        if (e) return e;
+        e = bh_step_half(c, 1, cs);                       // reorder .. update
+        if (!e && nsteps > 1) e = bh_step(c, nsteps - 1, cs);
+        if (e) return e;
+    }
+    // export on the compute stream, downloads behind it: no device-wide sync needed
     e = bh_export_launch(c->posm, c->vel, c->acc, c->ids, c->n, s, s + na, s + 2 * na, s + 3 * na, s + 4 * na, s + 5 * na,
-                         nullptr, nullptr, nullptr, c->own_stream);
+                         nullptr, nullptr, nullptr, cs);
     if (e) return e;
     float* dst[6] = {px, py, pz, vx, vy, vz};
     for (int k = 0; k < 6; ++k)
-        BH_CUDA_TRY(cudaMemcpyAsync(dst[k], s + (size_t)k * na, (size_t)n * 4, cudaMemcpyDeviceToHost, c->own_stream));
-    BH_CUDA_TRY(cudaStreamSynchronize(c->own_stream));
+        BH_CUDA_TRY(cudaMemcpyAsync(dst[k], s + (size_t)k * na, bytes, cudaMemcpyDeviceToHost, cs));
+    BH_CUDA_TRY(cudaStreamSynchronize(cs));
     return 0;
 }
 

@@ -316,6 +316,25 @@ __global__ void __launch_bounds__(kThreads) import_kernel(const float* __restric
     }
 }
 
+// The same import in two parts, for the host-pointer step: positions first (all that bounds, keys and the radix
+// sort read), masses + velocities + ids when their upload has landed.
+__global__ void __launch_bounds__(kThreads) import_pos_kernel(const float* __restrict__ px, const float* __restrict__ py,
+                                                             const float* __restrict__ pz, int64_t n, float4* __restrict__ posm) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+        posm[i] = make_float4(px[i], py[i], pz[i], 0.0f);
+}
+
+__global__ void __launch_bounds__(kThreads) import_rest_kernel(const float* __restrict__ vx, const float* __restrict__ vy,
+                                                              const float* __restrict__ vz, const float* __restrict__ m, int64_t n,
+                                                              float4* __restrict__ posm, float4* __restrict__ vel,
+                                                              int32_t* __restrict__ ids) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        reinterpret_cast<float*>(posm + i)[3] = m[i];
+        vel[i] = make_float4(vx[i], vy[i], vz[i], 0.0f);
+        ids[i] = (int32_t)i;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) export_kernel(const float4* __restrict__ posm, const float4* __restrict__ vel,
                                                          const float4* __restrict__ acc, const int32_t* __restrict__ ids,
                                                          int64_t n, float* px, float* py, float* pz, float* vx,
@@ -403,6 +422,17 @@ int bh_import_launch(const float* px, const float* py, const float* pz, const fl
                      const float* vy, const float* vz, const float* m, int64_t n, float4* posm,
                      float4* vel, int32_t* ids, cudaStream_t st) {
     import_kernel<<<grid_for(n, 2), kThreads, 0, st>>>(px, py, pz, vx, vy, vz, m, n, posm, vel, ids);
+    return (int)cudaGetLastError();
+}
+
+int bh_import_pos_launch(const float* px, const float* py, const float* pz, int64_t n, float4* posm, cudaStream_t st) {
+    import_pos_kernel<<<grid_for(n, 2), kThreads, 0, st>>>(px, py, pz, n, posm);
+    return (int)cudaGetLastError();
+}
+
+int bh_import_rest_launch(const float* vx, const float* vy, const float* vz, const float* m, int64_t n, float4* posm,
+                          float4* vel, int32_t* ids, cudaStream_t st) {
+    import_rest_kernel<<<grid_for(n, 2), kThreads, 0, st>>>(vx, vy, vz, m, n, posm, vel, ids);
     return (int)cudaGetLastError();
 }
 

@@ -135,3 +135,31 @@ def test_bench_front_end_prints_the_reference_table(bh):
     assert any(ln.startswith("Frame      | Trajanje (ms)   | FPS") for ln in out)
     assert sum(1 for ln in out if ln[:1].isdigit() and "|" in ln) == 3
     assert any("interactions/s" in ln for ln in out) and any("octree build" in ln for ln in out)
+
+
+def test_the_reference_bench_itself_runs_on_libbh(bh):
+    """INTEGRATION.md, compiled: /root/reference/nbody_v5_bench.cu with the documented patch applied by
+    tools/integration/patch_reference.py (simulationStep() -> bh_step, bh_create/bh_import_soa after the reference's
+    own uploads, bh_export_soa into its arrays before its cudaFrees) and linked with -lbh.  Its own main() generates
+    the disk, prints its own table; the state it reads back equals the engine driven through the Python binding."""
+    import re
+
+    exe = os.path.join(os.path.dirname(os.path.dirname(bh.library_path())), "oracle", "_ref", "nbody_v5_bench_libbh")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/nbody_v5_bench_libbh not built (needs /root/reference at build time)")
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    out = r.stdout
+    assert "Pokretanje Benchmarka za N = 500000" in out                      # bench:287 with the reference's default N (bench:31)
+    frames = re.findall(r"^(\d+)\s+\|\s+([0-9.]+)\s+\|\s+([0-9.]+)", out, re.M)
+    assert len(frames) == 100 and [int(f[0]) for f in frames] == list(range(100))
+    m = re.search(r"libbh: sum\(posX\) after 100 frames = ([-0-9.eE+]+), interactions/body = ([0-9.]+), device error flag = (\d+)", out)
+    assert m and int(m.group(3)) == 0 and 500 < float(m.group(2)) < 3000
+    n = 500_000
+    soa = bh.ic_refdisk(n, 42)
+    with bh.BHEngine(n) as eng:
+        eng.load_soa(*soa)
+        eng.simulation_step(100)
+        want = eng.read_soa(want_acc=False)[0].astype(np.float64).sum()
+    assert abs(float(m.group(1)) - want) <= 1e-6 * max(1.0, abs(want))
+    assert np.median([float(f[1]) for f in frames]) < 5.0                    # ms per frame at 500k bodies (reference: ~30)
