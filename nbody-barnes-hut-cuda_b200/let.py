@@ -663,14 +663,14 @@ def run_let_bench(args, w, bh, dist, rank, world, local):
         "metric": "body-steps/s", "value": n * args.steps / (total_ms * 1e-3), "unit": "body-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "desc": w["desc"], "n_bodies": n, "theta": 0.5, "G": 0.5, "dt": 0.02,
-                   "softening": 50.0, "max_speed": 500.0, "group": 32, "key_bits": key_bits,
-                   "let_interval": sim.interval,
+        "config": bench.workload_config(args, w),
+        "engine": {"group": 32, "key_bits": key_bits, "let_interval": sim.interval,
                    "parallelism": f"locally-essential-tree x{world}: work-weighted sampled key splitters, body migration, "
                                   "per-peer export walk against octree-aligned domain boxes, NCCL all-to-all of point "
                                   "masses, traversal of the own tree + of a small tree of the imported points",
                    "l2": "state far larger than L2; no flush between steps"},
         "interactions_per_body": float(inter.item()) / n, "interactions_per_s": float(inter.item()) * args.steps / (total_ms * 1e-3),
+        "force_share": max(row[4] for row in stats_all.tolist()) / (total_ms / args.steps),
         "let_exported_imported_local_migrated_per_rank": [[int(x) for x in row[:4]] for row in stats_all.tolist()],
         "strays_rank0_last_step": int(sim.stats.get("strays", 0)),
         "forces_update_ms_per_rank": [round(row[4], 3) for row in stats_all.tolist()],
