@@ -123,8 +123,11 @@ struct BodyMove {
     float4* posm_out; float4* vel_out; int32_t* ids_out;
 };
 
+#ifndef BH_SORT_MIN_CTAS
+#define BH_SORT_MIN_CTAS 3
+#endif
 template <bool IOTA, bool MOVE>
-__global__ void __launch_bounds__(SORT_THREADS, 3) onesweep_kernel(const uint32_t* __restrict__ keys_in,
+__global__ void __launch_bounds__(SORT_THREADS, BH_SORT_MIN_CTAS) onesweep_kernel(const uint32_t* __restrict__ keys_in,
                                                                const uint32_t* __restrict__ vals_in,
                                                                uint32_t* __restrict__ keys_out,
                                                                uint32_t* __restrict__ vals_out, int64_t n, int shift,
