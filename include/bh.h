@@ -191,6 +191,11 @@ int  bh_set_slice(bh_ctx* ctx, int rank, int world);
  * (reads positions only); half 1 = reorder, tree, centre of mass, traversal, update (needs velocities
  * and ids as well).  bh_step_half(0) + bh_step_half(1) == bh_step(ctx, 1).                          */
 int  bh_step_half(bh_ctx* ctx, int half, void* stream);
+/* The same step in THREE parts, for hosts that overlap transfers with compute: part 0 = cube, keys, radix sort (reads
+ * positions only); part 1 = reorder of positions + masses, tree, centre of mass, traversal (still no velocity, and no
+ * id unless the state came through bh_import_state); part 2 = reorder of velocities + ids, update.
+ * bh_step_part(0) + (1) + (2) == bh_step(ctx, 1) bit for bit.  bh_mg_step and bh_step_host are built on it.      */
+int  bh_step_part(bh_ctx* ctx, int part, void* stream);
 /* Device pointers to the CURRENT Morton-ordered state (float4 posm, float4
  * vel, int32 ids) and this rank's slice [first, first+count).              */
 int  bh_state_ptrs(bh_ctx* ctx, void** posm, void** vel, void** ids,

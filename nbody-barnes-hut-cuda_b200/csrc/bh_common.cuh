@@ -156,8 +156,11 @@ int bh_import_launch(const float* px, const float* py, const float* pz, const fl
                      const float* vy, const float* vz, const float* m, int64_t n, float4* posm,
                      float4* vel, int32_t* ids, cudaStream_t st);
 int bh_import_pos_launch(const float* px, const float* py, const float* pz, int64_t n, float4* posm, cudaStream_t st);
-int bh_import_rest_launch(const float* vx, const float* vy, const float* vz, const float* m, int64_t n, float4* posm,
-                          float4* vel, int32_t* ids, cudaStream_t st);
+int bh_import_mass_launch(const float* m, int64_t n, float4* posm, cudaStream_t st);
+int bh_import_vel_launch(const float* vx, const float* vy, const float* vz, int64_t n, float4* vel, int32_t* ids, cudaStream_t st);
+int bh_reorder_posm_launch(const float4* posm_in, const uint32_t* perm, float4* posm_out, int64_t n, cudaStream_t st);
+int bh_reorder_rest_launch(const float4* vel_in, const int32_t* ids_in, const uint32_t* perm, float4* vel_out, int32_t* ids_out,
+                           int64_t n, cudaStream_t st);
 int bh_export_launch(const float4* posm, const float4* vel, const float4* acc, const int32_t* ids,
                      int64_t n, float* px, float* py, float* pz, float* vx, float* vy, float* vz,
                      float* ax, float* ay, float* az, cudaStream_t st);

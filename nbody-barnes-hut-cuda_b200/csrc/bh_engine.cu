@@ -76,13 +76,16 @@ struct bh_ctx {
 
     cudaGraphExec_t graph_exec = nullptr;
     int64_t graph_n = -1, graph_first = -1, graph_count = -1;
-    cudaGraphExec_t half_exec[2] = {nullptr, nullptr};   // head / tail of the step (bh_step_half)
+    // the step in three parts (bh_step_part): 0 = cube, keys, radix sort (positions only); 1 = reorder positions +
+    // masses, tree, centre of mass, traversal; 2 = reorder velocities + ids, update
+    cudaGraphExec_t half_exec[3] = {nullptr, nullptr, nullptr};
+    bool may_have_ghosts = false;   // ids < 0 possible (bh_import_state / checkpoint): the traversal must read the ids
     int64_t graph_half_n = -1, graph_half_first = -1, graph_half_count = -1;
     cudaStream_t own_stream = nullptr;
     cudaStream_t aux_stream = nullptr;       // second branch of the step: the centre-of-mass prefix sums run beside the tree build
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaStream_t copy_stream = nullptr;      // host uploads of bh_step_host (its events must not be the ones a capture re-records)
-    cudaEvent_t ev_h2d_pos = nullptr, ev_h2d_rest = nullptr;
+    cudaEvent_t ev_h2d_pos = nullptr, ev_h2d_mass = nullptr, ev_h2d_rest = nullptr;
     cudaEvent_t ev[BH_PHASE_COUNT + 1] = {};
     float phase_ms[BH_PHASE_COUNT] = {};
 };
@@ -105,6 +108,7 @@ void free_all(bh_ctx* c) {
     if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
     if (c->ev_h2d_pos) cudaEventDestroy(c->ev_h2d_pos);
     if (c->ev_h2d_rest) cudaEventDestroy(c->ev_h2d_rest);
+    if (c->ev_h2d_mass) cudaEventDestroy(c->ev_h2d_mass);
     void* ptrs[] = {c->posm, c->vel, c->posm_s, c->vel_s, c->acc, c->ids, c->ids_s, c->keys0, c->keys1, c->vals0,
                     c->vals1, c->sort_tmp, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
                     c->com_scratch, c->cell_com, c->sc, c->stage, c->d_scratch, c->heavy_list, c->heavy_flag, c->kid_src, c->kid_lv, c->kid_info, c->let_boxes, c->let_counts, c->let_queue, c->klo, c->kaux, c->keys64};
@@ -212,7 +216,8 @@ int phase_com(bh_ctx* c, cudaStream_t st) {
 }
 
 int phase_force(bh_ctx* c, cudaStream_t st) {
-    return bh_force_launch(c->posm_s, c->levels == 20 ? (const void*)c->keys64 : (const void*)c->keys0, c->levels, c->ids_s, c->n, c->slice_first, c->slice_count, c->cell_meta,
+    return bh_force_launch(c->posm_s, c->levels == 20 ? (const void*)c->keys64 : (const void*)c->keys0, c->levels,
+                           c->may_have_ghosts ? c->ids_s : nullptr, c->n, c->slice_first, c->slice_count, c->cell_meta,
                            c->cell_com, c->kid_src, c->kid_info, c->acc, c->sc, c->heavy_list, c->heavy_flag, c->max_chunks, c->prm.theta,
                            c->prm.softening, c->prm.G, c->prm.group_split, c->num_sms, nullptr, nullptr, 0, st);
 }
@@ -249,28 +254,44 @@ int launch_all_phases(bh_ctx* c, cudaStream_t st) {
     return e;
 }
 
-// The step in two halves for multi-GPU overlap: the HEAD (bounds, keys, radix sort) reads positions only, so
-// it can run while the all-gather of velocities and ids is still in flight; the TAIL is everything else.
-int launch_half(bh_ctx* c, int half, cudaStream_t st) {
-    if (half == 0) {
+// The step in THREE parts, so that transfers can hide behind compute (NVLink all-gathers in bh_mg_step, PCIe uploads in
+// bh_step_host): part 0 — cube, keys, radix sort — reads positions only; part 1 — reorder of positions + masses, tree,
+// centre of mass, traversal — still needs no velocity (and no id unless ghosts are possible); only part 2 — reorder of
+// velocities + ids, kick-drift-clamp — needs the rest of the state.
+int launch_part(bh_ctx* c, int part, cudaStream_t st) {
+    if (part == 0) {
         int e = phase_keys(c, st);
         if (e) return e;
         return sort_keys_only(c, st);
     }
-    int e = reorder_only(c, st);
-    if (!e) e = launch_tail_overlapped(c, st);
+    if (part == 1) {
+        int e = c->may_have_ghosts ? reorder_only(c, st) : bh_reorder_posm_launch(c->posm, c->perm, c->posm_s, c->n, st);
+        if (e) return e;
+        BH_CUDA_TRY(cudaEventRecord(c->ev_fork, st));
+        BH_CUDA_TRY(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+        e = bh_com_prefix_launch(c->posm_s, c->n, c->com_scratch, c->aux_stream);
+        if (!e) e = phase_build(c, st);
+        BH_CUDA_TRY(cudaEventRecord(c->ev_join, c->aux_stream));
+        BH_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));
+        if (e) return e;
+        e = bh_com_cells_launch(c->posm_s, c->n, c->cell_meta, c->cell_child, c->com_scratch, c->cell_com, c->kid_src, c->kid_info, c->sc, st);
+        if (!e) e = phase_force(c, st);
+        return e;
+    }
+    int e = c->may_have_ghosts ? 0 : bh_reorder_rest_launch(c->vel, c->ids, c->perm, c->vel_s, c->ids_s, c->n, st);
+    if (!e) e = phase_update(c, st);
     return e;
 }
 
 int ensure_half_graphs(bh_ctx* c) {
-    if (c->half_exec[0] && c->half_exec[1] && c->graph_half_n == c->n && c->graph_half_first == c->slice_first &&
+    if (c->half_exec[0] && c->half_exec[1] && c->half_exec[2] && c->graph_half_n == c->n && c->graph_half_first == c->slice_first &&
         c->graph_half_count == c->slice_count)
         return 0;
-    for (int h = 0; h < 2; ++h) {
+    for (int h = 0; h < 3; ++h) {
         if (c->half_exec[h]) { cudaGraphExecDestroy(c->half_exec[h]); c->half_exec[h] = nullptr; }
         cudaGraph_t graph = nullptr;
         BH_CUDA_TRY(cudaStreamBeginCapture(c->own_stream, cudaStreamCaptureModeThreadLocal));
-        int e = launch_half(c, h, c->own_stream);
+        int e = launch_part(c, h, c->own_stream);
         cudaError_t ce = cudaStreamEndCapture(c->own_stream, &graph);
         if (e) { if (graph) cudaGraphDestroy(graph); return e; }
         if (ce != cudaSuccess) return (int)ce;
@@ -296,6 +317,16 @@ int ensure_graph(bh_ctx* c) {
     cudaGraphDestroy(graph);
     if (ce != cudaSuccess) return (int)ce;
     c->graph_n = c->n; c->graph_first = c->slice_first; c->graph_count = c->slice_count;
+    return 0;
+}
+
+// the captured graphs bake in whether the traversal reads the ids: drop them when that changes
+int set_ghosts_possible(bh_ctx* c, bool yes) {
+    if (c->may_have_ghosts == yes) return 0;
+    c->may_have_ghosts = yes;
+    BH_CUDA_TRY(cudaDeviceSynchronize());
+    if (c->graph_exec) { cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }
+    for (auto& g : c->half_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     return 0;
 }
 
@@ -376,6 +407,7 @@ int bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device) 
     TRYA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
     TRYA(cudaEventCreateWithFlags(&c->ev_h2d_pos, cudaEventDisableTiming));
     TRYA(cudaEventCreateWithFlags(&c->ev_h2d_rest, cudaEventDisableTiming));
+    TRYA(cudaEventCreateWithFlags(&c->ev_h2d_mass, cudaEventDisableTiming));
     for (auto& ev : c->ev) TRYA(cudaEventCreate(&ev));
 #undef TRYA
     if (e == cudaSuccess) e = cudaMemset(c->sc, 0, sizeof(BhDevScalars));
@@ -399,6 +431,7 @@ int bh_import_soa(bh_ctx* c, const float* px, const float* py, const float* pz, 
     if (!c || !px || !py || !pz || !vx || !vy || !vz || !mass || n <= 0 || n > c->n_max) return BH_E_INVAL;
     BH_CUDA_TRY(cudaSetDevice(c->device));
     c->n = n; c->steps = 0; c->have_sorted = false; c->bbox_fresh = false;
+    { int eg = set_ghosts_possible(c, false); if (eg) return eg; }
     default_slice(c);
     // scheduling history of the previous body set is meaningless now
     BH_CUDA_TRY(cudaMemsetAsync((char*)c->sc + offsetof(BhDevScalars, epoch), 0,
@@ -470,6 +503,7 @@ int bh_import_state(bh_ctx* c, const void* posm, const void* vel, const int32_t*
     BH_CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     c->n = n; c->steps = 0; c->have_sorted = false; c->bbox_fresh = false;
+    { int eg = set_ghosts_possible(c, true); if (eg) return eg; }   // the caller's ids may mark ghosts (id < 0)
     default_slice(c);
     BH_CUDA_TRY(cudaMemsetAsync((char*)c->sc + offsetof(BhDevScalars, epoch), 0,
                                 sizeof(BhDevScalars) - offsetof(BhDevScalars, epoch), st));
@@ -715,22 +749,29 @@ int bh_step(bh_ctx* c, int nsteps, void* stream) {
     return 0;
 }
 
-int bh_step_half(bh_ctx* c, int half, void* stream) {
-    if (!c || half < 0 || half > 1) return BH_E_INVAL;
+int bh_step_part(bh_ctx* c, int part, void* stream) {
+    if (!c || part < 0 || part > 2) return BH_E_INVAL;
     if (!c->have_state) return BH_E_STATE;
     BH_CUDA_TRY(cudaSetDevice(c->device));
-    if (half == 0) { int e = pre_keys(c, (cudaStream_t)stream); if (e) return e; }
+    if (part == 0) { int e = pre_keys(c, (cudaStream_t)stream); if (e) return e; }
     if (c->prm.flags & (BH_FLAG_NO_GRAPH | BH_FLAG_PHASE_TIMER)) {
-        int e = launch_half(c, half, (cudaStream_t)stream);
+        int e = launch_part(c, part, (cudaStream_t)stream);
         if (e) return e;
     } else {
         int e = ensure_half_graphs(c);
         if (e) return e;
-        BH_CUDA_TRY(cudaGraphLaunch(c->half_exec[half], (cudaStream_t)stream));
+        BH_CUDA_TRY(cudaGraphLaunch(c->half_exec[part], (cudaStream_t)stream));
     }
-    if (half == 0) { c->bbox_fresh = false; c->keys_sorted = true; }   // images consumed by the keys phase; keys sorted
-    if (half == 1) { c->steps += 1; c->have_sorted = true; post_update(c); }
+    if (part == 0) { c->bbox_fresh = false; c->keys_sorted = true; }   // images consumed by the keys phase; keys sorted
+    if (part == 2) { c->steps += 1; c->have_sorted = true; post_update(c); }
     return 0;
+}
+
+int bh_step_half(bh_ctx* c, int half, void* stream) {
+    if (!c || half < 0 || half > 1) return BH_E_INVAL;
+    if (half == 0) return bh_step_part(c, 0, stream);
+    int e = bh_step_part(c, 1, stream);
+    return e ? e : bh_step_part(c, 2, stream);
 }
 
 int bh_run_phase(bh_ctx* c, int phase, void* stream) {
@@ -806,14 +847,20 @@ int bh_step_host(bh_ctx* c, float* px, float* py, float* pz, float* vx, float* v
         if (!e) e = bh_step(c, nsteps, cs);
         if (e) return e;
     } else {
-        const float* first[3] = {px, py, pz};
-        const float* rest[4] = {vx, vy, vz, mass};
-        for (int k = 0; k < 3; ++k) BH_CUDA_TRY(cudaMemcpyAsync(s + (size_t)k * na, first[k], bytes, cudaMemcpyHostToDevice, xs));
-        BH_CUDA_TRY(cudaEventRecord(c->ev_h2d_pos, xs));
-        for (int k = 0; k < 4; ++k) BH_CUDA_TRY(cudaMemcpyAsync(s + (size_t)(3 + k) * na, rest[k], bytes, cudaMemcpyHostToDevice, xs));
+        // upload order = order of need: positions (cube, keys, sort), masses (tree, centre of mass, traversal),
+        // velocities (update only) — the whole velocity upload hides behind the tree build and the traversal
+        const float* src[7] = {px, py, pz, mass, vx, vy, vz};
+        const int slot[7] = {0, 1, 2, 6, 3, 4, 5};
+        for (int k = 0; k < 7; ++k) {
+            BH_CUDA_TRY(cudaMemcpyAsync(s + (size_t)slot[k] * na, src[k], bytes, cudaMemcpyHostToDevice, xs));
+            if (k == 2) BH_CUDA_TRY(cudaEventRecord(c->ev_h2d_pos, xs));
+            if (k == 3) BH_CUDA_TRY(cudaEventRecord(c->ev_h2d_mass, xs));
+        }
         BH_CUDA_TRY(cudaEventRecord(c->ev_h2d_rest, xs));
-        // what bh_import_soa does, in two parts
+        // what bh_import_soa does, in three parts
         c->n = n; c->steps = 0; c->have_sorted = false; c->bbox_fresh = false;
+        e = set_ghosts_possible(c, false);
+        if (e) return e;
         default_slice(c);
         BH_CUDA_TRY(cudaMemsetAsync((char*)c->sc + offsetof(BhDevScalars, epoch), 0, sizeof(BhDevScalars) - offsetof(BhDevScalars, epoch), cs));
         BH_CUDA_TRY(cudaMemsetAsync(c->heavy_flag, 0, 8 * (size_t)c->max_chunks, cs));
@@ -821,12 +868,15 @@ int bh_step_host(bh_ctx* c, float* px, float* py, float* pz, float* vx, float* v
         e = bh_import_pos_launch(s, s + na, s + 2 * na, n, c->posm, cs);
         if (e) return e;
         c->have_state = true;
-        e = bh_step_half(c, 0, cs);                       // bounds, keys, radix sort: positions only
+        e = bh_step_part(c, 0, cs);                       // cube, keys, radix sort: positions only
+        if (e) return e;
+        BH_CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_h2d_mass, 0));
+        e = bh_import_mass_launch(s + 6 * na, n, c->posm, cs);
+        if (!e) e = bh_step_part(c, 1, cs);               // reorder positions + masses, tree, centre of mass, traversal
         if (e) return e;
         BH_CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_h2d_rest, 0));
-        e = bh_import_rest_launch(s + 3 * na, s + 4 * na, s + 5 * na, s + 6 * na, n, c->posm, c->vel, c->ids, cs);
-        if (e) return e;
-        e = bh_step_half(c, 1, cs);                       // reorder .. update
+        e = bh_import_vel_launch(s + 3 * na, s + 4 * na, s + 5 * na, n, c->vel, c->ids, cs);
+        if (!e) e = bh_step_part(c, 2, cs);               // reorder velocities + ids, update
         if (!e && nsteps > 1) e = bh_step(c, nsteps - 1, cs);
         if (e) return e;
     }
@@ -895,6 +945,7 @@ int bh_debug_set(bh_ctx* c, int what, const void* src, size_t bytes) {
     if (bytes != want) return BH_E_INVAL;
     if (bytes == 0) return 0;
     c->bbox_fresh = false;   // the caller may have moved bodies
+    if (what == BH_DBG_IDS || what == BH_DBG_IDS_SORTED) { int eg = set_ghosts_possible(c, true); if (eg) return eg; }
     return (int)cudaMemcpy(p, src, bytes, cudaMemcpyHostToDevice);
 }
 
@@ -1069,6 +1120,7 @@ int bh_load_checkpoint(bh_ctx* c, const char* path) {
     c->prm.theta = h.theta; c->prm.G = h.G; c->prm.dt = h.dt;
     c->prm.softening = h.softening; c->prm.max_speed = h.max_speed;
     c->n = h.n; c->steps = h.steps; c->have_state = true; c->have_sorted = false; c->bbox_fresh = false;
+    { int eg = set_ghosts_possible(c, true); if (eg) return eg; }   // ids come from the file
     default_slice(c);
     BH_CUDA_TRY(cudaMemset((char*)c->sc + offsetof(BhDevScalars, epoch), 0, sizeof(BhDevScalars) - offsetof(BhDevScalars, epoch)));
     BH_CUDA_TRY(cudaMemset(c->heavy_flag, 0, 8 * (size_t)c->max_chunks));

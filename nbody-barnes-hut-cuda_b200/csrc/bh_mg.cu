@@ -4,10 +4,10 @@
 // GPU holds the full state; each step every rank sorts and builds on all bodies (deterministic: identical trees
 // without a broadcast), traverses + integrates only its own Morton slice, and the ranks all-gather the updated
 // slices in place over NCCL / NVLink (posm 16 B, vel 16 B, ids 4 B per body).  Everything is asynchronous:
-//   compute stream   [wait posm] keys + sort   [wait vel, ids] reorder .. traversal .. update   [record done]
+//   compute stream   [wait posm] keys + sort, tree, centre of mass, traversal   [wait vel, ids] update   [record done]
 //   comm stream      [wait done] all-gather posm [record]  all-gather vel, ids [record]
-// so the next step's keys + radix sort — which read positions only — run while velocities and ids are still
-// crossing NVLink, and no host thread ever blocks.
+// Only the kick-drift update reads velocities and ids, so their gathers (20 of the 36 B/body) hide behind the whole
+// next step up to its last kernel, and no host thread ever blocks.
 //
 // NCCL is loaded lazily with dlopen (RTLD_NOLOAD first: a host process that already carries an NCCL — e.g. the
 // one bundled with PyTorch — keeps exactly that one); libbh.so itself has no link-time dependency on it.
@@ -168,11 +168,12 @@ int bh_mg_step(bh_mg* m, int nsteps, void* stream) {
     int e = mg_refresh(m);
     if (e) return e;
     for (int s = 0; s < nsteps; ++s) {
-        if (m->in_flight) BH_CUDA_TRY(cudaStreamWaitEvent(st, m->ev_posm, 0));   // positions of the previous step are complete
-        e = bh_step_half(m->ctx, 0, st);
+        if (m->in_flight) BH_CUDA_TRY(cudaStreamWaitEvent(st, m->ev_posm, 0));   // positions + masses of the previous step are complete
+        e = bh_step_part(m->ctx, 0, st);                                          // cube, keys, radix sort
+        if (!e) e = bh_step_part(m->ctx, 1, st);                                  // tree, centre of mass, traversal: no velocity needed
         if (e) return e;
-        if (m->in_flight) BH_CUDA_TRY(cudaStreamWaitEvent(st, m->ev_rest, 0));   // velocities and ids too
-        e = bh_step_half(m->ctx, 1, st);
+        if (m->in_flight) BH_CUDA_TRY(cudaStreamWaitEvent(st, m->ev_rest, 0));   // velocities and ids: only the update reads them
+        e = bh_step_part(m->ctx, 2, st);
         if (e) return e;
         if (m->world > 1) { e = mg_gather(m, st); if (e) return e; }
     }

@@ -167,6 +167,23 @@ __global__ void __launch_bounds__(kThreads) reorder_kernel(const float4* __restr
     }
 }
 
+// the same in two parts (three-part step: positions are needed long before velocities and ids)
+__global__ void __launch_bounds__(kThreads) reorder_posm_kernel(const float4* __restrict__ posm_in, const uint32_t* __restrict__ perm,
+                                                               float4* __restrict__ posm_out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
+        posm_out[i] = __ldg(posm_in + perm[i]);
+}
+
+__global__ void __launch_bounds__(kThreads) reorder_rest_kernel(const float4* __restrict__ vel_in, const int32_t* __restrict__ ids_in,
+                                                               const uint32_t* __restrict__ perm, float4* __restrict__ vel_out,
+                                                               int32_t* __restrict__ ids_out, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        const uint32_t j = perm[i];
+        vel_out[i] = __ldg(vel_in + j);
+        ids_out[i] = __ldg(ids_in + j);
+    }
+}
+
 // ---- kick-drift-clamp ----------------------------------------------------------------------
 // bench:232-248 with the contraction nvcc applies to it:
 //   v = fma(a,DT,v); s = fma(vz,vz,fma(vx,vx,vy*vy)); if s > MAX^2: v *= MAX/sqrt(s); p = fma(v,DT,p)
@@ -324,12 +341,15 @@ __global__ void __launch_bounds__(kThreads) import_pos_kernel(const float* __res
         posm[i] = make_float4(px[i], py[i], pz[i], 0.0f);
 }
 
-__global__ void __launch_bounds__(kThreads) import_rest_kernel(const float* __restrict__ vx, const float* __restrict__ vy,
-                                                              const float* __restrict__ vz, const float* __restrict__ m, int64_t n,
-                                                              float4* __restrict__ posm, float4* __restrict__ vel,
-                                                              int32_t* __restrict__ ids) {
-    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+__global__ void __launch_bounds__(kThreads) import_mass_kernel(const float* __restrict__ m, int64_t n, float4* __restrict__ posm) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads)
         reinterpret_cast<float*>(posm + i)[3] = m[i];
+}
+
+__global__ void __launch_bounds__(kThreads) import_vel_kernel(const float* __restrict__ vx, const float* __restrict__ vy,
+                                                             const float* __restrict__ vz, int64_t n, float4* __restrict__ vel,
+                                                             int32_t* __restrict__ ids) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
         vel[i] = make_float4(vx[i], vy[i], vz[i], 0.0f);
         ids[i] = (int32_t)i;
     }
@@ -430,9 +450,24 @@ int bh_import_pos_launch(const float* px, const float* py, const float* pz, int6
     return (int)cudaGetLastError();
 }
 
-int bh_import_rest_launch(const float* vx, const float* vy, const float* vz, const float* m, int64_t n, float4* posm,
-                          float4* vel, int32_t* ids, cudaStream_t st) {
-    import_rest_kernel<<<grid_for(n, 2), kThreads, 0, st>>>(vx, vy, vz, m, n, posm, vel, ids);
+int bh_import_mass_launch(const float* m, int64_t n, float4* posm, cudaStream_t st) {
+    import_mass_kernel<<<grid_for(n, 2), kThreads, 0, st>>>(m, n, posm);
+    return (int)cudaGetLastError();
+}
+
+int bh_import_vel_launch(const float* vx, const float* vy, const float* vz, int64_t n, float4* vel, int32_t* ids, cudaStream_t st) {
+    import_vel_kernel<<<grid_for(n, 2), kThreads, 0, st>>>(vx, vy, vz, n, vel, ids);
+    return (int)cudaGetLastError();
+}
+
+int bh_reorder_posm_launch(const float4* posm_in, const uint32_t* perm, float4* posm_out, int64_t n, cudaStream_t st) {
+    reorder_posm_kernel<<<grid_for(n, 2), kThreads, 0, st>>>(posm_in, perm, posm_out, n);
+    return (int)cudaGetLastError();
+}
+
+int bh_reorder_rest_launch(const float4* vel_in, const int32_t* ids_in, const uint32_t* perm, float4* vel_out, int32_t* ids_out,
+                           int64_t n, cudaStream_t st) {
+    reorder_rest_kernel<<<grid_for(n, 2), kThreads, 0, st>>>(vel_in, ids_in, perm, vel_out, ids_out, n);
     return (int)cudaGetLastError();
 }
 

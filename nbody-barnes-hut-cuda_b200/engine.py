@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
     L.bh_import_soa_host.argtypes = [vp] + [vp] * 7 + [i64]
     L.bh_step.argtypes = [vp, i32, vp]
     L.bh_step_half.argtypes = [vp, i32, vp]
+    L.bh_step_part.argtypes = [vp, i32, vp]
     L.bh_export_soa.argtypes = [vp] + [vp] * 9 + [vp]
     L.bh_export_soa_host.argtypes = [vp] + [vp] * 9
     L.bh_step_host.argtypes = [vp] + [vp] * 7 + [i64, i32]
@@ -352,6 +353,10 @@ class BHEngine:
     def step_half(self, half: int, stream: int = 0):
         """Head (0: bounds, keys, sort — positions only) or tail (1: the rest) of one step."""
         _check(lib().bh_step_half(self._ctx, half, C.c_void_p(stream)), "bh_step_half")
+
+    def step_part(self, part: int, stream: int = 0):
+        """One of the three parts of a step (0: cube, keys, sort; 1: tree, centre of mass, traversal; 2: update)."""
+        _check(lib().bh_step_part(self._ctx, part, C.c_void_p(stream)), "bh_step_part")
 
     def read_soa(self, want_acc: bool = True):
         """Device state -> host SoA in ORIGINAL body order: (px,py,pz,vx,vy,vz[,ax,ay,az])."""

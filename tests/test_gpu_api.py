@@ -133,6 +133,50 @@ def test_step_halves_equal_a_full_step(bh):
             assert (got[2] == want[2]).all()
 
 
+def test_step_parts_and_host_step_equal_a_full_step(bh):
+    """bh_step_part(0) + (1) + (2) == bh_step(1), with and without graphs, also for a state with ghosts (where part 1
+    moves the ids too); bh_step_host — which uploads in order of need and runs the parts as the data lands — gives the
+    same bits as load + step + read."""
+    import torch
+
+    n = 30000
+    soa = bh.ic_refdisk(n, 42)
+    with bh.BHEngine(n) as ref:
+        ref.load_soa(*soa)
+        ref.simulation_step(3)
+        want = (ref.debug_get(bh.DBG.POSM), ref.debug_get(bh.DBG.VEL), ref.debug_get(bh.DBG.IDS))
+        want_soa = ref.read_soa(want_acc=False)
+    for flags in (0, 1):
+        with bh.BHEngine(n, flags=flags) as eng:
+            eng.load_soa(*soa)
+            for _ in range(3):
+                for part in range(3):
+                    eng.step_part(part)
+            eng.check_device_error()
+            assert eng.stat(bh.STAT.STEPS) == 3
+            got = (eng.debug_get(bh.DBG.POSM), eng.debug_get(bh.DBG.VEL), eng.debug_get(bh.DBG.IDS))
+            assert got[0].tobytes() == want[0].tobytes() and got[1].tobytes() == want[1].tobytes() and (got[2] == want[2]).all()
+    # a state that came through bh_import_state (ghosts possible): same physics when every id is >= 0
+    posm = torch.from_numpy(np.stack([soa[0], soa[1], soa[2], soa[6]], 1)).cuda()
+    vel = torch.from_numpy(np.stack([soa[3], soa[4], soa[5], np.zeros(n, np.float32)], 1)).cuda()
+    ids = torch.arange(n, dtype=torch.int32, device="cuda")
+    with bh.BHEngine(n) as eng:
+        eng.import_state(posm, vel, ids, n)
+        for _ in range(3):
+            for part in range(3):
+                eng.step_part(part)
+        got = (eng.debug_get(bh.DBG.POSM), eng.debug_get(bh.DBG.VEL), eng.debug_get(bh.DBG.IDS))
+        assert got[0].tobytes() == want[0].tobytes() and got[1].tobytes() == want[1].tobytes() and (got[2] == want[2]).all()
+    # host step: 3 steps inside one call
+    host = [a.copy() for a in soa]
+    with bh.BHEngine(n) as eng:
+        eng.step_host(*host, nsteps=3)
+        for k in range(6):
+            assert host[k].tobytes() == want_soa[k].tobytes()
+        eng.step_host(*[a.copy() for a in soa], nsteps=1)     # a second call on the same context (graphs reused)
+        eng.check_device_error()
+
+
 def test_soa_and_visual_exports_skip_slots_without_a_local_id(bh):
     """contexts filled through bh_import_state may hold ghosts (id -1) and global ids >= n; the SoA and
     vertex-buffer exports index the caller's n-element arrays by id and must leave those slots alone."""
