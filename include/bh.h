@@ -59,6 +59,11 @@ typedef struct bh_params {
 
 #define BH_FLAG_NO_GRAPH    1  /* launch kernels directly instead of a CUDA graph  */
 #define BH_FLAG_PHASE_TIMER 2  /* record per-phase cudaEvents (implies NO_GRAPH)   */
+#define BH_FLAG_QUADRUPOLE  4  /* accepted cells act with their traceless quadrupole as well (set before bh_create).
+                                * The reference has monopoles only (nbody_v5_bench.cu:205-213) and that stays the
+                                * default; this is an accuracy / throughput knob: the same acceptance test, a 3-6x
+                                * smaller error, so a larger theta reaches the monopole accuracy with fewer
+                                * interactions.  Not available in the locally-essential-tree calls.            */
 
 typedef struct bh_ctx bh_ctx;
 
@@ -158,6 +163,8 @@ enum {
     BH_DBG_IDS_SORTED,   /* i32[n]     matching original ids                */
     BH_DBG_KEYS64,       /* u64[n]     key_bits = 60 only: sorted 60-bit keys
                             (reference key << 30 | low word)                */
+    BH_DBG_CELL_QUAD,    /* float[cells*8] BH_FLAG_QUADRUPOLE only: xx,xy,xz,yy,yz,zz,0,0 per cell (traceless, about
+                            the centre of mass)                                                   */
     BH_DBG_COUNT
 };
 int  bh_debug_get(bh_ctx* ctx, int what, void* dst, size_t bytes);

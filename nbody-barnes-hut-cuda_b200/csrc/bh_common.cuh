@@ -131,12 +131,17 @@ int bh_tree_launch(const void* keys, int levels, int64_t n, int2* pair_info, int
 // each child contributes when its parent is opened (a loose body's {x,y,z,m}, a child cell's {com,mass}) and
 // {stack word of a child cell = id << 3 | its child count - 1 | BH_KID_BUCKET, squared width as float bits}.
 size_t bh_com_scratch_bytes(int64_t n);
-// the two halves of bh_com_launch: prefix sums over the sorted bodies (independent of the tree), then one thread per cell
-int bh_com_prefix_launch(const float4* posm, int64_t n, void* com_scratch, cudaStream_t st);
-int bh_com_cells_launch(const float4* posm, int64_t n, const int4* cell_meta, const int32_t* cell_child, void* com_scratch,
-                        float4* cell_com, float4* kid_src, uint2* kid_info, BhDevScalars* sc, cudaStream_t st);
+size_t bh_quad_scratch_bytes(int64_t n);   // second moments (quadrupole option)
+// quad_scratch / cell_quad / kid_quad: nullptr without BH_FLAG_QUADRUPOLE.  cell_quad: 2 float4 per cell {xx,xy,xz,yy},
+// {yz,zz,0,0} (traceless, about the centre of mass); kid_quad: the same per dense child entry (index as kid_src).
 int bh_com_launch(const float4* posm, int64_t n, const int4* cell_meta, const int32_t* cell_child, void* com_scratch,
-                  float4* cell_com, float4* kid_src, uint2* kid_info, BhDevScalars* sc, cudaStream_t st);
+                  float4* cell_com, float4* kid_src, uint2* kid_info, BhDevScalars* sc, void* quad_scratch, float4* cell_quad,
+                  float4* kid_quad, cudaStream_t st);
+// the two halves of bh_com_launch: prefix sums over the sorted bodies (independent of the tree), then one thread per cell
+int bh_com_prefix_launch(const float4* posm, int64_t n, void* com_scratch, void* quad_scratch, const BhDevScalars* sc, cudaStream_t st);
+int bh_com_cells_launch(const float4* posm, int64_t n, const int4* cell_meta, const int32_t* cell_child, void* com_scratch,
+                        float4* cell_com, float4* kid_src, uint2* kid_info, BhDevScalars* sc, void* quad_scratch,
+                        float4* cell_quad, float4* kid_quad, cudaStream_t st);
 // heavy_list, heavy_flag: 2 * max_chunks u32 each (see BhDevScalars::epoch)
 // ids: nullptr, or per-body ids where id < 0 marks a ghost (a source whose own acceleration is not wanted)
 int bh_force_launch(const float4* posm, const void* keys, int levels, const int32_t* ids, int64_t n, int64_t first_body,
@@ -146,7 +151,9 @@ int bh_force_launch(const float4* posm, const void* keys, int levels, const int3
                     float theta, float softening, float G, float split_alpha, int num_sms,
                     // cross-tree pass: the tree (scalars, cells, the bodies its buckets index) of ANOTHER body set;
                     // nullptr/nullptr/0 = the ordinary pass over the bodies' own tree
-                    const float4* src_posm, const BhDevScalars* tree_sc, int accumulate, cudaStream_t st);
+                    const float4* src_posm, const BhDevScalars* tree_sc, int accumulate,
+                    // quadrupole option: per-cell and per-child-entry moments (bh_com_launch); nullptr = monopoles only
+                    const float4* cell_quad, const float4* kid_quad, cudaStream_t st);
 int bh_force_prepare();
 int bh_integrate_launch(const float4* posm_s, const float4* vel_s, const int32_t* ids_s, const float4* acc,
                         float4* posm, float4* vel, int32_t* ids, int64_t first_body, int64_t body_count,

@@ -56,6 +56,10 @@ struct bh_ctx {
     int32_t* cell_child = nullptr;
     float4* cell_com = nullptr;
     void* com_scratch = nullptr;   // prefix sums of the centre-of-mass pass (bh_com_scratch_bytes)
+    // BH_FLAG_QUADRUPOLE only: second-moment prefix sums, per-cell quadrupoles, and their copy in the dense child lines
+    bool quad = false;
+    void* quad_scratch = nullptr;
+    float4 *cell_quad = nullptr, *kid_quad = nullptr;
     float4* kid_src = nullptr;   // 8 per cell
     uint8_t* kid_lv = nullptr;   // 8 per cell (digit-indexed)
     uint2* kid_info = nullptr;   // 8 per cell (dense, pairs with kid_src)
@@ -111,7 +115,7 @@ void free_all(bh_ctx* c) {
     if (c->ev_h2d_mass) cudaEventDestroy(c->ev_h2d_mass);
     void* ptrs[] = {c->posm, c->vel, c->posm_s, c->vel_s, c->acc, c->ids, c->ids_s, c->keys0, c->keys1, c->vals0,
                     c->vals1, c->sort_tmp, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
-                    c->com_scratch, c->cell_com, c->sc, c->stage, c->d_scratch, c->heavy_list, c->heavy_flag, c->kid_src, c->kid_lv, c->kid_info, c->let_boxes, c->let_counts, c->let_queue, c->klo, c->kaux, c->keys64};
+                    c->com_scratch, c->cell_com, c->sc, c->stage, c->d_scratch, c->heavy_list, c->heavy_flag, c->kid_src, c->kid_lv, c->kid_info, c->quad_scratch, c->cell_quad, c->kid_quad, c->let_boxes, c->let_counts, c->let_queue, c->klo, c->kaux, c->keys64};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
 
@@ -212,14 +216,15 @@ int phase_build(bh_ctx* c, cudaStream_t st) {
 }
 
 int phase_com(bh_ctx* c, cudaStream_t st) {
-    return bh_com_launch(c->posm_s, c->n, c->cell_meta, c->cell_child, c->com_scratch, c->cell_com, c->kid_src, c->kid_info, c->sc, st);
+    return bh_com_launch(c->posm_s, c->n, c->cell_meta, c->cell_child, c->com_scratch, c->cell_com, c->kid_src, c->kid_info, c->sc, c->quad_scratch,
+                         c->cell_quad, c->kid_quad, st);
 }
 
 int phase_force(bh_ctx* c, cudaStream_t st) {
     return bh_force_launch(c->posm_s, c->levels == 20 ? (const void*)c->keys64 : (const void*)c->keys0, c->levels,
                            c->may_have_ghosts ? c->ids_s : nullptr, c->n, c->slice_first, c->slice_count, c->cell_meta,
                            c->cell_com, c->kid_src, c->kid_info, c->acc, c->sc, c->heavy_list, c->heavy_flag, c->max_chunks, c->prm.theta,
-                           c->prm.softening, c->prm.G, c->prm.group_split, c->num_sms, nullptr, nullptr, 0, st);
+                           c->prm.softening, c->prm.G, c->prm.group_split, c->num_sms, nullptr, nullptr, 0, c->cell_quad, c->kid_quad, st);
 }
 
 int phase_update(bh_ctx* c, cudaStream_t st) {
@@ -236,12 +241,13 @@ const phase_fn kPhases[BH_PHASE_TOTAL] = {phase_keys, phase_sort, phase_build, p
 int launch_tail_overlapped(bh_ctx* c, cudaStream_t st) {
     BH_CUDA_TRY(cudaEventRecord(c->ev_fork, st));
     BH_CUDA_TRY(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
-    int e = bh_com_prefix_launch(c->posm_s, c->n, c->com_scratch, c->aux_stream);
+    int e = bh_com_prefix_launch(c->posm_s, c->n, c->com_scratch, c->quad_scratch, c->sc, c->aux_stream);
     if (!e) e = phase_build(c, st);
     BH_CUDA_TRY(cudaEventRecord(c->ev_join, c->aux_stream));   // always join, also on error (an open fork breaks a capture)
     BH_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));
     if (e) return e;
-    e = bh_com_cells_launch(c->posm_s, c->n, c->cell_meta, c->cell_child, c->com_scratch, c->cell_com, c->kid_src, c->kid_info, c->sc, st);
+    e = bh_com_cells_launch(c->posm_s, c->n, c->cell_meta, c->cell_child, c->com_scratch, c->cell_com, c->kid_src, c->kid_info, c->sc,
+                            c->quad_scratch, c->cell_quad, c->kid_quad, st);
     if (!e) e = phase_force(c, st);
     if (!e) e = phase_update(c, st);
     return e;
@@ -269,12 +275,13 @@ int launch_part(bh_ctx* c, int part, cudaStream_t st) {
         if (e) return e;
         BH_CUDA_TRY(cudaEventRecord(c->ev_fork, st));
         BH_CUDA_TRY(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
-        e = bh_com_prefix_launch(c->posm_s, c->n, c->com_scratch, c->aux_stream);
+        e = bh_com_prefix_launch(c->posm_s, c->n, c->com_scratch, c->quad_scratch, c->sc, c->aux_stream);
         if (!e) e = phase_build(c, st);
         BH_CUDA_TRY(cudaEventRecord(c->ev_join, c->aux_stream));
         BH_CUDA_TRY(cudaStreamWaitEvent(st, c->ev_join, 0));
         if (e) return e;
-        e = bh_com_cells_launch(c->posm_s, c->n, c->cell_meta, c->cell_child, c->com_scratch, c->cell_com, c->kid_src, c->kid_info, c->sc, st);
+        e = bh_com_cells_launch(c->posm_s, c->n, c->cell_meta, c->cell_child, c->com_scratch, c->cell_com, c->kid_src, c->kid_info, c->sc,
+                            c->quad_scratch, c->cell_quad, c->kid_quad, st);
         if (!e) e = phase_force(c, st);
         return e;
     }
@@ -396,6 +403,11 @@ int bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device) 
     TRYA(dev_alloc(&c->pair_info, na)); TRYA(dev_alloc(&c->pair_scan, na)); TRYA(dev_alloc(&c->tile_sums, na / 2048 + 16));
     TRYA(dev_alloc(&c->cell_meta, na)); TRYA(dev_alloc(&c->cell_child, na * 8));
     TRYA(dev_alloc(&c->cell_com, na)); TRYA(cudaMalloc(&c->com_scratch, bh_com_scratch_bytes(c->n_alloc)));
+    c->quad = (prm.flags & BH_FLAG_QUADRUPOLE) != 0;
+    if (c->quad) {
+        TRYA(cudaMalloc(&c->quad_scratch, bh_quad_scratch_bytes(c->n_alloc)));
+        TRYA(dev_alloc(&c->cell_quad, na * 2)); TRYA(dev_alloc(&c->kid_quad, na * 16));
+    }
     TRYA(dev_alloc(&c->kid_src, na * 8)); TRYA(dev_alloc(&c->kid_lv, na * 8)); TRYA(dev_alloc(&c->kid_info, na * 8));
     TRYA(dev_alloc(&c->sc, 1)); TRYA(dev_alloc(&c->d_scratch, 8));
     c->max_chunks = (int64_t)(na / BH_GROUP + 1);
@@ -585,6 +597,7 @@ int bh_force_from(bh_ctx* c, bh_ctx* src, void* stream) {
     if (!c || !src || c == src) return BH_E_INVAL;
     if (!c->have_state || !c->have_sorted || !src->have_state || !src->have_sorted) return BH_E_STATE;
     if (c->device != src->device || c->levels != src->levels) return BH_E_INVAL;
+    if (c->quad || src->quad) return BH_E_UNSUPPORTED;   // exported points carry monopoles only
     if (!c->fixed_bounds_set || !src->fixed_bounds_set || memcmp(c->fixed_bounds, src->fixed_bounds, sizeof(c->fixed_bounds)) != 0)
         return BH_E_STATE;   // cell widths are derived from the cube: both trees must live on the same grid
     BH_CUDA_TRY(cudaSetDevice(c->device));
@@ -592,7 +605,7 @@ int bh_force_from(bh_ctx* c, bh_ctx* src, void* stream) {
     return bh_force_launch(c->posm_s, c->levels == 20 ? (const void*)c->keys64 : (const void*)c->keys0, c->levels, c->ids_s, c->n,
                            c->slice_first, c->slice_count, src->cell_meta, src->cell_com, src->kid_src,
                            src->kid_info, c->acc, c->sc, c->heavy_list, c->heavy_flag, c->max_chunks, c->prm.theta,
-                           c->prm.softening, c->prm.G, c->prm.group_split, c->num_sms, src->posm_s, src->sc, 1,
+                           c->prm.softening, c->prm.G, c->prm.group_split, c->num_sms, src->posm_s, src->sc, 1, nullptr, nullptr,
                            (cudaStream_t)stream);
 }
 
@@ -619,6 +632,7 @@ int bh_let_export(bh_ctx* c, const float* boxes_lohi, int npeers, int K, void* o
         cap_per_peer < 1)
         return BH_E_INVAL;
     if (!c->have_state || !c->have_sorted) return BH_E_STATE;
+    if (c->quad) return BH_E_UNSUPPORTED;   // the export emits {centre of mass, mass} points
     BH_CUDA_TRY(cudaSetDevice(c->device));
     cudaStream_t st = (cudaStream_t)stream;
     { int e0 = let_scratch(c); if (e0) return e0; }
@@ -790,7 +804,7 @@ int bh_run_phase(bh_ctx* c, int phase, void* stream) {
 
 int bh_set_flags(bh_ctx* c, int flags) {
     if (!c) return BH_E_INVAL;
-    c->prm.flags = flags;
+    c->prm.flags = (flags & ~BH_FLAG_QUADRUPOLE) | (c->quad ? BH_FLAG_QUADRUPOLE : 0);   // the moment arrays are allocated at creation
     return 0;
 }
 
@@ -894,7 +908,7 @@ int bh_step_host(bh_ctx* c, float* px, float* py, float* pz, float* vx, float* v
 static int dbg_locate(bh_ctx* c, int what, void** ptr, size_t* bytes) {
     BhDevScalars h;
     int M = 0;
-    if (what == BH_DBG_CELL_META || what == BH_DBG_CELL_COM || what == BH_DBG_CELL_CHILD) {
+    if (what == BH_DBG_CELL_META || what == BH_DBG_CELL_COM || what == BH_DBG_CELL_CHILD || what == BH_DBG_CELL_QUAD) {
         BH_CUDA_TRY(cudaMemcpy(&h, c->sc, sizeof(h), cudaMemcpyDeviceToHost));
         M = h.num_cells;
     }
@@ -913,6 +927,9 @@ static int dbg_locate(bh_ctx* c, int what, void** ptr, size_t* bytes) {
         case BH_DBG_CELL_META: *ptr = c->cell_meta; *bytes = (size_t)M * 16; break;
         case BH_DBG_CELL_COM: *ptr = c->cell_com; *bytes = (size_t)M * 16; break;
         case BH_DBG_CELL_CHILD: *ptr = c->cell_child; *bytes = (size_t)M * 32; break;
+        case BH_DBG_CELL_QUAD:
+            if (!c->quad) return BH_E_UNSUPPORTED;
+            *ptr = c->cell_quad; *bytes = (size_t)M * 32; break;
         case BH_DBG_POSM_SORTED: *ptr = c->posm_s; *bytes = n * 16; break;
         case BH_DBG_VEL_SORTED: *ptr = c->vel_s; *bytes = n * 16; break;
         case BH_DBG_IDS_SORTED: *ptr = c->ids_s; *bytes = n * 4; break;

@@ -74,9 +74,11 @@ constexpr int SRC_CAP = 32 + ROUND_ITEMS + 32;   // pending sources: < 32 left o
 static_assert((SRC_CAP & (SRC_CAP - 1)) == 0, "the pending list is a ring of whole tiles");
 constexpr unsigned LOOP_GUARD = 1u << 24;
 
-struct __align__(16) WarpScratch {
+constexpr int Q_CAP = 128;       // quadrupole option: pending CELL sources (3 float4 each), a ring of whole tiles like SRC_CAP
+template <bool QUAD> struct __align__(16) WarpScratchT {
     float4 src[SRC_CAP];       // pending sources, stored as PAIRS (see SrcPair)
     unsigned stack[STACK_CAP]; // cells waiting to be opened: id << 3 | children - 1
+    float4 qsrc[QUAD ? Q_CAP * 3 : 1];   // {com, mass}, {Qxx, Qxy, Qxz, Qyy}, {Qyz, Qzz, -, -}
 };
 
 // r2 >= SOFTENING > 0, never denormal: the flush-to-zero form is a bare MUFU.RSQ (the default
@@ -174,18 +176,42 @@ __device__ __forceinline__ void eval_tile(const SrcPair* __restrict__ src, f32x2
     }
 }
 
-template <int LEVELS>
+// 32 accepted cells with quadrupoles against this lane's body (BH_FLAG_QUADRUPOLE):
+//   a += M d / R^3 - Q d / R^5 + 5/2 (d.Q.d) d / R^7,   d = c - p,  R^2 = d^2 + soft     (G is applied at the end)
+// The reference evaluates the first term only (bench:205-213).  Scalar FP32: this path is the accuracy knob, the
+// packed monopole tile above stays the default.
+__device__ __forceinline__ void eval_qtile(const float4* __restrict__ q, float px, float py, float pz, float soft, float& ax,
+                                           float& ay, float& az) {
+#pragma unroll 2
+    for (int k = 0; k < 32; ++k) {
+        const float4 c = q[3 * k], a = q[3 * k + 1], b = q[3 * k + 2];   // uniform addresses: LDS.128 broadcasts
+        const float dx = c.x - px, dy = c.y - py, dz = c.z - pz;
+        const float r2 = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, soft)));
+        const float rinv = rsqrt_fast(r2);
+        const float i2 = rinv * rinv, i3 = rinv * i2, i5 = i3 * i2, i7 = i5 * i2;
+        const float qx = fmaf(a.z, dz, fmaf(a.y, dy, a.x * dx));      // Q d: xx xy xz / xy yy yz / xz yz zz
+        const float qy = fmaf(b.x, dz, fmaf(a.w, dy, a.y * dx));
+        const float qz = fmaf(b.y, dz, fmaf(b.x, dy, a.z * dx));
+        const float dqd = fmaf(dz, qz, fmaf(dy, qy, dx * qx));
+        const float s = fmaf(2.5f * dqd, i7, c.w * i3);
+        ax += fmaf(s, dx, -i5 * qx);
+        ay += fmaf(s, dy, -i5 * qy);
+        az += fmaf(s, dz, -i5 * qz);
+    }
+}
+
+template <int LEVELS, bool QUAD>
 __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
     const float4* __restrict__ posm, const typename BhKey<LEVELS>::type* __restrict__ keys, const int32_t* __restrict__ ids,
     int64_t first_body, int64_t body_count, const int4* __restrict__ cell_meta, const float4* __restrict__ cell_com,
     const float4* __restrict__ kid_src, const uint2* __restrict__ kid_info, float4* __restrict__ acc, BhDevScalars* sc,
     uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_flag, int64_t max_chunks, float theta, float soft,
     float G, float split_alpha, const float4* __restrict__ src_posm, const BhDevScalars* __restrict__ tree_sc,
-    int accumulate) {
-    __shared__ WarpScratch s_warp[FORCE_WARPS];
+    int accumulate, const float4* __restrict__ cell_quad, const float4* __restrict__ kid_quad) {
+    __shared__ WarpScratchT<QUAD> s_warp[FORCE_WARPS];
 
     const int lane = bh_lane();
-    WarpScratch& W = s_warp[threadIdx.x >> 5];
+    WarpScratchT<QUAD>& W = s_warp[threadIdx.x >> 5];
     SrcPair* const slist = reinterpret_cast<SrcPair*>(W.src);
     const float theta2 = __fmul_rn(theta, theta);
     const int root = tree_sc->root;
@@ -314,12 +340,21 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
 
         // pending sources live in a ring of SRC_CAP / 32 tiles: [head, head + ns); head stays a multiple of 32
         int head = 0;
+        int qhead = 0, nq = 0;                    // quadrupole option: the same for accepted cells
+        float qax = 0.f, qay = 0.f, qaz = 0.f;
         // evaluate every full tile of 32 pending sources
         auto drain = [&]() {
             while (ns >= 32) {
                 eval_tile(slist + (head >> 1), npx, npy, npz, soft2, t);
                 head = (head + 32) & (SRC_CAP - 1);
                 ns -= 32;
+            }
+            if (QUAD) {
+                while (nq >= 32) {
+                    eval_qtile(W.qsrc + 3 * qhead, me.x, me.y, me.z, soft, qax, qay, qaz);
+                    qhead = (qhead + 32) & (Q_CAP - 1);
+                    nq -= 32;
+                }
             }
         };
         // append the bodies [bfirst, bfirst+bcount) of a rejected bucket
@@ -339,8 +374,16 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
             const float4 rcm = __ldg(cell_com + root);
             const int4 rmt = __ldg(cell_meta + root);
             if (accepts(rcm, __int_as_float(root_w2_bits - ((rmt.z & 0xFF) << 24)))) {
-                if (lane == 0) { store_source(slist, 0, rcm); my_cells = 1; }   // head = 0, ns = 0
-                ns = 1;
+                if (QUAD) {
+                    if (lane == 0) {
+                        W.qsrc[0] = rcm; W.qsrc[1] = __ldg(cell_quad + 2 * (size_t)root); W.qsrc[2] = __ldg(cell_quad + 2 * (size_t)root + 1);
+                        my_cells = 1;
+                    }
+                    nq = 1;
+                } else {
+                    if (lane == 0) { store_source(slist, 0, rcm); my_cells = 1; }   // head = 0, ns = 0
+                    ns = 1;
+                }
             } else if ((rmt.z >> 8) & 1) {
                 append_bucket(rmt.x, rmt.y);
             } else {
@@ -380,6 +423,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
             float4 s[ITEMS];
             uint2 w[ITEMS];
             bool has[ITEMS];
+            unsigned item[ITEMS];
             int before = 0;
 #pragma unroll
             for (int j = 0; j < ITEMS; ++j) {
@@ -388,6 +432,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
                 const int owner = before + __popc(starts[j] & le_mask) - 1;
                 before += __popc(starts[j]);
                 const unsigned idx = __shfl_sync(0xffffffffu, base, owner & 31) + (unsigned)k;
+                item[j] = idx;
                 if (has[j]) {
                     s[j] = __ldg(kid_src + idx);
                     w[j] = __ldg(kid_info + idx);
@@ -402,7 +447,7 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
             for (int j = 0; j < ITEMS; ++j) {
                 const bool body = has[j] && (int)w[j].y < 0;
                 const bool ok = has[j] && accepts(s[j], __uint_as_float(w[j].y));
-                is_src[j] = ok;
+                is_src[j] = QUAD ? body : ok;              // quadrupole option: accepted CELLS go to their own list
                 is_bucket[j] = has[j] && !ok && (w[j].x & BH_KID_BUCKET);
                 is_push[j] = has[j] && !ok && !(w[j].x & BH_KID_BUCKET);
                 my_bodies += body;
@@ -412,6 +457,20 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
                 m_bucket |= __ballot_sync(0xffffffffu, is_bucket[j]);
             }
             if (sp + T > STACK_CAP) { if (lane == 0) atomicOr(&sc->err, BH_DERR_STACK); break; }   // unreachable by construction
+            if (QUAD) {
+#pragma unroll
+                for (int j = 0; j < ITEMS; ++j) {
+                    const bool qcell = has[j] && (int)w[j].y >= 0 && !is_push[j] && !is_bucket[j];   // an accepted cell
+                    const unsigned mq = __ballot_sync(0xffffffffu, qcell);
+                    if (qcell) {
+                        const int slot = (qhead + nq + __popc(mq & lt_mask)) & (Q_CAP - 1);
+                        W.qsrc[3 * slot] = s[j];
+                        W.qsrc[3 * slot + 1] = __ldg(kid_quad + 2 * (size_t)item[j]);
+                        W.qsrc[3 * slot + 2] = __ldg(kid_quad + 2 * (size_t)item[j] + 1);
+                    }
+                    nq += __popc(mq);
+                }
+            }
 #pragma unroll
             for (int j = 0; j < ITEMS; ++j) {
                 if (is_src[j]) store_source(slist, (head + ns + __popc(m_src[j] & lt_mask)) & (SRC_CAP - 1), s[j]);
@@ -449,11 +508,22 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
             __syncwarp();
         }
 
+        if (QUAD && nq > 0) {   // the last partial tile of cells: zero mass and zero moments add exactly 0
+            if (lane >= nq) {
+                const int slot = (qhead + lane) & (Q_CAP - 1);
+                W.qsrc[3 * slot] = make_float4(0.f, 0.f, 0.f, 0.f);
+                W.qsrc[3 * slot + 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+                W.qsrc[3 * slot + 2] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            __syncwarp();
+            eval_qtile(W.qsrc + 3 * qhead, me.x, me.y, me.z, soft, qax, qay, qaz);
+            __syncwarp();
+        }
         if (in_group) {
             float lo, hi;
-            unpack2(t.x, lo, hi); ax = lo + hi;
-            unpack2(t.y, lo, hi); ay = lo + hi;
-            unpack2(t.z, lo, hi); az = lo + hi;
+            unpack2(t.x, lo, hi); ax = lo + hi + qax;
+            unpack2(t.y, lo, hi); ay = lo + hi + qay;
+            unpack2(t.z, lo, hi); az = lo + hi + qaz;
         }
         acc_cells_w += acc_cells * gsize;
         dir_bodies_w += dir_bodies * gsize;
@@ -512,16 +582,21 @@ __global__ void __launch_bounds__(256) zero_acc_kernel(float4* acc, int64_t firs
 
 }  // namespace
 
-static int g_force_ctas_per_sm = 0;
+static int g_force_ctas_per_sm = 0, g_force_ctas_per_sm_quad = 0;
 // occupancy query done once, outside any stream capture
 int bh_force_prepare() {
     if (g_force_ctas_per_sm > 0) return 0;
     int a = 0, b = 0;
-    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, force_kernel<10>, FORCE_THREADS, 0);
-    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, force_kernel<20>, FORCE_THREADS, 0);
+    cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, force_kernel<10, false>, FORCE_THREADS, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, force_kernel<20, false>, FORCE_THREADS, 0);
     if (e != cudaSuccess) return (int)e;
     const int max_ctas = a < b ? a : b;
     g_force_ctas_per_sm = max_ctas < 1 ? 1 : max_ctas;
+    a = b = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, force_kernel<10, true>, FORCE_THREADS, 0);
+    if (e == cudaSuccess) e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, force_kernel<20, true>, FORCE_THREADS, 0);
+    if (e != cudaSuccess) return (int)e;
+    g_force_ctas_per_sm_quad = (a < b ? a : b) < 1 ? 1 : (a < b ? a : b);
     return 0;
 }
 
@@ -530,7 +605,8 @@ int bh_force_launch(const float4* posm, const void* keys, int levels, const int3
                     const float4* kid_src, const uint2* kid_info,
                     float4* acc, BhDevScalars* sc, uint32_t* heavy_list, uint32_t* heavy_flag, int64_t max_chunks,
                     float theta, float softening, float G, float split_alpha, int num_sms, const float4* src_posm,
-                    const BhDevScalars* tree_sc, int accumulate, cudaStream_t st) {
+                    const BhDevScalars* tree_sc, int accumulate, const float4* cell_quad, const float4* kid_quad,
+                    cudaStream_t st) {
     if (body_count <= 0) return 0;
     if (!src_posm) src_posm = posm;
     if (!tree_sc) tree_sc = sc;
@@ -544,20 +620,16 @@ int bh_force_launch(const float4* posm, const void* keys, int levels, const int3
         return (int)cudaGetLastError();
     }
     { int e = bh_force_prepare(); if (e) return e; }
-    const int max_ctas = g_force_ctas_per_sm;
+    const bool quad = cell_quad != nullptr && kid_quad != nullptr;
+    const int max_ctas = quad ? g_force_ctas_per_sm_quad : g_force_ctas_per_sm;
     const int64_t ngroups = (body_count + BH_GROUP - 1) / BH_GROUP;
     int64_t want = (ngroups + FORCE_WARPS - 1) / FORCE_WARPS;
     int64_t grid = (int64_t)(num_sms > 0 ? num_sms : BH_NUM_SMS_FALLBACK) * max_ctas;  // persistent: fill the chip once
     if (grid > want) grid = want;
-    if (levels == 20)
-        force_kernel<20><<<(int)grid, FORCE_THREADS, 0, st>>>(posm, (const uint64_t*)keys, ids, first_body, body_count, cell_meta,
-                                                             cell_com, kid_src, kid_info, acc, sc, heavy_list,
-                                                             heavy_flag, max_chunks, theta, softening, G, split_alpha, src_posm, tree_sc,
-                                                             accumulate);
-    else
-        force_kernel<10><<<(int)grid, FORCE_THREADS, 0, st>>>(posm, (const uint32_t*)keys, ids, first_body, body_count, cell_meta,
-                                                             cell_com, kid_src, kid_info, acc, sc, heavy_list,
-                                                             heavy_flag, max_chunks, theta, softening, G, split_alpha, src_posm, tree_sc,
-                                                             accumulate);
+#define BH_FORCE(L, Q, KT) force_kernel<L, Q><<<(int)grid, FORCE_THREADS, 0, st>>>(posm, (const KT*)keys, ids, first_body, body_count, cell_meta, \
+        cell_com, kid_src, kid_info, acc, sc, heavy_list, heavy_flag, max_chunks, theta, softening, G, split_alpha, src_posm, tree_sc, accumulate, cell_quad, kid_quad)
+    if (levels == 20) { if (quad) BH_FORCE(20, true, uint64_t); else BH_FORCE(20, false, uint64_t); }
+    else { if (quad) BH_FORCE(10, true, uint32_t); else BH_FORCE(10, false, uint32_t); }
+#undef BH_FORCE
     return (int)cudaGetLastError();
 }

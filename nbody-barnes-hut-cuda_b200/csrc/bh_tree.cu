@@ -360,10 +360,103 @@ __global__ void __launch_bounds__(1024) com_base_kernel(const D4* __restrict__ t
     if (threadIdx.x == 0) base[nblocks] = s_carry;
 }
 
+// ---- second moments for the quadrupole option (bh_params.flags & BH_FLAG_QUADRUPOLE) -------------------------
+// The same prefix-sum construction with six running sums per body: m x'x', m x'y', m x'z', m y'y', m y'z', m z'z',
+// x' = x - o with o the centre of the key cube (keeps the sums small; the shift is undone exactly in com_cells_kernel).
+// The reference has monopoles only (bench:205-213); this is the accuracy knob of SURVEY §8f N4.
+struct __align__(16) D6 { double v[6]; };
+__device__ __forceinline__ D6 d6_zero() { D6 r; for (int k = 0; k < 6; ++k) r.v[k] = 0.0; return r; }
+__device__ __forceinline__ D6 d6_add(const D6& a, const D6& b) { D6 r; for (int k = 0; k < 6; ++k) r.v[k] = __dadd_rn(a.v[k], b.v[k]); return r; }
+__device__ __forceinline__ D6 d6_sub(const D6& a, const D6& b) { D6 r; for (int k = 0; k < 6; ++k) r.v[k] = __dsub_rn(a.v[k], b.v[k]); return r; }
+__device__ __forceinline__ D6 d6_shfl_up(const D6& a, int o) { D6 r; for (int k = 0; k < 6; ++k) r.v[k] = __shfl_up_sync(0xffffffffu, a.v[k], o); return r; }
+__device__ __forceinline__ D6 d6_term(const float4 p, double ox, double oy, double oz) {
+    const double m = (double)p.w, x = (double)p.x - ox, y = (double)p.y - oy, z = (double)p.z - oz;
+    D6 r;
+    r.v[0] = m * x * x; r.v[1] = m * x * y; r.v[2] = m * x * z; r.v[3] = m * y * y; r.v[4] = m * y * z; r.v[5] = m * z * z;
+    return r;
+}
+template <int NW>
+__device__ __forceinline__ D6 d6_block_exclusive(const D6 v, D6* s_w, D6& total) {
+    const int lane = bh_lane(), warp = threadIdx.x >> 5;
+    D6 incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const D6 u = d6_shfl_up(incl, o);
+        if (lane >= o) incl = d6_add(incl, u);
+    }
+    D6 prev = d6_shfl_up(incl, 1);
+    if (lane == 0) prev = d6_zero();
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    D6 before = d6_zero(), all = d6_zero();
+#pragma unroll 1
+    for (int w = 0; w < NW; ++w) {
+        if (w == warp) before = all;
+        all = d6_add(all, s_w[w]);
+    }
+    total = all;
+    __syncthreads();
+    return d6_add(before, prev);
+}
+
+__device__ __forceinline__ void cube_centre(const BhDevScalars* sc, double& ox, double& oy, double& oz) {
+    const float half = __fmul_rn(0.5f, fmaxf(__fsub_rn(sc->bounds[3], sc->bounds[0]), 1.0f));
+    ox = (double)__fadd_rn(sc->bounds[0], half); oy = (double)__fadd_rn(sc->bounds[1], half); oz = (double)__fadd_rn(sc->bounds[2], half);
+}
+
+__global__ void __launch_bounds__(CT) quad_scan_kernel(const float4* __restrict__ posm, int n, const BhDevScalars* __restrict__ sc,
+                                                      D6* __restrict__ local, D6* __restrict__ totals) {
+    __shared__ D6 s_w[CT / 32];
+    double ox, oy, oz;
+    cube_centre(sc, ox, oy, oz);
+    const int i0 = blockIdx.x * CB + threadIdx.x * CPT;
+    D6 sum = d6_zero();
+#pragma unroll 2
+    for (int k = 0; k < CPT; ++k)
+        if (i0 + k < n) sum = d6_add(sum, d6_term(__ldg(posm + i0 + k), ox, oy, oz));
+    D6 total;
+    D6 run = d6_block_exclusive<CT / 32>(sum, s_w, total);
+#pragma unroll 2
+    for (int k = 0; k < CPT; ++k) {
+        if (i0 + k <= n) local[i0 + k] = run;
+        if (i0 + k < n) run = d6_add(run, d6_term(__ldg(posm + i0 + k), ox, oy, oz));
+    }
+    if (threadIdx.x == 0) totals[blockIdx.x] = total;
+    if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1 && (blockIdx.x + 1) * CB == n) local[n] = d6_zero();
+}
+
+__global__ void __launch_bounds__(1024) quad_base_kernel(const D6* __restrict__ totals, int nblocks, D6* __restrict__ base) {
+    __shared__ D6 s_w[32];
+    __shared__ D6 s_carry;
+    if (threadIdx.x == 0) s_carry = d6_zero();
+    __syncthreads();
+    for (int c0 = 0; c0 < nblocks; c0 += 1024) {
+        const int b = c0 + threadIdx.x;
+        const D6 v = b < nblocks ? totals[b] : d6_zero();
+        D6 total;
+        const D6 pre = d6_block_exclusive<32>(v, s_w, total);
+        const D6 carry = s_carry;
+        if (b < nblocks) base[b] = d6_add(carry, pre);
+        __syncthreads();
+        if (threadIdx.x == 0) s_carry = d6_add(carry, total);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) base[nblocks] = s_carry;
+}
+
+// what the quadrupole option adds to com_cells_kernel's arguments
+struct QuadArgs {
+    const D6* local2; const D6* base2;
+    float4* cell_quad;   // 2 float4 per cell: {xx, xy, xz, yy}, {yz, zz, 0, 0}
+    float4* kid_quad;    // 2 float4 per dense child entry (same index as kid_src)
+};
+
+template <bool QUAD>
 __global__ void __launch_bounds__(TB) com_cells_kernel(const float4* __restrict__ posm, const int4* __restrict__ cell_meta,
                                                       const int32_t* __restrict__ cell_child, const D4* __restrict__ local,
                                                       const D4* __restrict__ base, float4* __restrict__ com,
-                                                      float4* __restrict__ kid_src, uint2* __restrict__ kid_info, BhDevScalars* sc) {
+                                                      float4* __restrict__ kid_src, uint2* __restrict__ kid_info, BhDevScalars* sc,
+                                                      QuadArgs qa) {
     const int M = sc->num_cells;
     const int4* child4 = reinterpret_cast<const int4*>(cell_child);
     // squared width of a level-L cell: root_w^2 with 2L taken off the exponent (exact); root_w is the key
@@ -378,6 +471,23 @@ __global__ void __launch_bounds__(TB) com_cells_kernel(const float4* __restrict_
         const float inv = (m > 1e-6f) ? __fdiv_rn(1.0f, m) : 0.0f;   // bench:181-183
         const float4 cm = make_float4(__fmul_rn(sx, inv), __fmul_rn(sy, inv), __fmul_rn(sz, inv), m);
         com[c] = cm;
+        float4 q0 = make_float4(0.f, 0.f, 0.f, 0.f), q1 = q0;
+        if (QUAD) {
+            // second moments about the cube centre o -> about the cell's centre of mass (in double: the shift is exact
+            // to 1e-16, the quantities differ by ~1e-4 at worst), then the traceless form Q = 3 P - tr(P) I
+            double ox, oy, oz;
+            cube_centre(sc, ox, oy, oz);
+            const D6 s2 = d6_add(d6_sub(qa.base2[end / CB], qa.base2[first / CB]), d6_sub(qa.local2[end], qa.local2[first]));
+            const double M = s.m, im = M > 0.0 ? 1.0 / M : 0.0;
+            const double cx = s.x * im - ox, cy = s.y * im - oy, cz = s.z * im - oz;
+            const double pxx = s2.v[0] - M * cx * cx, pxy = s2.v[1] - M * cx * cy, pxz = s2.v[2] - M * cx * cz;
+            const double pyy = s2.v[3] - M * cy * cy, pyz = s2.v[4] - M * cy * cz, pzz = s2.v[5] - M * cz * cz;
+            const double tr = pxx + pyy + pzz;
+            q0 = make_float4((float)(3.0 * pxx - tr), (float)(3.0 * pxy), (float)(3.0 * pxz), (float)(3.0 * pyy - tr));
+            q1 = make_float4((float)(3.0 * pyz), (float)(3.0 * pzz - tr), 0.f, 0.f);
+            qa.cell_quad[2 * (size_t)c] = q0;
+            qa.cell_quad[2 * (size_t)c + 1] = q1;
+        }
         const bool bucket = (mt.z >> 8) & 1;
         int nkids = 1;   // buckets are never opened as cells: the field is unused for them
         if (!bucket) {   // the loose bodies of this cell: their entries in its dense line
@@ -407,6 +517,10 @@ __global__ void __launch_bounds__(TB) com_cells_kernel(const float4* __restrict_
         for (int q = 0; q < 8; ++q) rank += (q < myslot && e[q] != BH_CHILD_EMPTY);
         kid_src[(size_t)p * 8 + rank] = cm;
         kid_info[(size_t)p * 8 + rank] = make_uint2(word | (bucket ? BH_KID_BUCKET : 0u), (unsigned)(root_w2_bits - ((mt.z & 0xFF) << 24)));
+        if (QUAD) {
+            qa.kid_quad[2 * ((size_t)p * 8 + rank)] = q0;
+            qa.kid_quad[2 * ((size_t)p * 8 + rank) + 1] = q1;
+        }
     }
 }
 
@@ -444,10 +558,16 @@ size_t bh_com_scratch_bytes(int64_t n) {
     const size_t nblocks = (size_t)((n + CB - 1) / CB) + 1;
     return sizeof(D4) * ((size_t)n + 1 + 2 * nblocks + 4);
 }
+// the same for the six second moments of the quadrupole option
+size_t bh_quad_scratch_bytes(int64_t n) {
+    const size_t nblocks = (size_t)((n + CB - 1) / CB) + 1;
+    return sizeof(D6) * ((size_t)n + 1 + 2 * nblocks + 4);
+}
 
 // The prefix sums need the sorted bodies only: they can run beside the tree construction (bh_com_prefix_launch on
-// another stream); bh_com_cells_launch needs both the tree and the sums.
-int bh_com_prefix_launch(const float4* posm, int64_t n64, void* com_scratch, cudaStream_t st) {
+// another stream); bh_com_cells_launch needs both the tree and the sums.  quad_scratch != nullptr: also the second moments.
+int bh_com_prefix_launch(const float4* posm, int64_t n64, void* com_scratch, void* quad_scratch, const BhDevScalars* sc,
+                         cudaStream_t st) {
     const int n = (int)n64;
     if (n < 2) return 0;
     const int nblocks = (n + CB - 1) / CB;
@@ -456,23 +576,40 @@ int bh_com_prefix_launch(const float4* posm, int64_t n64, void* com_scratch, cud
     D4* base = totals + nblocks + 1;
     com_scan_kernel<<<nblocks, CT, 0, st>>>(posm, n, local, totals);
     com_base_kernel<<<1, 1024, 0, st>>>(totals, nblocks, base);
+    if (quad_scratch) {
+        D6* local2 = reinterpret_cast<D6*>(quad_scratch);
+        D6* totals2 = local2 + (size_t)n + 1;
+        D6* base2 = totals2 + nblocks + 1;
+        quad_scan_kernel<<<nblocks, CT, 0, st>>>(posm, n, sc, local2, totals2);
+        quad_base_kernel<<<1, 1024, 0, st>>>(totals2, nblocks, base2);
+    }
     return (int)cudaGetLastError();
 }
 
 int bh_com_cells_launch(const float4* posm, int64_t n64, const int4* cell_meta, const int32_t* cell_child, void* com_scratch,
-                        float4* cell_com, float4* kid_src, uint2* kid_info, BhDevScalars* sc, cudaStream_t st) {
+                        float4* cell_com, float4* kid_src, uint2* kid_info, BhDevScalars* sc, void* quad_scratch,
+                        float4* cell_quad, float4* kid_quad, cudaStream_t st) {
     const int n = (int)n64;
     if (n < 2) return 0;
     const int nblocks = (n + CB - 1) / CB;
     const D4* local = reinterpret_cast<const D4*>(com_scratch);
     const D4* base = local + (size_t)n + 1 + nblocks + 1;
-    com_cells_kernel<<<capped_grid(n, TB), TB, 0, st>>>(posm, cell_meta, cell_child, local, base, cell_com, kid_src, kid_info, sc);
+    QuadArgs qa{nullptr, nullptr, cell_quad, kid_quad};
+    if (quad_scratch) {
+        qa.local2 = reinterpret_cast<const D6*>(quad_scratch);
+        qa.base2 = qa.local2 + (size_t)n + 1 + nblocks + 1;
+        com_cells_kernel<true><<<capped_grid(n, TB), TB, 0, st>>>(posm, cell_meta, cell_child, local, base, cell_com, kid_src, kid_info, sc, qa);
+    } else {
+        com_cells_kernel<false><<<capped_grid(n, TB), TB, 0, st>>>(posm, cell_meta, cell_child, local, base, cell_com, kid_src, kid_info, sc, qa);
+    }
     return (int)cudaGetLastError();
 }
 
 int bh_com_launch(const float4* posm, int64_t n64, const int4* cell_meta, const int32_t* cell_child, void* com_scratch,
-                  float4* cell_com, float4* kid_src, uint2* kid_info, BhDevScalars* sc, cudaStream_t st) {
-    int e = bh_com_prefix_launch(posm, n64, com_scratch, st);
+                  float4* cell_com, float4* kid_src, uint2* kid_info, BhDevScalars* sc, void* quad_scratch, float4* cell_quad,
+                  float4* kid_quad, cudaStream_t st) {
+    int e = bh_com_prefix_launch(posm, n64, com_scratch, quad_scratch, sc, st);
     if (e) return e;
-    return bh_com_cells_launch(posm, n64, cell_meta, cell_child, com_scratch, cell_com, kid_src, kid_info, sc, st);
+    return bh_com_cells_launch(posm, n64, cell_meta, cell_child, com_scratch, cell_com, kid_src, kid_info, sc, quad_scratch, cell_quad,
+                               kid_quad, st);
 }

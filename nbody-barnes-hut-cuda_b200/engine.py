@@ -41,6 +41,7 @@ class BHParams(C.Structure):
 
 FLAG_NO_GRAPH = 1
 FLAG_PHASE_TIMER = 2
+FLAG_QUADRUPOLE = 4   # accepted cells act with their quadrupole too (set at creation)
 
 
 class PHASE:
@@ -50,7 +51,7 @@ class PHASE:
 
 class DBG:
     (BOUNDS, KEYS, PERM, IDS, POSM, VEL, ACC, CELL_META, CELL_COM, CELL_CHILD,
-     POSM_SORTED, VEL_SORTED, IDS_SORTED, KEYS64) = range(14)
+     POSM_SORTED, VEL_SORTED, IDS_SORTED, KEYS64, CELL_QUAD) = range(15)
 
 
 class STAT:
@@ -397,7 +398,7 @@ class BHEngine:
 
     def debug_get(self, what: int) -> np.ndarray:
         n, M = self.n, None
-        if what in (DBG.CELL_META, DBG.CELL_COM, DBG.CELL_CHILD):
+        if what in (DBG.CELL_META, DBG.CELL_COM, DBG.CELL_CHILD, DBG.CELL_QUAD):
             M = self.stat(STAT.CELLS)
         shapes = {
             DBG.BOUNDS: ((6,), np.float32), DBG.KEYS: ((n,), np.uint32), DBG.PERM: ((n,), np.int32),
@@ -405,6 +406,7 @@ class BHEngine:
             DBG.ACC: ((n, 4), np.float32), DBG.CELL_META: ((M, 4), np.int32), DBG.CELL_COM: ((M, 4), np.float32),
             DBG.CELL_CHILD: ((M, 8), np.int32), DBG.POSM_SORTED: ((n, 4), np.float32),
             DBG.VEL_SORTED: ((n, 4), np.float32), DBG.IDS_SORTED: ((n,), np.int32), DBG.KEYS64: ((n,), np.uint64),
+            DBG.CELL_QUAD: ((M, 8), np.float32),
         }
         shape, dt = shapes[what]
         out = np.zeros(shape, dt)

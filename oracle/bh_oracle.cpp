@@ -585,6 +585,34 @@ extern "C" void orc_tree_com(const float* posm, int64_t n64, const int32_t* meta
     }
 }
 
+// Traceless quadrupole of every cell about its centre of mass, Q_ij = sum m (3 x_i x_j - |x|^2 delta_ij), x = s - c
+// (bh_params.flags & BH_FLAG_QUADRUPOLE; the reference has monopoles only, bench:205-213 — this is the accuracy knob of
+// SURVEY §8f N4).  Straight double sums over the cell's body range: deliberately NOT the kernels' prefix-sum route, so
+// the two check each other.  quad: 6 floats per cell {xx, xy, xz, yy, yz, zz}.
+void orc_tree_quad(const float* posm, const int32_t* meta, int64_t M64, float* quad) {
+    const int M = (int)M64;
+#pragma omp parallel for schedule(dynamic, 64)
+    for (int c = 0; c < M; ++c) {
+        const int first = meta[4 * (int64_t)c], count = meta[4 * (int64_t)c + 1];
+        double m = 0, cx = 0, cy = 0, cz = 0;
+        for (int i = first; i < first + count; ++i) {
+            const float* q = posm + 4 * (int64_t)i;
+            m += q[3]; cx += (double)q[3] * q[0]; cy += (double)q[3] * q[1]; cz += (double)q[3] * q[2];
+        }
+        if (m > 0) { cx /= m; cy /= m; cz /= m; }
+        double xx = 0, xy = 0, xz = 0, yy = 0, yz = 0, zz = 0;
+        for (int i = first; i < first + count; ++i) {
+            const float* q = posm + 4 * (int64_t)i;
+            const double x = q[0] - cx, y = q[1] - cy, z = q[2] - cz, w = q[3];
+            xx += w * x * x; xy += w * x * y; xz += w * x * z; yy += w * y * y; yz += w * y * z; zz += w * z * z;
+        }
+        const double tr = xx + yy + zz;
+        float* o = quad + 6 * (int64_t)c;
+        o[0] = (float)(3 * xx - tr); o[1] = (float)(3 * xy); o[2] = (float)(3 * xz);
+        o[3] = (float)(3 * yy - tr); o[4] = (float)(3 * yz); o[5] = (float)(3 * zz - tr);
+    }
+}
+
 // Force with the GROUP acceptance test (engine: bh_force.cu).
 // Group = `group` Morton-consecutive bodies; box = exact AABB of their positions;
 // d = distance from the cell's centre of mass to that box.  A cell is accepted for the whole
@@ -598,6 +626,11 @@ void orc_force_groups(const float* posm, int64_t n64, const float* bounds,
                       const int32_t* meta, const int32_t* child, const float* com,
                       int64_t M64, int32_t root, const int32_t* gstart, int ngroups, float theta, float soft, float G,
                       float* acc, int64_t* counts, int32_t* group_entries /*nullable: list length per group*/);
+// same with quadrupole corrections of the accepted cells (quad: 6 floats per cell, nullptr = monopoles only)
+void orc_force_groups_quad(const float* posm, int64_t n64, const float* bounds,
+                           const int32_t* meta, const int32_t* child, const float* com, const float* quad,
+                           int64_t M64, int32_t root, const int32_t* gstart, int ngroups, float theta, float soft, float G,
+                           float* acc, int64_t* counts, int32_t* group_entries);
 
 void orc_force_group(const float* posm, int64_t n64, const float* bounds,
                      const int32_t* meta, const int32_t* child, const float* com,
@@ -616,6 +649,14 @@ void orc_force_groups(const float* posm, int64_t n64, const float* bounds,
                       const int32_t* meta, const int32_t* child, const float* com,
                       int64_t M64, int32_t root, const int32_t* gstart, int ngroups, float theta, float soft, float G,
                       float* acc, int64_t* counts, int32_t* group_entries) {
+    orc_force_groups_quad(posm, n64, bounds, meta, child, com, nullptr, M64, root, gstart, ngroups, theta, soft, G, acc, counts,
+                          group_entries);
+}
+
+void orc_force_groups_quad(const float* posm, int64_t n64, const float* bounds,
+                           const int32_t* meta, const int32_t* child, const float* com, const float* quad,
+                           int64_t M64, int32_t root, const int32_t* gstart, int ngroups, float theta, float soft, float G,
+                           float* acc, int64_t* counts, int32_t* group_entries) {
     const int n = (int)n64; (void)n;
     const float root_w = fmaxf(bounds[3] - bounds[0], 1.0f);   // the key grid's size, clamped like bench:52
     const float theta2 = theta * theta;
@@ -646,6 +687,21 @@ void orc_force_groups(const float* posm, int64_t n64, const float* bounds,
                 f[3 * i] += (double)(s * dx); f[3 * i + 1] += (double)(s * dy); f[3 * i + 2] += (double)(s * dz);
             }
         };
+        // an accepted cell with quadrupole Q: a = G [ M d / R^3 - Q d / R^5 + 5/2 (d.Q.d) d / R^7 ], d = c - p, R^2 = d^2 + soft
+        auto interact_quad = [&](const float* cm, const float* Q) {
+            for (int i = 0; i < nb; ++i) {
+                const float* p = posm + 4 * (int64_t)(b0 + i);
+                float dx = cm[0] - p[0], dy = cm[1] - p[1], dz = cm[2] - p[2];
+                float d2 = fmaf(dz, dz, fmaf(dx, dx, dy * dy));
+                float rinv = 1.0f / sqrtf(d2 + soft);
+                float r2 = rinv * rinv, r3 = rinv * r2, r5 = r3 * r2, r7 = r5 * r2;
+                float qx = Q[0] * dx + Q[1] * dy + Q[2] * dz, qy = Q[1] * dx + Q[3] * dy + Q[4] * dz, qz = Q[2] * dx + Q[4] * dy + Q[5] * dz;
+                float dqd = dx * qx + dy * qy + dz * qz;
+                float s = cm[3] * r3 + 2.5f * dqd * r7;
+                f[3 * i] += (double)(G * (s * dx - r5 * qx)); f[3 * i + 1] += (double)(G * (s * dy - r5 * qy));
+                f[3 * i + 2] += (double)(G * (s * dz - r5 * qz));
+            }
+        };
         std::vector<int> stack;
         int64_t entries = 0;
         if (root >= 0) stack.push_back(root);
@@ -661,7 +717,8 @@ void orc_force_groups(const float* posm, int64_t n64, const float* bounds,
             float dz = fmaxf(0.0f, fabsf(cm[2] - ctr[2]) - half[2]);
             float d2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
             if (w2[L] < theta2 * (d2 + soft)) {
-                interact(cm[0], cm[1], cm[2], cm[3]);
+                if (quad) interact_quad(cm, quad + 6 * (int64_t)c);
+                else interact(cm[0], cm[1], cm[2], cm[3]);
                 ncell += nb; ++entries;
             } else if (bucket) {
                 for (int j = mt[0]; j < mt[0] + mt[1]; ++j) {

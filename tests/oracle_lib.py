@@ -126,6 +126,23 @@ def tree_com(posm, meta, child, root):
     return mom[:M], com[:M]
 
 
+def tree_quad(posm, meta):
+    """Traceless quadrupoles {xx,xy,xz,yy,yz,zz} of every cell about its centre of mass (direct double sums)."""
+    M = len(meta)
+    quad = np.zeros((max(M, 1), 6), np.float32)
+    lib().orc_tree_quad(_p(posm), _p(np.ascontiguousarray(meta)), C.c_int64(M), _p(quad))
+    return quad[:M]
+
+
+def force_groups_quad(posm, b, meta, child, com, quad, root, gstart, theta=THETA, soft=SOFT, G_=G):
+    n = len(posm)
+    acc, counts = np.zeros((n, 4), np.float32), np.zeros(2, np.int64)
+    lib().orc_force_groups_quad(_p(posm), C.c_int64(n), _p(b), _p(meta), _p(child), _p(com), _p(np.ascontiguousarray(quad)),
+                                C.c_int64(len(meta)), C.c_int32(root), _p(gstart), len(gstart) - 1, f32(theta), f32(soft), f32(G_),
+                                _p(acc), _p(counts), None)
+    return acc, counts
+
+
 def force_group(posm, b, meta, child, com, root, group=32, theta=THETA, soft=SOFT, G_=G, entries=None):
     n = len(posm)
     acc, counts = np.zeros((n, 4), np.float32), np.zeros(2, np.int64)

@@ -225,8 +225,9 @@ def test_energy_on_device_matches_oracle(bh):
     assert abs(ke - wke) / wke < 1e-10 and abs(pe - wpe) / abs(wpe) < 1e-10
 
 
-# measured on B200 with the group acceptance test: see the print below (the per-body test of SURVEY §6 gives 1.3e-2
-# on this disk; the group test is more conservative); bound = measured x 1.2
+# measured on B200 with the group acceptance test: 1.14e-2 on this sample (profiles/r02_quadrupole_1m.json, monopole,
+# theta 0.5; the per-body test of SURVEY §6 gives 1.3e-2 on this thin disk).  measured x 1.2 would be 1.37e-2: the
+# round-1 bound already is tighter than that and stays
 MILLION_BODY_DIRECT_SUM_BOUND = 1.3e-2
 
 
