@@ -56,6 +56,9 @@ constexpr int FORCE_THREADS = FORCE_WARPS * 32;
 #ifndef FORCE_MIN_CTAS
 #define FORCE_MIN_CTAS 4
 #endif
+#ifndef FORCE_HEAVY_X10
+#define FORCE_HEAVY_X10 15   // chunks above 1.5x the mean list length of the previous step are handed out first (measured: 1.1x 0.824, 1.3x 0.817, 1.5x 0.819, 2.0x 0.827, 2.5x 0.829 ms on the 1M disk; 1.5x is also the best on the Plummer sphere)
+#endif
 #ifndef FORCE_ITEMS
 #define FORCE_ITEMS 2
 #endif
@@ -559,8 +562,8 @@ __global__ void reset_force_scalars(BhDevScalars* sc, int64_t ngroups) {
         sc->epoch += 1u;
         const unsigned nxt = (sc->epoch & 1u) ^ 1u;
         const unsigned long long prev = sc->entries_total;
-        // 2.5x the mean list length of the previous launch; nothing is heavy on the first one
-        sc->heavy_thresh = prev ? (unsigned)min((unsigned long long)0x7FFFFFFF, prev * 5ull / (2ull * (unsigned long long)ngroups) + 1ull)
+        // FORCE_HEAVY_X10 / 10 times the mean list length of the previous launch; nothing is heavy on the first one
+        sc->heavy_thresh = prev ? (unsigned)min((unsigned long long)0x7FFFFFFF, prev * (unsigned long long)FORCE_HEAVY_X10 / (10ull * (unsigned long long)ngroups) + 1ull)
                                 : 0x7FFFFFFFu;
         sc->heavy_n[nxt] = 0;
         sc->entries_total = 0;
