@@ -20,8 +20,9 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-LAUNCHES_PER_STEP = 17   # cube+keys 2, sort 6 (the last pass moves the bodies), tree 5, com 1, force 2, integrate 1 (it also
-                         # reduces the next step's bounding box); +2 (reset, bounds) on the first step after an import
+LAUNCHES_PER_STEP = 19   # cube+keys 2, sort 6 (the last pass moves the bodies), tree 5, centre of mass 3 (two of them on a
+                         # parallel graph branch), force 2, integrate 1 (it also reduces the next step's bounding box);
+                         # +2 (reset, bounds) on the first step after an import
 FLOP_PER_INTERACTION = 20  # SURVEY §8d (GPU-Gems convention; bench:205-213 op count)
 
 WORKLOADS = {
