@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define BH_ABI_VERSION 1
+#define BH_ABI_VERSION 2   /* 2: bh_mg_*, bh_step_part, BH_FLAG_QUADRUPOLE, BH_DBG_CELL_QUAD; checkpoint header v2 */
 
 /* negative error codes (positive values are cudaError_t) */
 #define BH_E_INVAL      (-1)  /* bad argument                                  */
@@ -62,8 +62,7 @@ typedef struct bh_params {
 #define BH_FLAG_QUADRUPOLE  4  /* accepted cells act with their traceless quadrupole as well (set before bh_create).
                                 * The reference has monopoles only (nbody_v5_bench.cu:205-213) and that stays the
                                 * default; this is an accuracy / throughput knob: the same acceptance test, a 3-6x
-                                * smaller error, so a larger theta reaches the monopole accuracy with fewer
-                                * interactions.  Not available in the locally-essential-tree calls.            */
+                                * smaller error on disc-like systems (see DESIGN.md 5.6 for where it does not pay).  Not available in the locally-essential-tree calls.            */
 
 typedef struct bh_ctx bh_ctx;
 
@@ -76,7 +75,9 @@ int  bh_group_size(void);
 const char* bh_error_string(int code);
 
 /* Replaces the 16 cudaMalloc calls + H2D copies of main()
- * (nbody_v5_bench.cu:311-335): allocates every buffer once for n_max bodies. */
+ * (nbody_v5_bench.cu:311-335): allocates every buffer once for n_max bodies
+ * (~392 B/body, +340 B/body with BH_FLAG_QUADRUPOLE; 0 < n_max < 2^28: the
+ * traversal's stack words are cell id << 3 plus a flag bit).               */
 int  bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device);
 /* Replaces nbody_v5_bench.cu:372-387. */
 void bh_destroy(bh_ctx* ctx);

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol(bh):
     L = bh.lib()
     missing = [n for n in declared_functions() if not hasattr(L, n)]
     assert not missing, missing
-    assert L.bh_abi_version() == 1
+    assert L.bh_abi_version() == 2
     import oracle_lib as O
 
     assert L.bh_group_size() == O.GROUP
