@@ -209,3 +209,31 @@ def test_soa_and_visual_exports_skip_slots_without_a_local_id(bh):
         assert (h[0, pad:pad + n][~local] == -777.0).all()                            # skipped, not scattered somewhere
         v = vbo.cpu().numpy()
         assert (v[:, :pad] == -777.0).all() and (v[:, pad + 3 * n:] == -777.0).all()
+
+
+def test_cpp_multi_gpu_driver_with_one_rank_equals_bh_step(bh):
+    """bh_mg_* (csrc/bh_mg.cu) on a world of ONE: NCCL is dlopen'ed, a communicator is made from a unique id, the step
+    loop runs its three-part schedule with the gather skipped — and must reproduce bh_step bit for bit.  The 2/4/8-GPU
+    equivalence is tools/check_sliced.py under torchrun; this keeps the driver inside the single-GPU suite."""
+    n = 50_001
+    soa = bh.ic_refdisk(n, 42)
+    with bh.BHEngine(n) as ref:
+        ref.load_soa(*soa)
+        ref.simulation_step(4)
+        want = (ref.debug_get(bh.DBG.POSM), ref.debug_get(bh.DBG.VEL), ref.debug_get(bh.DBG.IDS))
+    uid = bh.mg_unique_id()
+    assert len(uid) == 128 and any(uid)
+    with bh.BHEngine(n) as eng:
+        eng.load_soa(*soa)
+        mg = bh.MultiGpu(eng, uid, 0, 1, 0)
+        try:
+            info = mg.info()
+            assert (info["rank"], info["world"], info["first"], info["count"]) == (0, 1, 0, n) and info["per"] % 32 == 0
+            mg.step(3)
+            mg.step(1)
+            mg.finish()
+            eng.check_device_error()
+            got = (eng.debug_get(bh.DBG.POSM), eng.debug_get(bh.DBG.VEL), eng.debug_get(bh.DBG.IDS))
+        finally:
+            mg.close()
+    assert got[0].tobytes() == want[0].tobytes() and got[1].tobytes() == want[1].tobytes() and (got[2] == want[2]).all()
