@@ -11,7 +11,7 @@
 //   1. one histogram kernel counts every pass's digits in a single read of the keys
 //      (shared-memory histograms, one global atomic per bin per CTA);
 //   2. a RADIX-thread kernel turns each pass's histogram into exclusive bucket bases;
-//   3. one "onesweep" kernel per digit: a CTA takes a tile ticket, ranks its 4096 keys with
+//   3. one "onesweep" kernel per digit: a CTA takes a tile ticket, ranks its 7,680 keys (384 threads x 20) with
 //      warp-level match/ballot digit histograms (stable), publishes its per-digit counts,
 //      resolves the cross-tile prefix by decoupled look-back on packed status words (RADIX / 256 digits
 //      per thread, their look-back chains interleaved), stages the tile digit-ordered in shared memory and
@@ -29,16 +29,21 @@ namespace {
 #endif
 constexpr int RADIX_BITS = BH_RADIX_BITS;
 constexpr int RADIX = 1 << RADIX_BITS;
-constexpr int SORT_THREADS = 256;
+#ifndef BH_SORT_THREADS
+#define BH_SORT_THREADS 384
+#endif
+constexpr int SORT_THREADS = BH_SORT_THREADS;
 constexpr int SORT_WARPS = SORT_THREADS / 32;
 #ifndef BH_SORT_ITEMS
-#define BH_SORT_ITEMS 16
+#define BH_SORT_ITEMS 20
 #endif
 constexpr int ITEMS = BH_SORT_ITEMS;
-constexpr int TILE = SORT_THREADS * ITEMS;  // 4096 pairs per CTA
+constexpr int TILE = SORT_THREADS * ITEMS;  // 7,680 pairs per CTA (round 1: 256 x 16 = 4,096; DESIGN.md 5.3 has the sweep)
 constexpr int MAX_PASSES = 4;                // 32 key bits = 4 x 8 (or 10 + 10 + 10 + 2)
-constexpr int DPT = RADIX / SORT_THREADS;    // digits per thread in the per-digit part of a pass
-static_assert(DPT * SORT_THREADS == RADIX && 32 * ITEMS < 65536, "digit ownership / 16-bit warp counters");
+// digits per thread in the per-digit part of a pass; with more threads than digits the first RADIX threads own one each
+constexpr int DPT = RADIX >= SORT_THREADS ? RADIX / SORT_THREADS : 1;
+static_assert((RADIX >= SORT_THREADS ? DPT * SORT_THREADS == RADIX : true) && 32 * ITEMS < 65536 && SORT_THREADS % 32 == 0,
+              "digit ownership / 16-bit warp counters");
 
 constexpr uint32_t ST_MASK = 0x3FFFFFFFu;
 constexpr uint32_t ST_LOCAL = 0x40000000u;  // tile's own count is published
@@ -124,7 +129,7 @@ struct BodyMove {
 };
 
 #ifndef BH_SORT_MIN_CTAS
-#define BH_SORT_MIN_CTAS 3
+#define BH_SORT_MIN_CTAS 2
 #endif
 template <bool IOTA, bool MOVE>
 __global__ void __launch_bounds__(SORT_THREADS, BH_SORT_MIN_CTAS) onesweep_kernel(const uint32_t* __restrict__ keys_in,
@@ -185,19 +190,22 @@ __global__ void __launch_bounds__(SORT_THREADS, BH_SORT_MIN_CTAS) onesweep_kerne
 
     // ---- per-digit: warp offsets, tile count, publish, look-back --------------------------
     {
-        const int d0 = threadIdx.x * DPT;   // this thread owns digits d0 .. d0 + DPT - 1
+        const bool owns = (int)threadIdx.x * DPT < RADIX;            // threads beyond the digits only take part in the scans
+        const int d0 = owns ? threadIdx.x * DPT : 0;                  // this thread owns digits d0 .. d0 + DPT - 1
         uint32_t running[DPT];
 #pragma unroll
         for (int q = 0; q < DPT; ++q) {
             uint32_t r = 0;
+            if (owns) {
 #pragma unroll
-            for (int w = 0; w < SORT_WARPS; ++w) {
-                const uint32_t c = s_whist[w][d0 + q];
-                s_whist[w][d0 + q] = (uint16_t)r;
-                r += c;
+                for (int w = 0; w < SORT_WARPS; ++w) {
+                    const uint32_t c = s_whist[w][d0 + q];
+                    s_whist[w][d0 + q] = (uint16_t)r;
+                    r += c;
+                }
+                lookback[(size_t)tile * RADIX + d0 + q] = (tile == 0 ? ST_INCL : ST_LOCAL) | r;
             }
             running[q] = r;
-            lookback[(size_t)tile * RADIX + d0 + q] = (tile == 0 ? ST_INCL : ST_LOCAL) | r;
         }
 
         // exclusive scan of the tile's digit counts across the threads (DPT consecutive digits each)
@@ -216,12 +224,12 @@ __global__ void __launch_bounds__(SORT_THREADS, BH_SORT_MIN_CTAS) onesweep_kerne
         for (int w = 0; w < warp; ++w) excl += s_scan[w];
         uint32_t excl_in_tile[DPT];
 #pragma unroll
-        for (int q = 0; q < DPT; ++q) { excl_in_tile[q] = excl; s_tile_excl[d0 + q] = excl; excl += running[q]; }
+        for (int q = 0; q < DPT; ++q) { excl_in_tile[q] = excl; if (owns) s_tile_excl[d0 + q] = excl; excl += running[q]; }
 
         uint32_t prior[DPT];
 #pragma unroll
         for (int q = 0; q < DPT; ++q) prior[q] = 0;
-        if (tile > 0) {
+        if (tile > 0 && owns) {
             // Decoupled look-back, LB_WIDE predecessors per round trip and the DPT digit chains of this thread
             // interleaved: the statuses of tiles p, p-1, ... are fetched together (independent loads) and
             // consumed in order.  The chain of dependent L2 round trips, which bounds the first wave when
@@ -261,8 +269,10 @@ __global__ void __launch_bounds__(SORT_THREADS, BH_SORT_MIN_CTAS) onesweep_kerne
 #pragma unroll
             for (int q = 0; q < DPT; ++q) lookback[(size_t)tile * RADIX + d0 + q] = ST_INCL | (prior[q] + running[q]);
         }
+        if (owns) {
 #pragma unroll
-        for (int q = 0; q < DPT; ++q) s_global_off[d0 + q] = bucket_base[d0 + q] + prior[q] - excl_in_tile[q];
+            for (int q = 0; q < DPT; ++q) s_global_off[d0 + q] = bucket_base[d0 + q] + prior[q] - excl_in_tile[q];
+        }
     }
     __syncthreads();
 

@@ -25,6 +25,9 @@ for n in (1_000_000, 16_000_000):
     for end_bit in (30,):
         for _ in range(3):
             bh.sort_pairs_u32(keys, vals, ko, vo, n, 0, end_bit, tmp)
+        # correctness of whatever library variant is loaded: stable ascending order
+        want_k, want_v = torch.sort(keys.to(torch.int64) & 0xFFFFFFFF, stable=True)
+        assert bool((ko.to(torch.int64) & 0xFFFFFFFF == want_k).all()) and bool((vo.to(torch.int64) == want_v).all()), "sort result wrong"
         ts = []
         for _ in range(20):
             flush.fill_(0)
