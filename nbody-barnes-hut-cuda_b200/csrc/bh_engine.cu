@@ -847,6 +847,7 @@ int bh_export_soa_host(bh_ctx* c, float* px, float* py, float* pz, float* vx, fl
 // Host state in -> nsteps -> host state out, every copy inside the call.  The uploads are ordered so that compute
 // starts early: positions first; bounds, keys and the radix sort (they read positions only) run while masses and
 // velocities are still crossing PCIe on the copy stream — the trick bh_mg_step plays for NVLink.
+#define BH_STEP_TRY(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) return fail((int)_e); } while (0)
 int bh_step_host(bh_ctx* c, float* px, float* py, float* pz, float* vx, float* vy, float* vz, const float* mass,
                  int64_t n, int nsteps) {
     if (!c || !px || !py || !pz || !vx || !vy || !vz || !mass || n <= 0 || n > c->n_max || nsteps < 0) return BH_E_INVAL;
@@ -856,54 +857,57 @@ int bh_step_host(bh_ctx* c, float* px, float* py, float* pz, float* vx, float* v
     const size_t na = (size_t)c->n_alloc, bytes = (size_t)n * 4;
     float* s = c->stage;
     cudaStream_t cs = c->own_stream, xs = c->copy_stream;   // compute / copies
+    // on any error the caller's host buffers must not be read (or written) behind its back any more
+    auto fail = [&](int code) { cudaStreamSynchronize(xs); cudaStreamSynchronize(cs); return code; };
     if (nsteps == 0 || (c->prm.flags & BH_FLAG_PHASE_TIMER)) {   // nothing to overlap with / phases are timed one by one
         e = import_host_impl(c, px, py, pz, vx, vy, vz, mass, n, false);
         if (!e) e = bh_step(c, nsteps, cs);
-        if (e) return e;
+        if (e) return fail(e);
     } else {
         // upload order = order of need: positions (cube, keys, sort), masses (tree, centre of mass, traversal),
         // velocities (update only) — the whole velocity upload hides behind the tree build and the traversal
         const float* src[7] = {px, py, pz, mass, vx, vy, vz};
         const int slot[7] = {0, 1, 2, 6, 3, 4, 5};
         for (int k = 0; k < 7; ++k) {
-            BH_CUDA_TRY(cudaMemcpyAsync(s + (size_t)slot[k] * na, src[k], bytes, cudaMemcpyHostToDevice, xs));
-            if (k == 2) BH_CUDA_TRY(cudaEventRecord(c->ev_h2d_pos, xs));
-            if (k == 3) BH_CUDA_TRY(cudaEventRecord(c->ev_h2d_mass, xs));
+            BH_STEP_TRY(cudaMemcpyAsync(s + (size_t)slot[k] * na, src[k], bytes, cudaMemcpyHostToDevice, xs));
+            if (k == 2) BH_STEP_TRY(cudaEventRecord(c->ev_h2d_pos, xs));
+            if (k == 3) BH_STEP_TRY(cudaEventRecord(c->ev_h2d_mass, xs));
         }
-        BH_CUDA_TRY(cudaEventRecord(c->ev_h2d_rest, xs));
+        BH_STEP_TRY(cudaEventRecord(c->ev_h2d_rest, xs));
         // what bh_import_soa does, in three parts
         c->n = n; c->steps = 0; c->have_sorted = false; c->bbox_fresh = false;
         e = set_ghosts_possible(c, false);
-        if (e) return e;
+        if (e) return fail(e);
         default_slice(c);
-        BH_CUDA_TRY(cudaMemsetAsync((char*)c->sc + offsetof(BhDevScalars, epoch), 0, sizeof(BhDevScalars) - offsetof(BhDevScalars, epoch), cs));
-        BH_CUDA_TRY(cudaMemsetAsync(c->heavy_flag, 0, 8 * (size_t)c->max_chunks, cs));
-        BH_CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_h2d_pos, 0));
+        BH_STEP_TRY(cudaMemsetAsync((char*)c->sc + offsetof(BhDevScalars, epoch), 0, sizeof(BhDevScalars) - offsetof(BhDevScalars, epoch), cs));
+        BH_STEP_TRY(cudaMemsetAsync(c->heavy_flag, 0, 8 * (size_t)c->max_chunks, cs));
+        BH_STEP_TRY(cudaStreamWaitEvent(cs, c->ev_h2d_pos, 0));
         e = bh_import_pos_launch(s, s + na, s + 2 * na, n, c->posm, cs);
-        if (e) return e;
+        if (e) return fail(e);
         c->have_state = true;
         e = bh_step_part(c, 0, cs);                       // cube, keys, radix sort: positions only
-        if (e) return e;
-        BH_CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_h2d_mass, 0));
+        if (e) return fail(e);
+        BH_STEP_TRY(cudaStreamWaitEvent(cs, c->ev_h2d_mass, 0));
         e = bh_import_mass_launch(s + 6 * na, n, c->posm, cs);
         if (!e) e = bh_step_part(c, 1, cs);               // reorder positions + masses, tree, centre of mass, traversal
-        if (e) return e;
-        BH_CUDA_TRY(cudaStreamWaitEvent(cs, c->ev_h2d_rest, 0));
+        if (e) return fail(e);
+        BH_STEP_TRY(cudaStreamWaitEvent(cs, c->ev_h2d_rest, 0));
         e = bh_import_vel_launch(s + 3 * na, s + 4 * na, s + 5 * na, n, c->vel, c->ids, cs);
         if (!e) e = bh_step_part(c, 2, cs);               // reorder velocities + ids, update
         if (!e && nsteps > 1) e = bh_step(c, nsteps - 1, cs);
-        if (e) return e;
+        if (e) return fail(e);
     }
     // export on the compute stream, downloads behind it: no device-wide sync needed
     e = bh_export_launch(c->posm, c->vel, c->acc, c->ids, c->n, s, s + na, s + 2 * na, s + 3 * na, s + 4 * na, s + 5 * na,
                          nullptr, nullptr, nullptr, cs);
-    if (e) return e;
+    if (e) return fail(e);
     float* dst[6] = {px, py, pz, vx, vy, vz};
     for (int k = 0; k < 6; ++k)
-        BH_CUDA_TRY(cudaMemcpyAsync(dst[k], s + (size_t)k * na, bytes, cudaMemcpyDeviceToHost, cs));
-    BH_CUDA_TRY(cudaStreamSynchronize(cs));
+        BH_STEP_TRY(cudaMemcpyAsync(dst[k], s + (size_t)k * na, bytes, cudaMemcpyDeviceToHost, cs));
+    BH_STEP_TRY(cudaStreamSynchronize(cs));
     return 0;
 }
+#undef BH_STEP_TRY
 
 static int dbg_locate(bh_ctx* c, int what, void** ptr, size_t* bytes) {
     BhDevScalars h;
