@@ -859,6 +859,16 @@ int bh_step_host(bh_ctx* c, float* px, float* py, float* pz, float* vx, float* v
     cudaStream_t cs = c->own_stream, xs = c->copy_stream;   // compute / copies
     // on any error the caller's host buffers must not be read (or written) behind its back any more
     auto fail = [&](int code) { cudaStreamSynchronize(xs); cudaStreamSynchronize(cs); return code; };
+#ifdef BH_TRACE_STEP_HOST   // build-time diagnostic: device timeline of one call on stderr (tools/build_variants.sh)
+    cudaEvent_t tr[12]; int ntr = 0; const char* trn[12];
+    for (auto& t : tr) cudaEventCreate(&t);
+    auto mark = [&](cudaStream_t q, const char* name) { trn[ntr] = name; cudaEventRecord(tr[ntr++], q); };
+    cudaStreamSynchronize(cs); cudaStreamSynchronize(xs);
+    mark(xs, "start"); cudaStreamWaitEvent(cs, tr[0], 0);
+#define BH_MARK(q, name) mark(q, name)
+#else
+#define BH_MARK(q, name) do {} while (0)
+#endif
     if (nsteps == 0 || (c->prm.flags & BH_FLAG_PHASE_TIMER)) {   // nothing to overlap with / phases are timed one by one
         e = import_host_impl(c, px, py, pz, vx, vy, vz, mass, n, false);
         if (!e) e = bh_step(c, nsteps, cs);
@@ -870,10 +880,11 @@ int bh_step_host(bh_ctx* c, float* px, float* py, float* pz, float* vx, float* v
         const int slot[7] = {0, 1, 2, 6, 3, 4, 5};
         for (int k = 0; k < 7; ++k) {
             BH_STEP_TRY(cudaMemcpyAsync(s + (size_t)slot[k] * na, src[k], bytes, cudaMemcpyHostToDevice, xs));
-            if (k == 2) BH_STEP_TRY(cudaEventRecord(c->ev_h2d_pos, xs));
-            if (k == 3) BH_STEP_TRY(cudaEventRecord(c->ev_h2d_mass, xs));
+            if (k == 2) { BH_STEP_TRY(cudaEventRecord(c->ev_h2d_pos, xs)); BH_MARK(xs, "h2d pos"); }
+            if (k == 3) { BH_STEP_TRY(cudaEventRecord(c->ev_h2d_mass, xs)); BH_MARK(xs, "h2d mass"); }
         }
         BH_STEP_TRY(cudaEventRecord(c->ev_h2d_rest, xs));
+        BH_MARK(xs, "h2d vel");
         // what bh_import_soa does, in three parts
         c->n = n; c->steps = 0; c->have_sorted = false; c->bbox_fresh = false;
         e = set_ghosts_possible(c, false);
@@ -887,24 +898,34 @@ int bh_step_host(bh_ctx* c, float* px, float* py, float* pz, float* vx, float* v
         c->have_state = true;
         e = bh_step_part(c, 0, cs);                       // cube, keys, radix sort: positions only
         if (e) return fail(e);
+        BH_MARK(cs, "part0 done");
         BH_STEP_TRY(cudaStreamWaitEvent(cs, c->ev_h2d_mass, 0));
         e = bh_import_mass_launch(s + 6 * na, n, c->posm, cs);
         if (!e) e = bh_step_part(c, 1, cs);               // reorder positions + masses, tree, centre of mass, traversal
         if (e) return fail(e);
+        BH_MARK(cs, "part1 done");
         BH_STEP_TRY(cudaStreamWaitEvent(cs, c->ev_h2d_rest, 0));
         e = bh_import_vel_launch(s + 3 * na, s + 4 * na, s + 5 * na, n, c->vel, c->ids, cs);
         if (!e) e = bh_step_part(c, 2, cs);               // reorder velocities + ids, update
         if (!e && nsteps > 1) e = bh_step(c, nsteps - 1, cs);
         if (e) return fail(e);
+        BH_MARK(cs, "part2 done");
     }
     // export on the compute stream, downloads behind it: no device-wide sync needed
     e = bh_export_launch(c->posm, c->vel, c->acc, c->ids, c->n, s, s + na, s + 2 * na, s + 3 * na, s + 4 * na, s + 5 * na,
                          nullptr, nullptr, nullptr, cs);
     if (e) return fail(e);
+    BH_MARK(cs, "export done");
     float* dst[6] = {px, py, pz, vx, vy, vz};
     for (int k = 0; k < 6; ++k)
         BH_STEP_TRY(cudaMemcpyAsync(dst[k], s + (size_t)k * na, bytes, cudaMemcpyDeviceToHost, cs));
+    BH_MARK(cs, "d2h done");
     BH_STEP_TRY(cudaStreamSynchronize(cs));
+#ifdef BH_TRACE_STEP_HOST
+    for (int i = 1; i < ntr; ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, tr[0], tr[i]); fprintf(stderr, "[step_host] %-12s %.3f ms\n", trn[i], ms); }
+    for (auto& t : tr) cudaEventDestroy(t);
+#endif
+#undef BH_MARK
     return 0;
 }
 #undef BH_STEP_TRY
