@@ -168,6 +168,8 @@ int bh_import_vel_launch(const float* vx, const float* vy, const float* vz, int6
 int bh_reorder_posm_launch(const float4* posm_in, const uint32_t* perm, float4* posm_out, int64_t n, cudaStream_t st);
 int bh_reorder_rest_launch(const float4* vel_in, const int32_t* ids_in, const uint32_t* perm, float4* vel_out, int32_t* ids_out,
                            int64_t n, cudaStream_t st);
+int bh_where_launch(const int32_t* ids, int64_t n, int32_t* where, cudaStream_t st);
+int bh_gather3_launch(const float4* src, const int32_t* where, int64_t n, float* ox, float* oy, float* oz, cudaStream_t st);
 int bh_export_launch(const float4* posm, const float4* vel, const float4* acc, const int32_t* ids,
                      int64_t n, float* px, float* py, float* pz, float* vx, float* vy, float* vz,
                      float* ax, float* ay, float* az, cudaStream_t st);

@@ -885,13 +885,18 @@ int bh_step_host(bh_ctx* c, float* px, float* py, float* pz, float* vx, float* v
         }
         BH_STEP_TRY(cudaEventRecord(c->ev_h2d_rest, xs));
         BH_MARK(xs, "h2d vel");
-        // what bh_import_soa does, in three parts
+        // what bh_import_soa does, in three parts.  A caller that steps the same system call after call hands back
+        // the bodies the last call returned: after the sort the chunks hold the same bodies again, so the record of
+        // which chunks were expensive (a scheduling hint, bh_force.cu) stays valid — it is only dropped when n changes.
+        const bool same_system = c->have_state && c->n == n && c->world == 1;   // a stale hint costs time, never correctness
         c->n = n; c->steps = 0; c->have_sorted = false; c->bbox_fresh = false;
         e = set_ghosts_possible(c, false);
         if (e) return fail(e);
         default_slice(c);
-        BH_STEP_TRY(cudaMemsetAsync((char*)c->sc + offsetof(BhDevScalars, epoch), 0, sizeof(BhDevScalars) - offsetof(BhDevScalars, epoch), cs));
-        BH_STEP_TRY(cudaMemsetAsync(c->heavy_flag, 0, 8 * (size_t)c->max_chunks, cs));
+        if (!same_system) {
+            BH_STEP_TRY(cudaMemsetAsync((char*)c->sc + offsetof(BhDevScalars, epoch), 0, sizeof(BhDevScalars) - offsetof(BhDevScalars, epoch), cs));
+            BH_STEP_TRY(cudaMemsetAsync(c->heavy_flag, 0, 8 * (size_t)c->max_chunks, cs));
+        }
         BH_STEP_TRY(cudaStreamWaitEvent(cs, c->ev_h2d_pos, 0));
         e = bh_import_pos_launch(s, s + na, s + 2 * na, n, c->posm, cs);
         if (e) return fail(e);
@@ -911,15 +916,27 @@ int bh_step_host(bh_ctx* c, float* px, float* py, float* pz, float* vx, float* v
         if (e) return fail(e);
         BH_MARK(cs, "part2 done");
     }
-    // export on the compute stream, downloads behind it: no device-wide sync needed
-    e = bh_export_launch(c->posm, c->vel, c->acc, c->ids, c->n, s, s + na, s + 2 * na, s + 3 * na, s + 4 * na, s + 5 * na,
-                         nullptr, nullptr, nullptr, cs);
-    if (e) return fail(e);
-    BH_MARK(cs, "export done");
+    // export on the compute stream as a gather (slot of every body id, then positions, then velocities), downloads on
+    // the copy stream behind each: the positions are already crossing PCIe while the velocities are still being
+    // gathered.  The second value buffer is sort scratch, free until the next step.
     float* dst[6] = {px, py, pz, vx, vy, vz};
-    for (int k = 0; k < 6; ++k)
-        BH_STEP_TRY(cudaMemcpyAsync(dst[k], s + (size_t)k * na, bytes, cudaMemcpyDeviceToHost, cs));
-    BH_MARK(cs, "d2h done");
+    int32_t* where = (int32_t*)(c->perm == c->vals1 ? c->vals0 : c->vals1);   // the value buffer that is not the permutation
+    e = bh_where_launch(c->ids, c->n, where, cs);
+    if (!e) e = bh_gather3_launch(c->posm, where, c->n, s, s + na, s + 2 * na, cs);
+    if (e) return fail(e);
+    BH_STEP_TRY(cudaEventRecord(c->ev_h2d_pos, cs));
+    e = bh_gather3_launch(c->vel, where, c->n, s + 3 * na, s + 4 * na, s + 5 * na, cs);
+    if (e) return fail(e);
+    BH_STEP_TRY(cudaEventRecord(c->ev_h2d_rest, cs));
+    BH_MARK(cs, "export done");
+    BH_STEP_TRY(cudaStreamWaitEvent(xs, c->ev_h2d_pos, 0));
+    for (int k = 0; k < 3; ++k)
+        BH_STEP_TRY(cudaMemcpyAsync(dst[k], s + (size_t)k * na, bytes, cudaMemcpyDeviceToHost, xs));
+    BH_STEP_TRY(cudaStreamWaitEvent(xs, c->ev_h2d_rest, 0));
+    for (int k = 3; k < 6; ++k)
+        BH_STEP_TRY(cudaMemcpyAsync(dst[k], s + (size_t)k * na, bytes, cudaMemcpyDeviceToHost, xs));
+    BH_MARK(xs, "d2h done");
+    BH_STEP_TRY(cudaStreamSynchronize(xs));
     BH_STEP_TRY(cudaStreamSynchronize(cs));
 #ifdef BH_TRACE_STEP_HOST
     for (int i = 1; i < ntr; ++i) { float ms = 0.f; cudaEventElapsedTime(&ms, tr[0], tr[i]); fprintf(stderr, "[step_host] %-12s %.3f ms\n", trn[i], ms); }

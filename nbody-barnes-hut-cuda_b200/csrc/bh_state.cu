@@ -478,6 +478,32 @@ int bh_export_launch(const float4* posm, const float4* vel, const float4* acc, c
     return (int)cudaGetLastError();
 }
 
+// Body-order export as a GATHER (bh_step_host): where[id] = slot of body id in the state arrays, then each output array
+// is written coalesced from one random 16-byte read per body.  The scatter of export_kernel costs six partial-sector
+// writes per body; here it is one (the slot index).  ids must be a permutation of [0, n) (no ghosts).
+__global__ void __launch_bounds__(kThreads) where_kernel(const int32_t* __restrict__ ids, int64_t n, int32_t* __restrict__ where) {
+    for (int64_t i = (int64_t)blockIdx.x * kThreads + threadIdx.x; i < n; i += (int64_t)gridDim.x * kThreads) {
+        const int32_t o = ids[i];
+        if (o >= 0 && (int64_t)o < n) where[o] = (int32_t)i;
+    }
+}
+__global__ void __launch_bounds__(kThreads) gather3_kernel(const float4* __restrict__ src, const int32_t* __restrict__ where,
+                                                          int64_t n, float* __restrict__ ox, float* __restrict__ oy,
+                                                          float* __restrict__ oz) {
+    for (int64_t o = (int64_t)blockIdx.x * kThreads + threadIdx.x; o < n; o += (int64_t)gridDim.x * kThreads) {
+        const float4 v = __ldg(src + where[o]);
+        ox[o] = v.x; oy[o] = v.y; oz[o] = v.z;
+    }
+}
+int bh_where_launch(const int32_t* ids, int64_t n, int32_t* where, cudaStream_t st) {
+    where_kernel<<<grid_for(n, 2), kThreads, 0, st>>>(ids, n, where);
+    return (int)cudaGetLastError();
+}
+int bh_gather3_launch(const float4* src, const int32_t* where, int64_t n, float* ox, float* oy, float* oz, cudaStream_t st) {
+    gather3_kernel<<<grid_for(n, 2), kThreads, 0, st>>>(src, where, n, ox, oy, oz);
+    return (int)cudaGetLastError();
+}
+
 // tile_scratch: n / 2048 + 2 ints.  The number of kept bodies is left in tile_scratch[tiles] (device).
 int bh_compact_real_launch(const float4* posm, const float4* vel, const int32_t* ids, const float4* acc, int64_t n,
                            int32_t* tile_scratch, float4* posm_out, float4* vel_out, int32_t* ids_out, cudaStream_t st) {

@@ -5,7 +5,7 @@ import nbody_barnes_hut_cuda_b200 as bh
 n = 1_000_000
 px, py, pz, vx, vy, vz, m = bh.ic_refdisk(n)
 harr = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory().numpy() for a in (px, py, pz, vx, vy, vz, m)]
-eng = bh.BHEngine(n)
+eng = bh.BHEngine(n, flags=int(os.environ.get('BH_TRACE_FLAGS', '0')))
 for i in range(8):
     t0 = time.perf_counter()
     eng.step_host(*harr, nsteps=1)
