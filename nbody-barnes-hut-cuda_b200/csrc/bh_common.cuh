@@ -124,7 +124,7 @@ int bh_reorder_launch(const float4* posm_in, const float4* vel_in, const int32_t
                       const uint32_t* perm, float4* posm_out, float4* vel_out, int32_t* ids_out,
                       int64_t n, cudaStream_t st);
 // kid_lv: 8 bytes per cell, digit-indexed like cell_child — level | bucket<<7 of child cells.
-int bh_tree_launch(const void* keys, int levels, int64_t n, int2* pair_info, int32_t* pair_scan,
+int bh_tree_launch(const void* keys, int levels, int64_t n, int2* pair_info, int2* pair_aux, int32_t* pair_scan,
                    int32_t* scan_block_sums, int4* cell_meta, int32_t* cell_child,
                    uint8_t* kid_lv, BhDevScalars* sc, cudaStream_t st);
 // kid_src / kid_info: 8 entries per cell, DENSE (the r-th existing child in digit order sits at 8c + r) — the SOURCE

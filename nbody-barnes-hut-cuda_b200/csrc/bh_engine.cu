@@ -51,6 +51,7 @@ struct bh_ctx {
     void* sort_tmp = nullptr;
     size_t sort_tmp_bytes = 0;
     int2* pair_info = nullptr;
+    int2* pair_aux = nullptr;    // leaders only: {last body of the cell, pair that names the parent}
     int32_t *pair_scan = nullptr, *tile_sums = nullptr;
     int4* cell_meta = nullptr;
     int32_t* cell_child = nullptr;
@@ -114,7 +115,7 @@ void free_all(bh_ctx* c) {
     if (c->ev_h2d_rest) cudaEventDestroy(c->ev_h2d_rest);
     if (c->ev_h2d_mass) cudaEventDestroy(c->ev_h2d_mass);
     void* ptrs[] = {c->posm, c->vel, c->posm_s, c->vel_s, c->acc, c->ids, c->ids_s, c->keys0, c->keys1, c->vals0,
-                    c->vals1, c->sort_tmp, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
+                    c->vals1, c->sort_tmp, c->pair_info, c->pair_aux, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
                     c->com_scratch, c->cell_com, c->sc, c->stage, c->d_scratch, c->heavy_list, c->heavy_flag, c->kid_src, c->kid_lv, c->kid_info, c->quad_scratch, c->cell_quad, c->kid_quad, c->let_boxes, c->let_counts, c->let_queue, c->klo, c->kaux, c->keys64};
     for (void* p : ptrs) if (p) cudaFree(p);
 }
@@ -211,7 +212,7 @@ int phase_sort(bh_ctx* c, cudaStream_t st) {
 }
 
 int phase_build(bh_ctx* c, cudaStream_t st) {
-    return bh_tree_launch(c->levels == 20 ? (const void*)c->keys64 : (const void*)c->keys0, c->levels, c->n, c->pair_info, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
+    return bh_tree_launch(c->levels == 20 ? (const void*)c->keys64 : (const void*)c->keys0, c->levels, c->n, c->pair_info, c->pair_aux, c->pair_scan, c->tile_sums, c->cell_meta, c->cell_child,
                           c->kid_lv, c->sc, st);
 }
 
@@ -400,7 +401,7 @@ int bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device) 
         c->perm = (c->levels == 20 && !even) ? c->vals1 : c->vals0;
     }
     if (c->levels == 20) { TRYA(dev_alloc(&c->klo, na)); TRYA(dev_alloc(&c->kaux, na)); TRYA(dev_alloc(&c->keys64, na)); }
-    TRYA(dev_alloc(&c->pair_info, na)); TRYA(dev_alloc(&c->pair_scan, na)); TRYA(dev_alloc(&c->tile_sums, na / 2048 + 16));
+    TRYA(dev_alloc(&c->pair_info, na)); TRYA(dev_alloc(&c->pair_aux, na)); TRYA(dev_alloc(&c->pair_scan, na)); TRYA(dev_alloc(&c->tile_sums, na / 2048 + 16));
     TRYA(dev_alloc(&c->cell_meta, na)); TRYA(dev_alloc(&c->cell_child, na * 8));
     TRYA(dev_alloc(&c->cell_com, na)); TRYA(cudaMalloc(&c->com_scratch, bh_com_scratch_bytes(c->n_alloc)));
     c->quad = (prm.flags & BH_FLAG_QUADRUPOLE) != 0;
