@@ -20,7 +20,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-LAUNCHES_PER_STEP = 19   # cube+keys 2, sort 6 (the last pass moves the bodies), tree 5, centre of mass 3 (two of them on a
+LAUNCHES_PER_STEP = 18   # graph step: 2 keys + 6 sort + 5 build + 3 centre of mass + 2 force (reset, traversal with the update fused in)
                          # parallel graph branch), force 2, integrate 1 (it also reduces the next step's bounding box);
                          # +2 (reset, bounds) on the first step after an import
 FLOP_PER_INTERACTION = 20  # SURVEY §8d (GPU-Gems convention; bench:205-213 op count)

@@ -142,6 +142,14 @@ int bh_com_prefix_launch(const float4* posm, int64_t n, void* com_scratch, void*
 int bh_com_cells_launch(const float4* posm, int64_t n, const int4* cell_meta, const int32_t* cell_child, void* com_scratch,
                         float4* cell_com, float4* kid_src, uint2* kid_info, BhDevScalars* sc, void* quad_scratch,
                         float4* cell_quad, float4* kid_quad, cudaStream_t st);
+// Optional tail of the traversal: the kick-drift-clamp of bench:227-249 for a chunk as soon as its accelerations are
+// final (same arithmetic as integrate_kernel, bit for bit), and the min/max of the new positions.  posm_out == nullptr:
+// the traversal only writes acc (the update is a launch of its own).
+struct BhFusedUpdate {
+    const float4* vel_s; const int32_t* ids_s;
+    float4* posm_out; float4* vel_out; int32_t* ids_out;
+    float dt, max_speed;
+};
 // heavy_list, heavy_flag: 2 * max_chunks u32 each (see BhDevScalars::epoch)
 // ids: nullptr, or per-body ids where id < 0 marks a ghost (a source whose own acceleration is not wanted)
 int bh_force_launch(const float4* posm, const void* keys, int levels, const int32_t* ids, int64_t n, int64_t first_body,
@@ -153,7 +161,7 @@ int bh_force_launch(const float4* posm, const void* keys, int levels, const int3
                     // nullptr/nullptr/0 = the ordinary pass over the bodies' own tree
                     const float4* src_posm, const BhDevScalars* tree_sc, int accumulate,
                     // quadrupole option: per-cell and per-child-entry moments (bh_com_launch); nullptr = monopoles only
-                    const float4* cell_quad, const float4* kid_quad, cudaStream_t st);
+                    const float4* cell_quad, const float4* kid_quad, cudaStream_t st, const BhFusedUpdate* fused = nullptr);
 int bh_force_prepare();
 int bh_integrate_launch(const float4* posm_s, const float4* vel_s, const int32_t* ids_s, const float4* acc,
                         float4* posm, float4* vel, int32_t* ids, int64_t first_body, int64_t body_count,

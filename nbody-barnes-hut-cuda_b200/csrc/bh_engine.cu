@@ -84,6 +84,7 @@ struct bh_ctx {
     // the step in three parts (bh_step_part): 0 = cube, keys, radix sort (positions only); 1 = reorder positions +
     // masses, tree, centre of mass, traversal; 2 = reorder velocities + ids, update
     cudaGraphExec_t half_exec[3] = {nullptr, nullptr, nullptr};
+    bool no_fused_update = false;   // BH_NO_FUSED_UPDATE=1 in the environment at creation: A/B switch for measurements
     bool may_have_ghosts = false;   // ids < 0 possible (bh_import_state / checkpoint): the traversal must read the ids
     int64_t graph_half_n = -1, graph_half_first = -1, graph_half_count = -1;
     cudaStream_t own_stream = nullptr;
@@ -228,6 +229,20 @@ int phase_force(bh_ctx* c, cudaStream_t st) {
                            c->prm.softening, c->prm.G, c->prm.group_split, c->num_sms, nullptr, nullptr, 0, c->cell_quad, c->kid_quad, st);
 }
 
+// traversal + update in one launch (whole-step paths without ghosts; the phases stay separate everywhere else)
+int phase_force_update(bh_ctx* c, cudaStream_t st) {
+    if (c->may_have_ghosts || c->n < 2 || c->no_fused_update) {
+        int e = phase_force(c, st);
+        return e ? e : bh_integrate_launch(c->posm_s, c->vel_s, c->ids_s, c->acc, c->posm, c->vel, c->ids, c->slice_first,
+                                           c->slice_count, c->prm.dt, c->prm.max_speed, c->sc, st);
+    }
+    const BhFusedUpdate fu{c->vel_s, c->ids_s, c->posm, c->vel, c->ids, c->prm.dt, c->prm.max_speed};
+    return bh_force_launch(c->posm_s, c->levels == 20 ? (const void*)c->keys64 : (const void*)c->keys0, c->levels, nullptr, c->n,
+                           c->slice_first, c->slice_count, c->cell_meta, c->cell_com, c->kid_src, c->kid_info, c->acc, c->sc,
+                           c->heavy_list, c->heavy_flag, c->max_chunks, c->prm.theta, c->prm.softening, c->prm.G, c->prm.group_split,
+                           c->num_sms, nullptr, nullptr, 0, c->cell_quad, c->kid_quad, st, &fu);
+}
+
 int phase_update(bh_ctx* c, cudaStream_t st) {
     return bh_integrate_launch(c->posm_s, c->vel_s, c->ids_s, c->acc, c->posm, c->vel, c->ids, c->slice_first,
                                c->slice_count, c->prm.dt, c->prm.max_speed, c->sc, st);
@@ -249,8 +264,7 @@ int launch_tail_overlapped(bh_ctx* c, cudaStream_t st) {
     if (e) return e;
     e = bh_com_cells_launch(c->posm_s, c->n, c->cell_meta, c->cell_child, c->com_scratch, c->cell_com, c->kid_src, c->kid_info, c->sc,
                             c->quad_scratch, c->cell_quad, c->kid_quad, st);
-    if (!e) e = phase_force(c, st);
-    if (!e) e = phase_update(c, st);
+    if (!e) e = phase_force_update(c, st);
     return e;
 }
 
@@ -382,6 +396,7 @@ int bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device) 
     bh_ctx* c = new (std::nothrow) bh_ctx();
     if (!c) return BH_E_NOMEM;
     c->device = device; c->prm = prm; c->n_max = n_max;
+    { const char* v = getenv("BH_NO_FUSED_UPDATE"); c->no_fused_update = v && v[0] == '1'; }
     c->levels = prm.key_bits / 3;
     c->n_alloc = ((n_max + 4095) / 4096 + 1) * 4096;  // room for slice padding in all-gathers
     int sms = 0;

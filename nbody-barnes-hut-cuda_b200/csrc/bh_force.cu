@@ -210,8 +210,9 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
     const float4* __restrict__ kid_src, const uint2* __restrict__ kid_info, float4* __restrict__ acc, BhDevScalars* sc,
     uint32_t* __restrict__ heavy_list, uint32_t* __restrict__ heavy_flag, int64_t max_chunks, float theta, float soft,
     float G, float split_alpha, const float4* __restrict__ src_posm, const BhDevScalars* __restrict__ tree_sc,
-    int accumulate, const float4* __restrict__ cell_quad, const float4* __restrict__ kid_quad) {
+    int accumulate, const float4* __restrict__ cell_quad, const float4* __restrict__ kid_quad, const BhFusedUpdate fu) {
     __shared__ WarpScratchT<QUAD> s_warp[FORCE_WARPS];
+    __shared__ unsigned s_bbox[FORCE_WARPS][6];   // fused update: min/max images of this warp's new positions
 
     const int lane = bh_lane();
     WarpScratchT<QUAD>& W = s_warp[threadIdx.x >> 5];
@@ -229,6 +230,9 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
 
     unsigned long long tot_cell = 0, tot_body = 0, tot_entries = 0;
     unsigned max_sp = 0;
+    unsigned* const bbox = s_bbox[threadIdx.x >> 5];
+    if (lane < 6) bbox[lane] = bh_f2ord(lane < 3 ? 1e10f : -1e10f);   // the reference's start values (bench:138)
+    __syncwarp();
 
     // heavy-first scheduling: tickets [0, heavy_n) replay last step's heavy chunks, the rest walk the
     // chunks in Morton order and skip the ones already handed out
@@ -539,10 +543,34 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
             if ((int64_t)slot < max_chunks) { list_nxt[slot] = g; flag_nxt[g] = epoch + 1u; }
         }
 
+        float4 a = make_float4(G * ax, G * ay, G * az, (float)chunk_entries);
         if (valid) {
-            float4 a = make_float4(G * ax, G * ay, G * az, (float)chunk_entries);
             if (accumulate) { const float4 o = acc[my]; a.x += o.x; a.y += o.y; a.z += o.z; a.w += o.w; }
             acc[my] = a;
+        }
+        if (fu.posm_out != nullptr) {   // warp-uniform.  integrate_kernel's arithmetic (bh_state.cu), bit for bit
+            float4 p = me, v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (valid) v = __ldg(fu.vel_s + my);
+            float x = __fmaf_rn(a.x, fu.dt, v.x), y = __fmaf_rn(a.y, fu.dt, v.y), z = __fmaf_rn(a.z, fu.dt, v.z);
+            const float s2 = __fmaf_rn(z, z, __fmaf_rn(x, x, __fmul_rn(y, y)));
+            if (s2 > __fmul_rn(fu.max_speed, fu.max_speed)) {
+                const float scale = __fdiv_rn(fu.max_speed, __fsqrt_rn(s2));
+                x = __fmul_rn(x, scale); y = __fmul_rn(y, scale); z = __fmul_rn(z, scale);
+            }
+            v.x = x; v.y = y; v.z = z;
+            p.x = __fmaf_rn(x, fu.dt, p.x); p.y = __fmaf_rn(y, fu.dt, p.y); p.z = __fmaf_rn(z, fu.dt, p.z);
+            if (valid) { fu.vel_out[my] = v; fu.posm_out[my] = p; fu.ids_out[my] = __ldg(fu.ids_s + my); }
+            // min/max as integrate_kernel forms them (fminf / fmaxf against the start values), reduced in the ordered image
+            const unsigned lx = __reduce_min_sync(0xffffffffu, valid ? bh_f2ord(fminf(1e10f, p.x)) : 0xFFFFFFFFu);
+            const unsigned ly = __reduce_min_sync(0xffffffffu, valid ? bh_f2ord(fminf(1e10f, p.y)) : 0xFFFFFFFFu);
+            const unsigned lz = __reduce_min_sync(0xffffffffu, valid ? bh_f2ord(fminf(1e10f, p.z)) : 0xFFFFFFFFu);
+            const unsigned ux = __reduce_max_sync(0xffffffffu, valid ? bh_f2ord(fmaxf(-1e10f, p.x)) : 0u);
+            const unsigned uy = __reduce_max_sync(0xffffffffu, valid ? bh_f2ord(fmaxf(-1e10f, p.y)) : 0u);
+            const unsigned uz = __reduce_max_sync(0xffffffffu, valid ? bh_f2ord(fmaxf(-1e10f, p.z)) : 0u);
+            if (lane == 0) {
+                bbox[0] = min(bbox[0], lx); bbox[1] = min(bbox[1], ly); bbox[2] = min(bbox[2], lz);
+                bbox[3] = max(bbox[3], ux); bbox[4] = max(bbox[4], uy); bbox[5] = max(bbox[5], uz);
+            }
         }
         tot_cell += acc_cells_w;
         tot_body += dir_bodies_w;
@@ -553,6 +581,9 @@ __global__ void __launch_bounds__(FORCE_THREADS, FORCE_MIN_CTAS) force_kernel(
         if (tot_body) atomicAdd(&sc->inter_body, tot_body);
         if (tot_entries && !accumulate) atomicAdd(&sc->entries_total, tot_entries);
         atomicMax(&sc->max_stack, max_sp);
+        if (fu.posm_out != nullptr) {
+            for (int k = 0; k < 3; ++k) { atomicMin(&sc->bbox_enc[k], bbox[k]); atomicMax(&sc->bbox_enc[3 + k], bbox[3 + k]); }
+        }
     }
 }
 
@@ -609,8 +640,10 @@ int bh_force_launch(const float4* posm, const void* keys, int levels, const int3
                     float4* acc, BhDevScalars* sc, uint32_t* heavy_list, uint32_t* heavy_flag, int64_t max_chunks,
                     float theta, float softening, float G, float split_alpha, int num_sms, const float4* src_posm,
                     const BhDevScalars* tree_sc, int accumulate, const float4* cell_quad, const float4* kid_quad,
-                    cudaStream_t st) {
+                    cudaStream_t st, const BhFusedUpdate* fused) {
     if (body_count <= 0) return 0;
+    if (fused && (accumulate || n < 2 || ids != nullptr)) return BH_E_INVAL;   // the update needs final accelerations of every body
+    const BhFusedUpdate fu = fused ? *fused : BhFusedUpdate{nullptr, nullptr, nullptr, nullptr, nullptr, 0.f, 0.f};
     if (!src_posm) src_posm = posm;
     if (!tree_sc) tree_sc = sc;
     if (accumulate) {
@@ -630,7 +663,7 @@ int bh_force_launch(const float4* posm, const void* keys, int levels, const int3
     int64_t grid = (int64_t)(num_sms > 0 ? num_sms : BH_NUM_SMS_FALLBACK) * max_ctas;  // persistent: fill the chip once
     if (grid > want) grid = want;
 #define BH_FORCE(L, Q, KT) force_kernel<L, Q><<<(int)grid, FORCE_THREADS, 0, st>>>(posm, (const KT*)keys, ids, first_body, body_count, cell_meta, \
-        cell_com, kid_src, kid_info, acc, sc, heavy_list, heavy_flag, max_chunks, theta, softening, G, split_alpha, src_posm, tree_sc, accumulate, cell_quad, kid_quad)
+        cell_com, kid_src, kid_info, acc, sc, heavy_list, heavy_flag, max_chunks, theta, softening, G, split_alpha, src_posm, tree_sc, accumulate, cell_quad, kid_quad, fu)
     if (levels == 20) { if (quad) BH_FORCE(20, true, uint64_t); else BH_FORCE(20, false, uint64_t); }
     else { if (quad) BH_FORCE(10, true, uint32_t); else BH_FORCE(10, false, uint32_t); }
 #undef BH_FORCE
