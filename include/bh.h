@@ -76,7 +76,7 @@ const char* bh_error_string(int code);
 
 /* Replaces the 16 cudaMalloc calls + H2D copies of main()
  * (nbody_v5_bench.cu:311-335): allocates every buffer once for n_max bodies
- * (~400 B/body, +340 B/body with BH_FLAG_QUADRUPOLE; 0 < n_max < 2^28: the
+ * (~370 B/body, +300 B/body with BH_FLAG_QUADRUPOLE; 0 < n_max < 2^28: the
  * traversal's stack words are cell id << 3 plus a flag bit).               */
 int  bh_create(bh_ctx** out, int64_t n_max, const bh_params* params, int device);
 /* Replaces nbody_v5_bench.cu:372-387. */

@@ -357,22 +357,26 @@ __global__ void __launch_bounds__(TB) link_kernel(const typename BhKey<LEVELS>::
     }
 }
 
-// ---- centre of mass: prefix sums over the sorted bodies ------------------------------------------
+// ---- centre of mass: sums over contiguous ranges of the sorted bodies -----------------------------
 // A cell is a contiguous range [first, first + count) of the Morton-sorted bodies (that is what the construction
-// above emits), so its moments are a DIFFERENCE OF PREFIX SUMS of {m, m x, m y, m z} — no walk up the tree, no
-// arrival counters, no float atomics (bench:158-189 adds 4 N floats per level with atomicAdd, which also makes the
-// reference's sums depend on the schedule).  Three flat kernels:
-//   com_scan_kernel   per block of 4,096 bodies: exclusive LOCAL prefix (restarts at 0 in every block) + block total;
+// above emits), so its moments {m, m x, m y, m z} need no walk up the tree, no arrival counters, no float atomics
+// (bench:158-189 adds 4 N floats per level with atomicAdd, which also makes the reference's sums depend on the
+// schedule).  A cell of at most DIRECT_MAX bodies — most cells — adds its bodies up directly, in order.  A larger
+// cell takes a DIFFERENCE OF PREFIX SUMS.  Three flat kernels:
+//   com_scan_kernel   per block of 4,096 bodies: the exclusive LOCAL prefix (restarts at 0 in every block) at the
+//                     start of every run of 16 bodies + the block total — 2 B/body written, not 32;
 //   com_base_kernel   exclusive prefix of the block totals (one CTA);
-//   com_cells_kernel  one thread per cell: moments = (base[b2] - base[b1]) + (local[e] - local[first]), centre of
-//                     mass as bench:181-186, and the cell's entries in the dense traversal lines.
-// Sums are double: m x is exact in double (24 x 24 bits), a small cell lies inside one block, so its difference
-// involves at most 4,096 terms and is far more accurate than any float32 summation order.  Every addition happens
-// in a fixed order (16 bodies per thread in sequence, Hillis-Steele across a warp, warps / chunks in sequence), which
-// oracle/bh_oracle.cpp:orc_tree_com reproduces operation for operation: the results are equal bit for bit.
+//   com_cells_kernel  one thread per cell: direct sum, or (base[b2] - base[b1]) + (P(end) - P(first)) with
+//                     P(i) = run prefix + the (< 16) bodies of the run before i, added in order; then the centre of
+//                     mass as bench:181-186 and the cell's entries in the dense traversal lines.
+// Sums are double: m x is exact in double (24 x 24 bits); a direct sum of <= 16 such terms and a difference of
+// block-local prefixes of <= 4,096 terms are both far more accurate than any float32 summation order.  Every
+// addition happens in a fixed order (16 bodies per thread in sequence, Hillis-Steele across a warp, warps / chunks
+// in sequence), which oracle/bh_oracle.cpp:orc_tree_com reproduces operation for operation: equal bit for bit.
 constexpr int CPT = 16;           // consecutive bodies per thread (summed in sequence)
 constexpr int CT = 256;           // threads per scan block
 constexpr int CB = CT * CPT;      // 4,096 bodies per scan block
+constexpr int DIRECT_MAX = 16;    // cells up to this many bodies are summed directly
 
 struct __align__(32) D4 { double m, x, y, z; };
 
@@ -424,26 +428,38 @@ __device__ __forceinline__ D4 d4_block_exclusive(const D4 v, D4* s_w /*NW*/, D4&
     return d4_add(before, prev);
 }
 
-__global__ void __launch_bounds__(CT) com_scan_kernel(const float4* __restrict__ posm, int n, D4* __restrict__ local,
+__global__ void __launch_bounds__(CT) com_scan_kernel(const float4* __restrict__ posm, int n, D4* __restrict__ runpre,
                                                      D4* __restrict__ totals) {
     __shared__ D4 s_w[CT / 32];
     const int i0 = blockIdx.x * CB + threadIdx.x * CPT;
-    D4 sum = d4_zero();   // this thread's bodies, in sequence
+    D4 sum = d4_zero();   // this thread's run of bodies, in sequence
 #pragma unroll 4
     for (int k = 0; k < CPT; ++k)
         if (i0 + k < n) sum = d4_add(sum, d4_term(__ldg(posm + i0 + k)));
     D4 total;
     const D4 pre = d4_block_exclusive<CT / 32>(sum, s_w, total);
-    // local[i] = sum of the bodies of this block before i; entry n (one past the last body) is written too.
-    // Second read of the thread's 256 bytes (L1/L2) instead of 16 live partial sums in registers.
-    D4 run = pre;
-#pragma unroll 4
-    for (int k = 0; k < CPT; ++k) {
-        if (i0 + k <= n) local[i0 + k] = run;
-        if (i0 + k < n) run = d4_add(run, d4_term(__ldg(posm + i0 + k)));
-    }
+    // runpre[r] = sum of the bodies of this block before run r; the run that starts at n (one past the last body) too
+    if (i0 <= n) runpre[i0 / CPT] = pre;
     if (threadIdx.x == 0) totals[blockIdx.x] = total;
-    if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1 && (blockIdx.x + 1) * CB == n) local[n] = d4_zero();   // n on a block boundary
+    if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1 && (blockIdx.x + 1) * CB == n) runpre[n / CPT] = d4_zero();   // n on a block boundary
+}
+
+// P(i): local prefix at body i = its run's prefix + the bodies of the run before i, in order
+__device__ __forceinline__ D4 d4_prefix_at(const float4* __restrict__ posm, const D4* __restrict__ runpre, int i) {
+    const int r0 = (i / CPT) * CPT;
+    D4 v = runpre[i / CPT];
+    for (int k = r0; k < i; ++k) v = d4_add(v, d4_term(__ldg(posm + k)));
+    return v;
+}
+// moments of the bodies [first, end)
+__device__ __forceinline__ D4 d4_range_sum(const float4* __restrict__ posm, const D4* __restrict__ runpre,
+                                           const D4* __restrict__ base, int first, int end) {
+    if (end - first <= DIRECT_MAX) {
+        D4 v = d4_zero();
+        for (int k = first; k < end; ++k) v = d4_add(v, d4_term(__ldg(posm + k)));
+        return v;
+    }
+    return d4_add(d4_sub(base[end / CB], base[first / CB]), d4_sub(d4_prefix_at(posm, runpre, end), d4_prefix_at(posm, runpre, first)));
 }
 
 __global__ void __launch_bounds__(1024) com_base_kernel(const D4* __restrict__ totals, int nblocks, D4* __restrict__ base) {
@@ -510,7 +526,7 @@ __device__ __forceinline__ void cube_centre(const BhDevScalars* sc, double& ox, 
 }
 
 __global__ void __launch_bounds__(CT) quad_scan_kernel(const float4* __restrict__ posm, int n, const BhDevScalars* __restrict__ sc,
-                                                      D6* __restrict__ local, D6* __restrict__ totals) {
+                                                      D6* __restrict__ runpre, D6* __restrict__ totals) {
     __shared__ D6 s_w[CT / 32];
     double ox, oy, oz;
     cube_centre(sc, ox, oy, oz);
@@ -520,14 +536,28 @@ __global__ void __launch_bounds__(CT) quad_scan_kernel(const float4* __restrict_
     for (int k = 0; k < CPT; ++k)
         if (i0 + k < n) sum = d6_add(sum, d6_term(__ldg(posm + i0 + k), ox, oy, oz));
     D6 total;
-    D6 run = d6_block_exclusive<CT / 32>(sum, s_w, total);
-#pragma unroll 2
-    for (int k = 0; k < CPT; ++k) {
-        if (i0 + k <= n) local[i0 + k] = run;
-        if (i0 + k < n) run = d6_add(run, d6_term(__ldg(posm + i0 + k), ox, oy, oz));
-    }
+    const D6 pre = d6_block_exclusive<CT / 32>(sum, s_w, total);
+    if (i0 <= n) runpre[i0 / CPT] = pre;
     if (threadIdx.x == 0) totals[blockIdx.x] = total;
-    if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1 && (blockIdx.x + 1) * CB == n) local[n] = d6_zero();
+    if (threadIdx.x == 0 && blockIdx.x == gridDim.x - 1 && (blockIdx.x + 1) * CB == n) runpre[n / CPT] = d6_zero();
+}
+
+__device__ __forceinline__ D6 d6_prefix_at(const float4* __restrict__ posm, const D6* __restrict__ runpre, int i, double ox,
+                                           double oy, double oz) {
+    const int r0 = (i / CPT) * CPT;
+    D6 v = runpre[i / CPT];
+    for (int k = r0; k < i; ++k) v = d6_add(v, d6_term(__ldg(posm + k), ox, oy, oz));
+    return v;
+}
+__device__ __forceinline__ D6 d6_range_sum(const float4* __restrict__ posm, const D6* __restrict__ runpre,
+                                           const D6* __restrict__ base, int first, int end, double ox, double oy, double oz) {
+    if (end - first <= DIRECT_MAX) {
+        D6 v = d6_zero();
+        for (int k = first; k < end; ++k) v = d6_add(v, d6_term(__ldg(posm + k), ox, oy, oz));
+        return v;
+    }
+    return d6_add(d6_sub(base[end / CB], base[first / CB]),
+                  d6_sub(d6_prefix_at(posm, runpre, end, ox, oy, oz), d6_prefix_at(posm, runpre, first, ox, oy, oz)));
 }
 
 __global__ void __launch_bounds__(1024) quad_base_kernel(const D6* __restrict__ totals, int nblocks, D6* __restrict__ base) {
@@ -571,7 +601,7 @@ __global__ void __launch_bounds__(TB) com_cells_kernel(const float4* __restrict_
     for (int c = blockIdx.x * TB + threadIdx.x; c < M; c += gridDim.x * TB) {
         const int4 mt = __ldg(cell_meta + c);
         const int first = mt.x, end = mt.x + mt.y;
-        const D4 s = d4_add(d4_sub(base[end / CB], base[first / CB]), d4_sub(local[end], local[first]));
+        const D4 s = d4_range_sum(posm, local, base, first, end);
         const float m = (float)s.m, sx = (float)s.x, sy = (float)s.y, sz = (float)s.z;
         const float inv = (m > 1e-6f) ? __fdiv_rn(1.0f, m) : 0.0f;   // bench:181-183
         const float4 cm = make_float4(__fmul_rn(sx, inv), __fmul_rn(sy, inv), __fmul_rn(sz, inv), m);
@@ -582,7 +612,7 @@ __global__ void __launch_bounds__(TB) com_cells_kernel(const float4* __restrict_
             // to 1e-16, the quantities differ by ~1e-4 at worst), then the traceless form Q = 3 P - tr(P) I
             double ox, oy, oz;
             cube_centre(sc, ox, oy, oz);
-            const D6 s2 = d6_add(d6_sub(qa.base2[end / CB], qa.base2[first / CB]), d6_sub(qa.local2[end], qa.local2[first]));
+            const D6 s2 = d6_range_sum(posm, qa.local2, qa.base2, first, end, ox, oy, oz);
             const double M = s.m, im = M > 0.0 ? 1.0 / M : 0.0;
             const double cx = s.x * im - ox, cy = s.y * im - oy, cz = s.z * im - oz;
             const double pxx = s2.v[0] - M * cx * cx, pxy = s2.v[1] - M * cx * cy, pxz = s2.v[2] - M * cx * cz;
@@ -658,15 +688,16 @@ int bh_tree_launch(const void* keys, int levels, int64_t n64, int2* pair_info, i
     return (int)cudaGetLastError();
 }
 
-// com_scratch: 32-byte aligned, bh_com_scratch_bytes(n) bytes — local prefixes (n + 1), block totals, block bases
+// com_scratch: 32-byte aligned, bh_com_scratch_bytes(n) bytes — run prefixes (n / 16 + 2), block totals, block bases
+static inline size_t com_runs(int64_t n) { return (size_t)(n / CPT) + 2; }
 size_t bh_com_scratch_bytes(int64_t n) {
     const size_t nblocks = (size_t)((n + CB - 1) / CB) + 1;
-    return sizeof(D4) * ((size_t)n + 1 + 2 * nblocks + 4);
+    return sizeof(D4) * (com_runs(n) + 2 * nblocks + 4);
 }
 // the same for the six second moments of the quadrupole option
 size_t bh_quad_scratch_bytes(int64_t n) {
     const size_t nblocks = (size_t)((n + CB - 1) / CB) + 1;
-    return sizeof(D6) * ((size_t)n + 1 + 2 * nblocks + 4);
+    return sizeof(D6) * (com_runs(n) + 2 * nblocks + 4);
 }
 
 // The prefix sums need the sorted bodies only: they can run beside the tree construction (bh_com_prefix_launch on
@@ -677,13 +708,13 @@ int bh_com_prefix_launch(const float4* posm, int64_t n64, void* com_scratch, voi
     if (n < 2) return 0;
     const int nblocks = (n + CB - 1) / CB;
     D4* local = reinterpret_cast<D4*>(com_scratch);
-    D4* totals = local + (size_t)n + 1;
+    D4* totals = local + com_runs(n);
     D4* base = totals + nblocks + 1;
     com_scan_kernel<<<nblocks, CT, 0, st>>>(posm, n, local, totals);
     com_base_kernel<<<1, 1024, 0, st>>>(totals, nblocks, base);
     if (quad_scratch) {
         D6* local2 = reinterpret_cast<D6*>(quad_scratch);
-        D6* totals2 = local2 + (size_t)n + 1;
+        D6* totals2 = local2 + com_runs(n);
         D6* base2 = totals2 + nblocks + 1;
         quad_scan_kernel<<<nblocks, CT, 0, st>>>(posm, n, sc, local2, totals2);
         quad_base_kernel<<<1, 1024, 0, st>>>(totals2, nblocks, base2);
@@ -698,11 +729,11 @@ int bh_com_cells_launch(const float4* posm, int64_t n64, const int4* cell_meta, 
     if (n < 2) return 0;
     const int nblocks = (n + CB - 1) / CB;
     const D4* local = reinterpret_cast<const D4*>(com_scratch);
-    const D4* base = local + (size_t)n + 1 + nblocks + 1;
+    const D4* base = local + com_runs(n) + nblocks + 1;
     QuadArgs qa{nullptr, nullptr, cell_quad, kid_quad};
     if (quad_scratch) {
         qa.local2 = reinterpret_cast<const D6*>(quad_scratch);
-        qa.base2 = qa.local2 + (size_t)n + 1 + nblocks + 1;
+        qa.base2 = qa.local2 + com_runs(n) + nblocks + 1;
         com_cells_kernel<true><<<capped_grid(n, TB), TB, 0, st>>>(posm, cell_meta, cell_child, local, base, cell_com, kid_src, kid_info, sc, qa);
     } else {
         com_cells_kernel<false><<<capped_grid(n, TB), TB, 0, st>>>(posm, cell_meta, cell_child, local, base, cell_com, kid_src, kid_info, sc, qa);

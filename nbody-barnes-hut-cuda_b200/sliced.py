@@ -26,6 +26,10 @@ from .engine import lib as _lib
 GROUP = int(_lib().bh_group_size())   # bodies per traversal chunk (BH_GROUP in csrc/bh_common.cuh)
 
 
+# kernels of one sliced step of one rank: the three-part step (2 keys + 6 sort, reorder of positions + 5 build + 3 centre of
+# mass + 2 force, reorder of the rest + update = 21) + the cube re-reduction over the gathered positions (2)
+SLICED_LAUNCHES_PER_STEP = 23
+
 def slice_bounds(n: int, rank: int, world: int):
     """Mirror of default_slice() in csrc/bh_engine.cu: (first, count, padded_per_rank)."""
     groups = (n + GROUP - 1) // GROUP
@@ -240,7 +244,7 @@ def run_sliced_bench(args, w, bh, dist, rank, world, local):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": bench.workload_config(args, w),
-        "engine": {"group": 32, "key_bits": 30, "launches_per_step": bench.LAUNCHES_PER_STEP + 4,
+        "engine": {"group": 32, "key_bits": 30, "launches_per_step": SLICED_LAUNCHES_PER_STEP,
                    "parallelism": f"morton-slices x{world}: replicated sort+tree, sliced traversal, in-place NCCL all-gather of 36 B/body",
                    "driver": "bh_mg_step (C++/NCCL behind the C ABI, csrc/bh_mg.cu); torch.distributed carries the NCCL id and reduces the timings",
                    "l2": "state far larger than L2 (>= 5 GB context at 16M bodies); no flush between steps"},
@@ -251,7 +255,7 @@ def run_sliced_bench(args, w, bh, dist, rank, world, local):
         "phase_ms_rank0": {k: round(v, 4) for k, v in acc.items()}, "force_ms_per_rank": force_per_rank,
         "allgather_ms": allgather_ms,
         "cells": cells, "e2e": e2e, "roofline": roofline,
-        "gpu_launches": (bench.LAUNCHES_PER_STEP + 4) * args.steps * world, "clocks": ck,
+        "gpu_launches": SLICED_LAUNCHES_PER_STEP * args.steps * world, "clocks": ck,
     }
     dist.destroy_process_group()
     return line if rank == 0 else None

@@ -493,12 +493,14 @@ int orc_tree_build64(const uint64_t* sorted_keys, int64_t n64, int levels, int32
     return M;
 }
 
-// Centre of mass from prefix sums (engine: bh_tree.cu "centre of mass").  A cell is a contiguous range of the
-// sorted bodies, so its moments {m, m x, m y, m z} are a difference of prefix sums, taken in double (m x is exact
-// in double).  The reference adds the same terms up the parent chain with float atomics in schedule order
-// (bench:158-176); any order is "the reference's", this one is fixed and more accurate than all of them.
+// Centre of mass (engine: bh_tree.cu "centre of mass").  A cell is a contiguous range of the sorted bodies.  Its
+// moments {m, m x, m y, m z} are taken in double (m x is exact in double): a cell of at most 16 bodies adds its
+// bodies up directly, in order; a larger one takes a difference of prefix sums.  The reference adds the same terms
+// up the parent chain with float atomics in schedule order (bench:158-176); any order is "the reference's", this
+// one is fixed and more accurate than all of them.
 // The order of every addition mirrors the kernels: blocks of 4,096 bodies; 16 consecutive bodies per thread in
-// sequence; Hillis-Steele across the 32 lanes of a warp; warps, and chunks of 1,024 block totals, in sequence.
+// sequence (a "run"); Hillis-Steele across the 32 lanes of a warp; warps, and chunks of 1,024 block totals, in
+// sequence; the prefix at a body = its run's prefix + the bodies of the run before it, in order.
 // com = moment * (1/m) on the float-rounded sums as bench:181-186 (m > 1e-6f guard).
 namespace {
 struct D4 { double m, x, y, z; };
@@ -532,8 +534,9 @@ extern "C" void orc_tree_com(const float* posm, int64_t n64, const int32_t* meta
     const int M = (int)M64, n = (int)n64;
     if (M == 0 || root < 0) return;
     constexpr int CT = 256, CPT = 16, CB = CT * CPT;   // 4,096 bodies per block, 16 consecutive bodies per thread
+    constexpr int DIRECT_MAX = 16;                      // cells up to this many bodies: direct sum
     const int nblocks = (n + CB - 1) / CB;
-    std::vector<D4> local((size_t)n + 1, kZero), totals((size_t)nblocks, kZero), base((size_t)nblocks + 1, kZero);
+    std::vector<D4> runpre((size_t)n / CPT + 2, kZero), totals((size_t)nblocks, kZero), base((size_t)nblocks + 1, kZero);
     auto term = [&](int i) {
         const float* q = posm + 4 * (int64_t)i;
         const double m = (double)q[3];
@@ -553,15 +556,11 @@ extern "C" void orc_tree_com(const float* posm, int64_t n64, const int32_t* meta
         block_exclusive(v, CT / 32, pre, total);
         for (int t = 0; t < CT; ++t) {
             const int i0 = b * CB + CPT * t;
-            D4 run = pre[t];
-            for (int k = 0; k < CPT; ++k) {
-                if (i0 + k <= n) local[i0 + k] = run;
-                if (i0 + k < n) run = d4_add(run, term(i0 + k));
-            }
+            if (i0 <= n) runpre[i0 / CPT] = pre[t];
         }
         totals[b] = total;
     }
-    if (nblocks * CB == n) local[n] = kZero;
+    if (nblocks * CB == n) runpre[n / CPT] = kZero;
     D4 carry = kZero;
     for (int c0 = 0; c0 < nblocks; c0 += 1024) {
         D4 v[1024], pre[1024], total;
@@ -571,11 +570,21 @@ extern "C" void orc_tree_com(const float* posm, int64_t n64, const int32_t* meta
         carry = d4_add(carry, total);
     }
     base[nblocks] = carry;
+    auto prefix_at = [&](int i) {   // d4_prefix_at in bh_tree.cu
+        D4 v = runpre[i / CPT];
+        for (int k = (i / CPT) * CPT; k < i; ++k) v = d4_add(v, term(k));
+        return v;
+    };
 #pragma omp parallel for schedule(static)
     for (int c = 0; c < M; ++c) {
         const int32_t* mt = meta + 4 * (int64_t)c;
         const int first = mt[0], end = mt[0] + mt[1];
-        const D4 s = d4_add(d4_sub(base[end / CB], base[first / CB]), d4_sub(local[end], local[first]));
+        D4 s = kZero;
+        if (end - first <= DIRECT_MAX) {
+            for (int k = first; k < end; ++k) s = d4_add(s, term(k));
+        } else {
+            s = d4_add(d4_sub(base[end / CB], base[first / CB]), d4_sub(prefix_at(end), prefix_at(first)));
+        }
         const float m = (float)s.m, sx = (float)s.x, sy = (float)s.y, sz = (float)s.z;
         float* o = mom + 4 * (int64_t)c;
         o[0] = sx; o[1] = sy; o[2] = sz; o[3] = m;
