@@ -277,7 +277,10 @@ __global__ void __launch_bounds__(SORT_THREADS, BH_SORT_MIN_CTAS) onesweep_kerne
             // interleaved: the statuses of tiles p, p-1, ... are fetched together (independent loads) and
             // consumed in order.  The chain of dependent L2 round trips, which bounds the first wave when
             // hundreds of tiles start together, shrinks by the same factor.
-            constexpr int LB_WIDE = DPT == 1 ? 8 : 4;
+#ifndef BH_SORT_LB_WIDE
+#define BH_SORT_LB_WIDE 8
+#endif
+            constexpr int LB_WIDE = DPT == 1 ? BH_SORT_LB_WIDE : 4;
             int p[DPT];
             bool done[DPT];
 #pragma unroll
