@@ -565,11 +565,11 @@ def _morton30_numpy(px, py, pz, cube):
 
 def launches_per_let_step(key_bits: int) -> int:
     """This library's kernel launches in one LET step of one rank that received imports (torch's and NCCL's own
-    kernels not counted): bounds 3, coarse election sort 8, local tree (keys, sort, reorder, tree 5, com), domain
+    kernels not counted): bounds 3, coarse election sort 8, local tree (keys, sort, reorder, tree 5, centre of mass 3), domain
     boxes 3, export walk (seed + one per level), force 2, ghost tree, cross-tree force 2, update 1, compaction 3."""
     levels = key_bits // 3
     sort = 6 if key_bits == 30 else 14        # histogram + scan + 4 passes; twice + gather + combine for 60 bits
-    tree = 1 + sort + 1 + 5 + 1
+    tree = 1 + sort + 1 + 5 + 3
     return 3 + 8 + tree + 3 + (1 + levels + 1) + 2 + tree + 2 + 1 + 3
 
 

@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 f = np.float32
 
 CASES = [("uniform", 2), ("uniform", 33), ("uniform", 16384), ("disk", 50001), ("clustered", 20000), ("coincident", 500),
-         ("lattice", 4096), ("plummer", 30000), ("line", 20000), ("bigbucket", 12000)]
+         ("lattice", 4096), ("plummer", 30000), ("line", 20000), ("bigbucket", 12000),
+         ("uniform", 2049), ("coincident", 5000), ("line", 4099)]   # around / across the 2,048-pair tiles of the tree build
 
 
 @pytest.mark.parametrize("kind,n", CASES)

@@ -48,7 +48,10 @@ def make_case(bh, kind, n, seed=1):
 
 CASES = [("uniform", 2), ("uniform", 3), ("uniform", 31), ("uniform", 33), ("uniform", 1000), ("uniform", 16384),
          ("disk", 50001), ("clustered", 20000), ("coincident", 500), ("lattice", 4096), ("plummer", 30000),
-         ("line", 20000), ("bigbucket", 12000), ("tracers", 9000)]
+         ("line", 20000), ("bigbucket", 12000), ("tracers", 9000),
+         # the tree build answers range questions per tile of 2,048 key pairs: sizes around the tile edge, buckets and
+         # chains that cross it
+         ("uniform", 2048), ("uniform", 2049), ("uniform", 2050), ("coincident", 5000), ("lattice", 4097), ("line", 4099)]
 
 
 @pytest.mark.parametrize("kind,n", CASES)
