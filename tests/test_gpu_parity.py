@@ -184,6 +184,45 @@ def test_step_host_equals_load_step_read(bh):
             assert arrs[k].tobytes() == a[k].tobytes()
 
 
+def test_repeated_host_steps_equal_one_run(bh):
+    """Call after call on the same system (bh_step_host keeps the chunk-cost record between calls: a scheduling hint,
+    it must never change a result) == the same number of steps in one go; a call with another n in between drops it."""
+    n = 20000
+    soa = make_case(bh, "uniform", n)   # no two bodies share a key: the order within the sort does not depend on the import order
+    with bh.BHEngine(n) as eng:
+        eng.load_soa(*soa)
+        eng.simulation_step(4)
+        want = eng.read_soa(want_acc=False)
+    with bh.BHEngine(n) as eng:
+        arrs = [x.copy() for x in soa]
+        eng.step_host(*arrs, nsteps=1)
+        eng.step_host(*arrs, nsteps=1)
+        small = [x[:777].copy() for x in make_case(bh, "uniform", 1000)]
+        eng.step_host(*small, nsteps=1)              # a different system through the same context
+        eng.step_host(*arrs, nsteps=2)
+        eng.check_device_error()
+        for k in range(6):
+            assert arrs[k].tobytes() == want[k].tobytes()
+
+
+def test_update_fused_into_the_traversal_equals_the_separate_kernel(bh, monkeypatch):
+    """bh_step's whole-step path integrates a chunk inside force_kernel; BH_NO_FUSED_UPDATE=1 (read at creation) keeps
+    integrate_kernel as a launch of its own.  Same arithmetic: states and the next step's cube must agree bit for bit."""
+    n = 30000
+    soa = make_case(bh, "plummer", n)
+    outs = []
+    for env in ("0", "1"):
+        monkeypatch.setenv("BH_NO_FUSED_UPDATE", env)
+        with bh.BHEngine(n) as eng:
+            eng.load_soa(*soa)
+            eng.simulation_step(5)
+            eng.check_device_error()
+            outs.append((eng.debug_get(bh.DBG.POSM).tobytes(), eng.debug_get(bh.DBG.VEL).tobytes(),
+                         eng.debug_get(bh.DBG.IDS).tobytes(), eng.debug_get(bh.DBG.ACC).tobytes(),
+                         eng.debug_get(bh.DBG.BOUNDS).tobytes()))
+    assert outs[0] == outs[1]
+
+
 def test_phase_timer_reports_every_phase(bh):
     n = 100000
     soa = make_case(bh, "disk", n)
