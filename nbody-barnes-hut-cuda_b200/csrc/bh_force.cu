@@ -139,9 +139,13 @@ struct Accum { f32x2 x, y, z; };
 #define EVAL_ILP_N 4
 #endif
 constexpr int EVAL_ILP = EVAL_ILP_N;
+#ifndef EVAL_K_UNROLL
+#define EVAL_K_UNROLL 4
+#endif
+constexpr int EVAL_KU = EVAL_K_UNROLL;   // copies of the 8-source step per loop trip (1 = a loop of four trips per tile)
 __device__ __forceinline__ void eval_tile(const SrcPair* __restrict__ src, f32x2 npx, f32x2 npy, f32x2 npz,
                                           f32x2 soft2, Accum& a) {
-#pragma unroll 1
+#pragma unroll EVAL_KU
     for (int k = 0; k < 16; k += EVAL_ILP) {
         f32x2 dx[EVAL_ILP], dy[EVAL_ILP], dz[EVAL_ILP], r[EVAL_ILP], m[EVAL_ILP];
 #pragma unroll
