@@ -115,7 +115,13 @@ int  bh_export_soa_host(bh_ctx* ctx,
                         float* ax, float* ay, float* az);
 
 /* End-to-end convenience used by bench.py's `e2e` leg: host SoA in, nsteps
- * steps, host SoA out (positions+velocities), all copies inside the call.  */
+ * steps, host SoA out (positions+velocities), all copies inside the call
+ * (uploads in order of need, the step in three parts behind them, the
+ * export as a gather whose position half downloads first).  Calling it
+ * step after step with the arrays it returned is the intended use: the
+ * context then keeps its record of which traversal chunks were expensive
+ * (a scheduling hint only; dropped when n changes — results never depend
+ * on it).  Equivalent to bh_import_soa_host + bh_step + bh_export_soa_host. */
 int  bh_step_host(bh_ctx* ctx,
                   float* px, float* py, float* pz,
                   float* vx, float* vy, float* vz,
