@@ -186,6 +186,42 @@ def test_com_matches_double_precision_sums():
         assert np.abs(com[c, :3] - want).max() < 1e-2 * (1 + np.abs(want).max()) * 1e-2
 
 
+def test_com_of_every_cell_is_the_rounded_exact_sum():
+    """Direct sums for cells of <= 16 bodies, differences of block-local run prefixes above that (bh_tree.cu
+    d4_range_sum / orc_tree_com): over several 4,096-body blocks, with cells that start or end on block and run
+    boundaries, every cell's mass and moments must be the float rounding of the exact sums (double accumulation of
+    exact products: a few 1e-16 off at most, i.e. the same float except on a rounding tie)."""
+    n = 70_001
+    soa = _random_soa(n, 11, clustered=True)
+    posm, vel, ids = O.soa_to_internal(soa)
+    b = O.bounds(*soa[:3])
+    keys, idx = O.morton_keys(*soa[:3], b)
+    ks, perm = O.stable_sort(keys, idx)
+    ps = posm[perm]
+    meta, child, root = O.tree_build(ks)
+    mom, com = O.tree_com(ps, meta, child, root)
+    p64 = ps.astype(np.longdouble)
+    cm = np.concatenate([[0], np.cumsum(p64[:, 3])])
+    cx = np.concatenate([np.zeros((1, 3), np.longdouble), np.cumsum(p64[:, :3] * p64[:, 3:4], axis=0)])
+    first, end = meta[:, 0].astype(np.int64), (meta[:, 0] + meta[:, 1]).astype(np.int64)
+    want_m = (cm[end] - cm[first]).astype(np.float64)
+    want_x = (cx[end] - cx[first]).astype(np.float64)
+    sizes = meta[:, 1]
+    assert (sizes <= 16).any() and (sizes > 16).any() and (sizes > 4096).any()        # all three routes are exercised
+    big = sizes > 16
+    assert ((first[big] % 16 == 0).any() or (end[big] % 16 == 0).any()) and (first[big] // 4096 != (end[big] - 1) // 4096).any()   # run edges, cells across blocks
+    ulp_m = np.abs(mom[:, 3].astype(np.float64) - want_m) / np.spacing(want_m.astype(np.float32)).astype(np.float64)
+    assert ulp_m.max() <= 1.0
+    scale = np.maximum(np.abs(want_x), 1e-30)
+    ulp_x = np.abs(mom[:, :3].astype(np.float64) - want_x) / np.spacing(scale.astype(np.float32)).astype(np.float64)
+    # a moment is a sum of signed terms: cancellation can leave the double sum a few float ulps of the RESULT off
+    # only when the terms are far larger than the result; bound it by the ulp of the largest partial magnitude instead
+    absx = np.concatenate([np.zeros((1, 3), np.longdouble), np.cumsum(np.abs(p64[:, :3] * p64[:, 3:4]), axis=0)])
+    mag = (absx[end] - absx[first]).astype(np.float64)
+    assert (np.abs(mom[:, :3].astype(np.float64) - want_x) <= 0.5 * np.spacing(scale.astype(np.float32)) + 1e-13 * mag).all()
+    assert np.median(ulp_x) <= 0.5
+
+
 def test_group_mac_is_conservative_and_more_accurate():
     # every body of a group accepts whatever the group accepts -> error no larger than per-body MAC
     soa = _random_soa(6000, 11)
